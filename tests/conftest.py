@@ -1,0 +1,37 @@
+import pathlib
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+for p in (ROOT, ROOT / "oracle"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+
+GOLDEN = ROOT / "tests" / "golden"
+VARIANTS = ("cu", "v2", "da")
+ORDER = {"cu": "jacobi", "v2": "gs", "da": "gs"}
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")
+
+
+def load_golden(case: str, tag: str):
+    z = np.load(GOLDEN / f"{case}_{tag}.npz")
+    return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(params=[(c, t) for c in ("tiny", "small") for t in VARIANTS], ids=lambda p: f"{p[0]}-{p[1]}")
+def golden(request):
+    case, tag = request.param
+    g = load_golden(case, tag)
+    g["case"], g["tag"], g["order"] = case, tag, ORDER[tag]
+    return g
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
