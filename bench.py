@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- edges/sec of the K-layer credibility-weighted LightGCN training step on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--impl ours|reference]
+
+A "step" is one full training step of the reference loop (lightgcn_cu.py:608-654 /
+Version-2/lighgcn_cu_pop.py:826-866) on one batch of 4096 users: on-device triple sampling,
+K-layer forward, fused BPR+L2 loss, adjoint propagation, dense Adam.  metric = train edges / step time.
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for every key.
+"""
+import argparse
+import json
+import os
+import pathlib
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "edges/sec (3-layer cred-weighted LightGCN fwd+bwd)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4"])
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    return ap.parse_args()
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        j = json.loads(p.read_text())
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(U, I, E, d, K):
+    """Gather model of SURVEY.md section 8d, fwd+bwd: r = 4d bytes per row; one SpMM moves E(4+4+r) + n_dst r;
+    a layer adds the running-sum epilogue 2(U+I)r."""
+    r = 4 * d
+    fwd = K * (2 * E * (8 + r) + (U + I) * r) + 2 * K * (U + I) * r
+    return 2 * fwd
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.stop_flag, self.index = [], threading.Event(), index
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_flag.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(name):
+    from credgcn import synth
+    t0 = time.time()
+    sg = synth.make_graph(name)
+    shp = synth.SHAPES[name]
+    return sg, shp, time.time() - t0
+
+
+def cpu_baseline(sg, shp, e0_u, e0_i, batches, steps, reg, edge_fraction=1.0):
+    """The reference's CPU execution strategy (COO torch.sparse.mm + autograd + Adam), timed on this
+    box's host cores via the oracle port.  Returns (edges_per_s, ms_per_step, cores, sample_text)."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import credgcn_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    edges = sg.train_edges
+    if edge_fraction < 1.0:
+        keep = np.random.default_rng(0).random(edges.shape[1]) < edge_fraction
+        edges = edges[:, keep]
+    ops = orc.Operators(edges, sg.num_users, sg.num_items, sg.cred, shp["variant"])
+    base = orc.TorchCpuBaseline(ops, e0_u, e0_i, shp["num_layers"], shp["order"])
+    ts = []
+    for s in range(steps + 1):
+        u, p, n = batches[s % len(batches)]
+        t0 = time.perf_counter()
+        base.step(u, p, n, reg)
+        ts.append(time.perf_counter() - t0)
+    ts = ts[1:] if len(ts) > 1 else ts            # first step pays allocator/first-touch costs
+    ms = 1e3 * float(np.mean(ts))
+    E = edges.shape[1]
+    sample = (f"{len(ts)} full training steps (fwd+loss+bwd+Adam) of workload {sg.name} on "
+              f"{E:,} train edges" + (f" (a {edge_fraction:.3f} edge subsample)" if edge_fraction < 1 else "")
+              + ", torch CPU sparse COO path, oracle port")
+    return E / (ms / 1e3), ms, torch.get_num_threads(), sample
+
+
+def host_triples(sg, batches_users, seed=11):
+    """(users, pos, neg) lists for the CPU arm: pos from the user's row, neg uniform (rejection skipped --
+    it does not change the arithmetic being timed)."""
+    from credgcn import synth  # noqa: F401
+    rng = np.random.default_rng(seed)
+    u_all, i_all = sg.train_edges[0].astype(np.int64), sg.train_edges[1].astype(np.int64)
+    order = np.argsort(u_all, kind="stable")
+    indptr = np.zeros(sg.num_users + 1, np.int64)
+    np.cumsum(np.bincount(u_all, minlength=sg.num_users), out=indptr[1:])
+    items = i_all[order]
+    out = []
+    for users in batches_users:
+        deg = indptr[users + 1] - indptr[users]
+        pos = items[indptr[users] + (rng.random(users.size) * deg).astype(np.int64)]
+        neg = rng.integers(0, sg.num_items, size=users.size)
+        out.append((users, pos, neg))
+    return out
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port) on the same config/metric/unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sg, shp, _ = make_workload(args.workload)
+    torch.manual_seed(42)
+    e0_u = torch.nn.init.xavier_uniform_(torch.empty(sg.num_users, shp["emb_dim"])).numpy()
+    e0_i = torch.nn.init.xavier_uniform_(torch.empty(sg.num_items, shp["emb_dim"])).numpy()
+    train_users = np.flatnonzero(np.bincount(sg.train_edges[0], minlength=sg.num_users) > 0)
+    np.random.default_rng(42).shuffle(train_users)
+    bu = [train_users[s:s + args.batch] for s in range(0, len(train_users), args.batch)]
+    batches = host_triples(sg, bu)
+    # probe one step, then bound the whole run to ~150 s by subsampling edges if needed
+    _, probe_ms, cores, _ = cpu_baseline(sg, shp, e0_u, e0_i, batches, 1, 1e-4)
+    total = args.steps + args.warmup
+    frac = min(1.0, 150.0 / max(total * probe_ms / 1e3, 1e-9))
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import credgcn_oracle as orc
+    edges = sg.train_edges
+    if frac < 1.0:
+        edges = edges[:, np.random.default_rng(0).random(edges.shape[1]) < frac]
+    ops = orc.Operators(edges, sg.num_users, sg.num_items, sg.cred, shp["variant"])
+    base = orc.TorchCpuBaseline(ops, e0_u, e0_i, shp["num_layers"], shp["order"])
+    for s in range(args.warmup):
+        base.step(*batches[s % len(batches)], 1e-4)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        base.step(*batches[s % len(batches)], 1e-4)
+    dt = time.perf_counter() - t0
+    ms = 1e3 * dt / max(args.steps, 1)
+    E = edges.shape[1]
+    val = E / (ms / 1e3)
+    sample = (f"each step = one full training step (fwd+loss+bwd+Adam) on {E:,} train edges"
+              + (f" (edge subsample {frac:.3f} of workload {args.workload})" if frac < 1 else f" (all of {args.workload})"))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "edges/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, sg, shp, flush=False),
+        "cpu_baseline": {"value": val, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, sg, shp, flush):
+    return {
+        "workload": f"{args.workload}: {sg.num_users:,} users x {sg.num_items:,} items x "
+                    f"{sg.train_edges.shape[1]:,} train edges ({shp['variant']} operator, {shp['order']} order)",
+        "emb_dim": shp["emb_dim"], "num_layers": shp["num_layers"], "batch_users": args.batch,
+        "step": "sample+fwd+loss+bwd+adam", "fake_user_frac": 0.05,
+        "l2": "flushed between timed steps (256 MiB write)" if flush else "not flushed",
+    }
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from credgcn import _lib, graph, model, sampler
+    if world > 1:
+        from credgcn import sharded
+        return sharded.bench_main(args, rank, world, dev)
+
+    sg, shp, t_gen = make_workload(args.workload)
+    U, I, E = sg.num_users, sg.num_items, sg.train_edges.shape[1]
+    d, K = shp["emb_dim"], shp["num_layers"]
+
+    # ---- graph build (timed once, device-resident edges, and once end to end from host) ----
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    gr = graph.build_graph(sg.train_edges, U, I, sg.cred, shp["variant"], dev)
+    torch.cuda.synchronize()
+    t_build_e2e = time.perf_counter() - t0
+    edges_dev = torch.from_numpy(sg.train_edges).to(dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    gr = graph.build_graph(edges_dev, U, I, torch.from_numpy(sg.cred).to(dev), shp["variant"], dev)
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t0
+
+    torch.manual_seed(42)
+    Net = model.CredLightGCN if shp["variant"] == "cu" else model.LightGCN
+    ops = (gr.operator("C"), gr.operator("A")) if shp["variant"] == "cu" else (gr.operator("A"), gr.operator("C"))
+    net = Net(U, I, d, K, *ops).to(dev)
+    e0_u = net.user_emb.weight.detach().cpu().numpy().copy()
+    e0_i = net.item_emb.weight.detach().cpu().numpy().copy()
+    step = model.TrainStep(net, lr=1e-3, reg_weight=1e-4)
+    samp = sampler.TripleSampler(gr, None if shp["variant"] == "cu" else 0.7, 0.75, 50, seed=42)
+
+    train_users = np.flatnonzero(np.diff(gr.user_csr_numpy()[0]) > 0)
+    np.random.default_rng(42).shuffle(train_users)
+    host_batches = [train_users[s:s + args.batch] for s in range(0, len(train_users), args.batch)]
+    dev_batches = [torch.from_numpy(b).to(dev) for b in host_batches]
+    pinned = [torch.from_numpy(b).pin_memory() for b in host_batches]
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def one_step(users_dev):
+        pos, neg = samp.sample(users_dev)
+        return step(users_dev, pos, neg)
+
+    # ---- warm-up ----
+    for s in range(max(args.warmup, 3)):
+        one_step(dev_batches[s % len(dev_batches)])
+    torch.cuda.synchronize()
+
+    # ---- timed: device-resident inputs ("value") ----
+    step.phase_events = []
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    launches0 = _lib.lib().cgx_launch_count()
+    with ClockSampler(local) as clocks:
+        torch.cuda.synchronize()
+        for s in range(args.steps):
+            if not args.no_flush:
+                flush_buf.fill_(s & 0xff)
+            starts[s].record()
+            one_step(dev_batches[s % len(dev_batches)])
+            ends[s].record()
+        torch.cuda.synchronize()
+        launches = _lib.lib().cgx_launch_count() - launches0
+        step_ms = [a.elapsed_time(b) for a, b in zip(starts, ends)]
+        phases = step.phase_events
+        step.phase_events = None
+
+        # ---- timed: end to end through the public API with host buffers ("e2e") ----
+        loss_host = 0.0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            users_dev = pinned[s % len(pinned)].to(dev, non_blocking=True)     # H2D of this step's input
+            loss_host = float(one_step(users_dev).item())                       # D2H of this step's result
+        torch.cuda.synchronize()
+        e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    clk = clocks.summary()
+
+    ms = float(np.mean(step_ms))
+    fwd_ms = float(np.mean([m[0].elapsed_time(m[1]) for m in phases]))
+    loss_ms = float(np.mean([m[1].elapsed_time(m[2]) for m in phases]))
+    bwd_ms = float(np.mean([m[2].elapsed_time(m[3]) for m in phases]))
+    prop_ms = fwd_ms + bwd_ms
+    hbm_peak, peak_src = peaks()
+    alg = algorithmic_bytes(U, I, gr.nnz, d, K)
+    n_spmm = 4 * K
+    achieved = alg / (prop_ms / 1e3) / 1e9
+
+    line = {
+        "metric": METRIC, "value": E / (ms / 1e3), "unit": "edges/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, sg, shp, flush=not args.no_flush),
+        "e2e": {"value": E / (e2e_ms / 1e3), "unit": "edges/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(host_batches[0].nbytes), "d2h_bytes_per_step": 4,
+                "api": "TripleSampler.sample + TrainStep.__call__ + loss.item()"},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": {
+            "bound": "hbm", "kernel": "k_spmm_rows (+ long-row partial/finish), 4K launches per step",
+            "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "peak_source": peak_src, "traffic": None,
+            "algorithmic_bytes_per_step": alg, "algorithmic_bytes_per_launch": alg / n_spmm,
+            "avg_launch_ms": prop_ms / n_spmm,
+            "note": "tables of this workload fit the 126 MB L2, so the gather-model figure can exceed the HBM peak",
+        },
+        "phases_ms": {"propagate_fwd": fwd_ms, "bpr_loss+grad_scatter": loss_ms, "propagate_bwd": bwd_ms,
+                      "sampler+adam+rest": ms - prop_ms - loss_ms},
+        "fwd_bwd_edges_per_s": E / (prop_ms / 1e3),
+        "graph_build_ms": {"device_resident": 1e3 * t_build, "from_host_edges": 1e3 * t_build_e2e,
+                           "edges_per_s": E / t_build},
+        "loss": loss_host,
+    }
+
+    if not args.no_cpu_baseline:
+        bt = host_triples(sg, host_batches)
+        v, cms, cores, sample = cpu_baseline(sg, shp, e0_u, e0_i, bt, args.cpu_steps, 1e-4)
+        line["cpu_baseline"] = {"value": v, "unit": "edges/s", "cores": cores, "kind": "port",
+                                "sample": sample, "ms_per_step": cms}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,122 @@
+"""ctypes binding of libcredgcn.so (include/credgcn.h).  No CPU fallback: a missing library or a
+non-CUDA tensor is an error, raised loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import pathlib
+import subprocess
+
+import torch
+
+PKG_DIR = pathlib.Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "libcredgcn.so"
+CSRC_DIR = PKG_DIR / "csrc"
+
+VARIANTS = {"cu": 0, "v2": 1, "da": 2}
+ORDERS = {"jacobi": 0, "gs": 1}
+PRECISIONS = {"fp32": 0, "bf16x3": 1, "bf16": 2}
+LONG_ROW = 512
+CHUNK = 2048
+
+
+class CgxError(RuntimeError):
+    pass
+
+
+class CsrStruct(C.Structure):
+    """struct cgx_csr"""
+    _fields_ = [
+        ("n_rows", C.c_int32), ("n_cols", C.c_int32), ("nnz", C.c_int64),
+        ("indptr", C.c_void_p), ("idx", C.c_void_p), ("val_fwd", C.c_void_p), ("val_bwd", C.c_void_p),
+        ("n_long", C.c_int32), ("n_chunks", C.c_int32), ("long_rows", C.c_void_p), ("chunk_ptr", C.c_void_p),
+    ]
+
+
+_P = C.c_void_p
+_CSR = C.POINTER(CsrStruct)
+_SIGNATURES = {
+    "cgx_last_error": (C.c_char_p, []),
+    "cgx_version": (C.c_int, []),
+    "cgx_launch_count": (C.c_uint64, []),
+    "cgx_emb_dim_supported": (C.c_int, [C.c_int32]),
+    "cgx_graph_build_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
+    "cgx_graph_build": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int, _P, _P, _P, _P, _P,
+                                  _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P, C.c_size_t, _P]),
+    "cgx_user_csr": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
+    "cgx_long_rows_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "cgx_long_rows_count": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P,
+                                      C.c_size_t, _P]),
+    "cgx_long_rows_fill": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
+    "cgx_spmm_workspace_bytes": (C.c_size_t, [_CSR, C.c_int32]),
+    "cgx_spmm": (C.c_int, [_CSR, C.c_int, C.c_int32, _P, _P, _P, _P, C.c_float, _P, C.c_size_t, _P]),
+    "cgx_propagate_workspace_bytes": (C.c_size_t, [_CSR, _CSR, C.c_int32]),
+    "cgx_propagate_fwd": (C.c_int, [_CSR, _CSR, C.c_int, C.c_int32, C.c_int32, _P, _P, _P, _P, _P,
+                                    C.c_size_t, _P]),
+    "cgx_propagate_bwd": (C.c_int, [_CSR, _CSR, C.c_int, C.c_int32, C.c_int32, _P, _P, _P, _P, _P,
+                                    C.c_size_t, _P]),
+    "cgx_bpr_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
+    "cgx_bpr_fwd_bwd": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P,
+                                  C.c_float, C.c_float, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "cgx_bpr_apply_ego": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
+    "cgx_sampler_build_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "cgx_sampler_build": (C.c_int, [_P, C.c_int32, C.c_double, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "cgx_sample_triples": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int32, _P, _P, _P, _P, _P, C.c_float,
+                                     C.c_int32, C.c_uint64, C.c_uint64, _P, _P, _P]),
+    "cgx_eval_topk_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int]),
+    "cgx_eval_topk": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.c_int, _P,
+                                _P, _P, C.c_size_t, _P]),
+    "cgx_score_candidates": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+}
+EXPORTED = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def build_library(verbose: bool = False) -> pathlib.Path:
+    """Compile csrc/*.cu for sm_100a into libcredgcn.so (nvcc cross-compiles without a GPU)."""
+    out = subprocess.run(["make", "-C", str(CSRC_DIR), "-j8"], capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout[-4000:], out.stderr[-4000:])
+    if out.returncode != 0:
+        raise CgxError("building libcredgcn.so failed (see output above)")
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise CgxError(
+                f"{LIB_PATH} is missing: the sm_100a extension has not been built. Run "
+                f"`python -c 'import __graft_entry__ as g; g.build()'` (or `make -C {CSRC_DIR}`). "
+                "There is no CPU fallback.")
+        handle = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)        # AttributeError here = header/library drift: fail loudly
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        raise CgxError(f"libcredgcn error {status}: {lib().cgx_last_error().decode()}")
+
+
+def ptr(t: torch.Tensor | None):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise CgxError("credgcn ops need CUDA tensors: there is no CPU fallback")
+    if not t.is_contiguous():
+        raise CgxError("credgcn ops need contiguous tensors")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)

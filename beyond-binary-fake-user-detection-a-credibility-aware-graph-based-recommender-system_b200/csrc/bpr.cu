@@ -1,0 +1,307 @@
+// Fused BPR + L2 (+ fairness) loss on a batch of (user, pos, neg) triples: forward value and the
+// gradients w.r.t. the propagated tables, scattered WITHOUT atomics.
+//
+// Replaces (reference, /root/reference): score / l2_reg / loss assembly lightgcn_cu.py:450-463,
+// 635-648; bpr_loss Version-2/lighgcn_cu_pop.py:495-508; and the index_put-with-accumulate
+// backward autograd runs for them.
+//
+// Scatter scheme: every triple t contributes to three rows (user u, item pos, item neg).  The 3B
+// (row, entry) pairs are packed into 64-bit keys and radix sorted; one thread group per distinct
+// row then walks its run in entry order and writes the row once.  Entry order is fixed by the
+// sort, so the result is bitwise reproducible.
+#include "common.cuh"
+
+namespace cgx {
+
+constexpr int BP_THREADS = 256;
+
+template <int G>
+__device__ __forceinline__ unsigned bp_group_mask() {
+  if (G == 32) return 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31;
+  return ((1u << (G & 31)) - 1u) << (lane & ~(G - 1));
+}
+
+template <int G>
+__device__ __forceinline__ float group_sum(float v, unsigned mask) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, G);
+  return v;
+}
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+  return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+}
+
+struct BprArgs {
+  const int64_t* users;
+  const int64_t* pos;
+  const int64_t* neg;
+  int64_t B;
+  int32_t U, I;
+  const float4* f_u;
+  const float4* f_i;
+  const float4* e0_u;
+  const float4* e0_i;
+  const float* pop;
+  float reg, fair;
+};
+
+// per triple: scores, loss term, coefficients, and the three sort keys
+template <int G, int V>
+__global__ void __launch_bounds__(BP_THREADS) k_bpr_triple(BprArgs a, int entry_bits, float* __restrict__ coef_pos,
+                                                           float* __restrict__ coef_neg,
+                                                           float* __restrict__ loss_term,
+                                                           uint64_t* __restrict__ keys,
+                                                           unsigned long long* __restrict__ bad) {
+  constexpr int ROW4 = G * V;
+  const int lane = threadIdx.x & (G - 1);
+  const int64_t t = (int64_t(blockIdx.x) * BP_THREADS + threadIdx.x) / G;
+  if (t >= a.B) return;
+  const unsigned mask = bp_group_mask<G>();
+  int64_t u = a.users[t], p = a.pos[t], n = a.neg[t];
+  if (u < 0 || u >= a.U || p < 0 || p >= a.I || n < 0 || n >= a.I) {
+    if (lane == 0) atomicAdd(bad, 1ull);
+    u = 0; p = 0; n = 0;
+  }
+  float yp = 0.f, yn = 0.f, l2 = 0.f;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const int o = v * G + lane;
+    const float4 fu = __ldg(a.f_u + u * ROW4 + o);
+    const float4 fp = __ldg(a.f_i + p * ROW4 + o);
+    const float4 fn = __ldg(a.f_i + n * ROW4 + o);
+    yp += dot4(fu, fp);
+    yn += dot4(fu, fn);
+    const float4 eu = __ldg(a.e0_u + u * ROW4 + o);
+    const float4 ep = __ldg(a.e0_i + p * ROW4 + o);
+    const float4 en = __ldg(a.e0_i + n * ROW4 + o);
+    l2 += dot4(eu, eu) + dot4(ep, ep) + dot4(en, en);
+  }
+  yp = group_sum<G>(yp, mask);
+  yn = group_sum<G>(yn, mask);
+  l2 = group_sum<G>(l2, mask);
+  if (lane == 0) {
+    const float invB = 1.0f / float(a.B);
+    const float x = yp - yn;
+    const float sig = 1.0f / (1.0f + expf(-x));
+    const float term = -logf(sig + 1e-12f);                      // lightgcn_cu.py:637 (epsilon form)
+    const float gx = -(sig * (1.0f - sig)) / (sig + 1e-12f) * invB;
+    const float pw = (a.pop != nullptr && a.fair != 0.f) ? a.fair * __ldg(a.pop + p) : 0.f;
+    coef_pos[t] = gx + pw * invB;
+    coef_neg[t] = -gx;
+    loss_term[t] = (term + pw * yp + a.reg * l2) * invB;
+    const uint64_t B = uint64_t(a.B);
+    keys[t] = (uint64_t(u) << entry_bits) | uint64_t(t);
+    keys[B + t] = (uint64_t(a.U + p) << entry_bits) | (B + uint64_t(t));
+    keys[2 * B + t] = (uint64_t(a.U + n) << entry_bits) | (2 * B + uint64_t(t));
+  }
+}
+
+// one group per sorted entry; run heads accumulate the whole run and write the row once
+template <int G, int V>
+__global__ void __launch_bounds__(BP_THREADS) k_bpr_scatter(BprArgs a, int entry_bits,
+                                                            const uint64_t* __restrict__ keys,
+                                                            const float* __restrict__ coef_pos,
+                                                            const float* __restrict__ coef_neg,
+                                                            float4* __restrict__ g_u, float4* __restrict__ g_i,
+                                                            int32_t* __restrict__ ego_rows,
+                                                            float* __restrict__ ego_coef) {
+  constexpr int ROW4 = G * V;
+  const int lane = threadIdx.x & (G - 1);
+  const int64_t k = (int64_t(blockIdx.x) * BP_THREADS + threadIdx.x) / G;
+  const int64_t n = 3 * a.B;
+  if (k >= n) return;
+  const uint64_t emask = (uint64_t(1) << entry_bits) - 1;
+  const uint64_t key = keys[k];
+  const int64_t row = int64_t(key >> entry_bits);
+  const bool head = (k == 0) || (int64_t(keys[k - 1] >> entry_bits) != row);
+  if (!head) {
+    if (lane == 0) ego_rows[k] = -1;
+    return;
+  }
+  float4 acc[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int mult = 0;
+  for (int64_t q = k; q < n; ++q) {
+    const uint64_t kq = keys[q];
+    if (int64_t(kq >> entry_bits) != row) break;
+    const int64_t e = int64_t(kq & emask);
+    const int64_t t = e % a.B;
+    const int type = int(e / a.B);
+    ++mult;
+    if (type == 0) {  // user row: cp * f_i[pos] + cn * f_i[neg]
+      const float cp = coef_pos[t], cn = coef_neg[t];
+      int64_t p = a.pos[t], ng = a.neg[t];
+      if (p < 0 || p >= a.I) p = 0;      // flagged by k_bpr_triple; keep the gather in bounds
+      if (ng < 0 || ng >= a.I) ng = 0;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const float4 fp = __ldg(a.f_i + p * ROW4 + v * G + lane);
+        const float4 fn = __ldg(a.f_i + ng * ROW4 + v * G + lane);
+        acc[v].x += cp * fp.x + cn * fn.x;
+        acc[v].y += cp * fp.y + cn * fn.y;
+        acc[v].z += cp * fp.z + cn * fn.z;
+        acc[v].w += cp * fp.w + cn * fn.w;
+      }
+    } else {  // item row: coefficient * f_u[user]
+      const float c = type == 1 ? coef_pos[t] : coef_neg[t];
+      int64_t u = a.users[t];
+      if (u < 0 || u >= a.U) u = 0;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const float4 fu = __ldg(a.f_u + u * ROW4 + v * G + lane);
+        acc[v].x += c * fu.x;
+        acc[v].y += c * fu.y;
+        acc[v].z += c * fu.z;
+        acc[v].w += c * fu.w;
+      }
+    }
+  }
+  float4* dst = row < a.U ? g_u + row * ROW4 : g_i + (row - a.U) * ROW4;
+#pragma unroll
+  for (int v = 0; v < V; ++v) dst[v * G + lane] = acc[v];
+  if (lane == 0) {
+    ego_rows[k] = int32_t(row);
+    ego_coef[k] = float(mult) * 2.0f * a.reg / float(a.B);
+  }
+}
+
+// deterministic sum of B terms by one CTA (fixed tree)
+__global__ void __launch_bounds__(1024) k_sum_terms(const float* __restrict__ terms, int64_t n,
+                                                    float* __restrict__ out) {
+  __shared__ double sh[1024];
+  double s = 0.0;
+  for (int64_t p = threadIdx.x; p < n; p += 1024) s += double(terms[p]);
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = float(sh[0]);
+}
+
+template <int G, int V>
+__global__ void __launch_bounds__(BP_THREADS) k_apply_ego(const int32_t* __restrict__ ego_rows,
+                                                          const float* __restrict__ ego_coef, int64_t n,
+                                                          int32_t U, const float4* __restrict__ e0_u,
+                                                          const float4* __restrict__ e0_i, float4* d_u,
+                                                          float4* d_i) {
+  constexpr int ROW4 = G * V;
+  const int lane = threadIdx.x & (G - 1);
+  const int64_t k = (int64_t(blockIdx.x) * BP_THREADS + threadIdx.x) / G;
+  if (k >= n) return;
+  const int32_t row = ego_rows[k];
+  if (row < 0) return;
+  const float c = ego_coef[k];
+  const float4* src = row < U ? e0_u + int64_t(row) * ROW4 : e0_i + int64_t(row - U) * ROW4;
+  float4* dst = row < U ? d_u + int64_t(row) * ROW4 : d_i + int64_t(row - U) * ROW4;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const float4 e = __ldg(src + v * G + lane);
+    float4 g = dst[v * G + lane];
+    g.x += c * e.x; g.y += c * e.y; g.z += c * e.z; g.w += c * e.w;
+    dst[v * G + lane] = g;
+  }
+}
+
+__global__ void k_check_bad(const unsigned long long* bad, float* loss_out) {
+  if (*bad != 0ull) *loss_out = __int_as_float(0x7fc00000);  // NaN: an index was out of range
+}
+
+static size_t bpr_ws(int64_t B) {
+  const int64_t n = 3 * B;
+  return 2 * align_up(size_t(n) * 8) + 3 * align_up(size_t(B) * 4) + radix_sort_temp_bytes(n) + 512;
+}
+
+template <int G, int V>
+static int bpr_run(const BprArgs& a, float* loss_out, float* g_u, float* g_i, int32_t* ego_rows, float* ego_coef,
+                   void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  const int64_t B = a.B, n = 3 * B;
+  Arena ws(workspace, workspace_bytes);
+  uint64_t* keys = ws.take<uint64_t>(n);
+  uint64_t* alt = ws.take<uint64_t>(n);
+  float* coef_pos = ws.take<float>(B);
+  float* coef_neg = ws.take<float>(B);
+  float* terms = ws.take<float>(B);
+  size_t sort_bytes = radix_sort_temp_bytes(n);
+  void* sort_tmp = ws.take<char>(sort_bytes);
+  unsigned long long* bad = ws.take<unsigned long long>(1);
+  CGX_REQUIRE(ws.ok, CGX_ERR_WORKSPACE, "bpr: workspace too small");
+  const int entry_bits = bits_for(n);
+  const int row_bits = bits_for(int64_t(a.U) + a.I);
+  constexpr int GROUPS = BP_THREADS / G;
+  CGX_CUDA(cudaMemsetAsync(bad, 0, 8, stream));
+  k_bpr_triple<G, V><<<(unsigned)ceil_div(B, GROUPS), BP_THREADS, 0, stream>>>(a, entry_bits, coef_pos, coef_neg,
+                                                                             terms, keys, bad);
+  CGX_LAUNCH_CHECK();
+  uint64_t* sorted = keys;
+  CGX_TRY(radix_sort_u64(keys, alt, n, entry_bits + row_bits, sort_tmp, sort_bytes, stream, &sorted));
+  k_bpr_scatter<G, V><<<(unsigned)ceil_div(n, GROUPS), BP_THREADS, 0, stream>>>(
+      a, entry_bits, sorted, coef_pos, coef_neg, reinterpret_cast<float4*>(g_u), reinterpret_cast<float4*>(g_i),
+      ego_rows, ego_coef);
+  CGX_LAUNCH_CHECK();
+  k_sum_terms<<<1, 1024, 0, stream>>>(terms, B, loss_out);
+  CGX_LAUNCH_CHECK();
+  k_check_bad<<<1, 1, 0, stream>>>(bad, loss_out);
+  CGX_LAUNCH_CHECK();
+  return CGX_OK;
+}
+
+}  // namespace cgx
+
+using namespace cgx;
+
+extern "C" size_t cgx_bpr_workspace_bytes(int64_t batch, int32_t, int32_t) { return bpr_ws(batch); }
+
+extern "C" int cgx_bpr_fwd_bwd(const int64_t* users, const int64_t* pos, const int64_t* neg, int64_t batch,
+                               int32_t U, int32_t I, int32_t d, const float* f_u, const float* f_i,
+                               const float* e0_u, const float* e0_i, const float* pop, float reg_weight,
+                               float fair_weight, float* loss_out, float* g_u, float* g_i, int32_t* ego_rows,
+                               float* ego_coef, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CGX_REQUIRE(users && pos && neg && f_u && f_i && e0_u && e0_i && loss_out && g_u && g_i && ego_rows && ego_coef,
+              CGX_ERR_ARG, "bpr: NULL pointer");
+  CGX_REQUIRE(batch > 0 && batch < (int64_t(1) << 29), CGX_ERR_ARG, "bpr: bad batch size %lld", (long long)batch);
+  CGX_REQUIRE(workspace_bytes >= bpr_ws(batch), CGX_ERR_WORKSPACE, "bpr: workspace too small");
+  BprArgs a{users, pos, neg, batch, U, I, reinterpret_cast<const float4*>(f_u),
+            reinterpret_cast<const float4*>(f_i), reinterpret_cast<const float4*>(e0_u),
+            reinterpret_cast<const float4*>(e0_i), pop, reg_weight, fair_weight};
+  switch (d) {
+    case 16: return bpr_run<4, 1>(a, loss_out, g_u, g_i, ego_rows, ego_coef, workspace, workspace_bytes, stream);
+    case 32: return bpr_run<8, 1>(a, loss_out, g_u, g_i, ego_rows, ego_coef, workspace, workspace_bytes, stream);
+    case 64: return bpr_run<16, 1>(a, loss_out, g_u, g_i, ego_rows, ego_coef, workspace, workspace_bytes, stream);
+    case 128: return bpr_run<32, 1>(a, loss_out, g_u, g_i, ego_rows, ego_coef, workspace, workspace_bytes, stream);
+    case 256: return bpr_run<32, 2>(a, loss_out, g_u, g_i, ego_rows, ego_coef, workspace, workspace_bytes, stream);
+    default:
+      set_error("bpr: emb_dim %d unsupported (16, 32, 64, 128, 256)", d);
+      return CGX_ERR_UNSUPPORTED;
+  }
+}
+
+extern "C" int cgx_bpr_apply_ego(const int32_t* ego_rows, const float* ego_coef, int64_t n_entries, int32_t U,
+                                 int32_t d, const float* e0_u, const float* e0_i, float* d_e0_u, float* d_e0_i,
+                                 void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CGX_REQUIRE(ego_rows && ego_coef && e0_u && e0_i && d_e0_u && d_e0_i && n_entries > 0, CGX_ERR_ARG,
+              "apply_ego: bad argument");
+#define CGX_EGO(GG, VV)                                                                                        \
+  k_apply_ego<GG, VV><<<(unsigned)ceil_div(n_entries, BP_THREADS / GG), BP_THREADS, 0, stream>>>(              \
+      ego_rows, ego_coef, n_entries, U, reinterpret_cast<const float4*>(e0_u),                                  \
+      reinterpret_cast<const float4*>(e0_i), reinterpret_cast<float4*>(d_e0_u), reinterpret_cast<float4*>(d_e0_i))
+  switch (d) {
+    case 16: CGX_EGO(4, 1); break;
+    case 32: CGX_EGO(8, 1); break;
+    case 64: CGX_EGO(16, 1); break;
+    case 128: CGX_EGO(32, 1); break;
+    case 256: CGX_EGO(32, 2); break;
+    default:
+      set_error("apply_ego: emb_dim %d unsupported", d);
+      return CGX_ERR_UNSUPPORTED;
+  }
+#undef CGX_EGO
+  CGX_LAUNCH_CHECK();
+  return CGX_OK;
+}

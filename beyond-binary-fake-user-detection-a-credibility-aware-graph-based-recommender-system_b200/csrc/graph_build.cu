@@ -1,0 +1,356 @@
+// Graph build on device: degree vectors, the duplicate-keeping user-row CSR, and both coalesced,
+// credibility-weighted operators in both row orders.
+//
+// Replaces (reference, /root/reference):
+//   edges_to_user_csr            lightgcn_cu.py:259-276
+//   build_cred_weighted_mats     lightgcn_cu.py:368-399
+//   build_message_passing_mats   Version-2/lighgcn_cu_pop.py:429-452,
+//                                version_1/lightgcn_cu_pop_Degree-Aware Message.py:349-403
+// Bit-exactness: the reference does this arithmetic with NumPy float32 ufuncs, which are
+// correctly rounded; every float op below is an explicit round-to-nearest intrinsic
+// (__fmul_rn / __fdiv_rn / __fsqrt_rn / __fadd_rn) so that nvcc can neither contract to FMA
+// nor substitute an approximate division.
+#include "common.cuh"
+
+namespace cgx {
+
+constexpr int GB_THREADS = 256;
+
+__global__ void k_pack_and_count(const int32_t* __restrict__ eu, const int32_t* __restrict__ ei, int64_t E,
+                                 int32_t U, int32_t I, int bits_u, int bits_i,
+                                 uint64_t* __restrict__ key_ui, uint64_t* __restrict__ key_iu,
+                                 int32_t* deg_u, int32_t* deg_i, unsigned long long* bad) {
+  int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int32_t u = eu[e], i = ei[e];
+  if (u < 0 || u >= U || i < 0 || i >= I) {
+    atomicAdd(bad, 1ull);
+    u = 0;
+    i = 0;  // keep the arrays well formed; the caller rejects the build when bad != 0
+  }
+  if (key_ui) key_ui[e] = (uint64_t(uint32_t(u)) << bits_i) | uint32_t(i);
+  if (key_iu) key_iu[e] = (uint64_t(uint32_t(i)) << bits_u) | uint32_t(u);
+  if (deg_u) atomicAdd(&deg_u[u], 1);
+  if (deg_i) atomicAdd(&deg_i[i], 1);
+}
+
+__global__ void k_widen(const uint32_t* __restrict__ in, int64_t* __restrict__ out, int64_t n) {
+  int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p < n) out[p] = int64_t(in[p]);
+}
+
+__global__ void k_unpack_minor(const uint64_t* __restrict__ keys, int64_t n, int minor_bits,
+                               int32_t* __restrict__ minor) {
+  int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p < n) minor[p] = int32_t(keys[p] & ((uint64_t(1) << minor_bits) - 1));
+}
+
+__global__ void k_head_flags(const uint64_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ flags) {
+  int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p < n) flags[p] = (p == 0 || keys[p] != keys[p - 1]) ? 1u : 0u;
+}
+
+struct WeightArgs {
+  const int32_t* deg_u;
+  const int32_t* deg_i;
+  const float* cred;
+  const float* alpha;
+  int variant;
+};
+
+// (w_A, w_C) of one (u, i) pair; mirrors oracle.edge_weights op for op.
+__device__ __forceinline__ void edge_weight(const WeightArgs& a, int32_t u, int32_t i, float* w_a, float* w_c) {
+  float du = float(a.deg_u[u]), di = float(a.deg_i[i]);  // int -> float, round to nearest even (== astype)
+  float c = a.cred[u];
+  if (a.variant == CGX_VARIANT_CU) {  // lightgcn_cu.py:386-389
+    float denom = __fsqrt_rn(fmaxf(__fmul_rn(du, di), 1e-12f));
+    *w_c = __fdiv_rn(c, denom);
+    *w_a = __fdiv_rn(1.0f, denom);
+  } else {  // lighgcn_cu_pop.py:436-446
+    float isu = __fdiv_rn(1.0f, __fsqrt_rn(fmaxf(du, 1.0f)));
+    float isi = __fdiv_rn(1.0f, __fsqrt_rn(fmaxf(di, 1.0f)));
+    float w = __fmul_rn(isu, isi);
+    if (a.variant == CGX_VARIANT_DA) w = __fmul_rn(w, a.alpha[i]);  // Degree-Aware Message.py:383
+    *w_a = w;
+    *w_c = __fmul_rn(c, w);
+  }
+}
+
+// One thread per sorted entry; run heads emit the coalesced entry.  Duplicates of one (u, i) pair
+// carry identical weights and are added left to right, as torch's CPU coalesce() does.
+__global__ void k_emit(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ pos, int64_t n,
+                       int minor_bits, int major_is_user, WeightArgs wa, int32_t* __restrict__ idx,
+                       float* __restrict__ val_fwd, float* __restrict__ val_bwd) {
+  int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  uint64_t k = keys[p];
+  if (p > 0 && keys[p - 1] == k) return;
+  int mult = 1;
+  while (p + mult < n && keys[p + mult] == k) ++mult;
+  int32_t minor = int32_t(k & ((uint64_t(1) << minor_bits) - 1));
+  int32_t major = int32_t(k >> minor_bits);
+  int32_t u = major_is_user ? major : minor;
+  int32_t i = major_is_user ? minor : major;
+  float w_a, w_c;
+  edge_weight(wa, u, i, &w_a, &w_c);
+  float s_a = w_a, s_c = w_c;
+  for (int m = 1; m < mult; ++m) {
+    s_a = __fadd_rn(s_a, w_a);
+    s_c = __fadd_rn(s_c, w_c);
+  }
+  uint32_t q = pos[p];
+  idx[q] = minor;
+  val_fwd[q] = major_is_user ? s_a : s_c;
+  val_bwd[q] = major_is_user ? s_c : s_a;
+}
+
+// indptr of the coalesced pattern from the duplicate-keeping row starts
+__global__ void k_coalesced_indptr(const uint32_t* __restrict__ row_start, const uint32_t* __restrict__ pos,
+                                   const uint32_t* __restrict__ nnz, int64_t n_entries, int32_t n_rows,
+                                   int64_t* __restrict__ indptr) {
+  int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r > n_rows) return;
+  uint32_t s = row_start[r];
+  indptr[r] = (int64_t(s) < n_entries) ? int64_t(pos[s]) : int64_t(*nnz);
+}
+
+__global__ void k_finish_counts(const uint32_t* nnz, const unsigned long long* bad, int64_t* out) {
+  out[0] = int64_t(*nnz);
+  out[1] = int64_t(*bad);
+}
+
+static inline unsigned grid_for(int64_t n) { return (unsigned)ceil_div(n > 0 ? n : 1, GB_THREADS); }
+
+static size_t build_ws_bytes(int64_t E, int32_t U, int32_t I) {
+  size_t b = 0;
+  b += 3 * align_up(size_t(E) * 8);                  // key_ui, key_iu, alt
+  b += align_up(size_t(E + 1) * 4);                  // flags / pos
+  b += align_up(size_t(int64_t(U) + 1) * 4);         // user row starts (u32)
+  b += align_up(size_t(int64_t(I) + 1) * 4);         // item row starts (u32)
+  b += radix_sort_temp_bytes(E);
+  int64_t m = E + 1;
+  if (int64_t(U) + 1 > m) m = int64_t(U) + 1;
+  if (int64_t(I) + 1 > m) m = int64_t(I) + 1;
+  b += scan_temp_bytes(m);
+  b += 1024;
+  return b;
+}
+
+}  // namespace cgx
+
+using namespace cgx;
+
+extern "C" size_t cgx_graph_build_workspace_bytes(int64_t num_edges, int32_t num_users, int32_t num_items) {
+  return build_ws_bytes(num_edges, num_users, num_items);
+}
+
+extern "C" int cgx_graph_build(const int32_t* edges_u, const int32_t* edges_i, int64_t E, int32_t U, int32_t I,
+                               const float* cred, int variant, const float* alpha, int32_t* deg_u,
+                               int32_t* deg_i, int64_t* samp_indptr, int32_t* samp_idx,
+                               int64_t* user_indptr, int32_t* user_idx, float* user_val_fwd,
+                               float* user_val_bwd, int64_t* item_indptr, int32_t* item_idx,
+                               float* item_val_fwd, float* item_val_bwd, int64_t* nnz_out, int deg_only,
+                               void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CGX_REQUIRE(E >= 0 && U > 0 && I > 0, CGX_ERR_ARG, "graph_build: bad sizes E=%lld U=%d I=%d", (long long)E, U, I);
+  CGX_REQUIRE(E < (int64_t(1) << 31), CGX_ERR_ARG, "graph_build: E must be < 2^31");
+  CGX_REQUIRE((E == 0 || (edges_u && edges_i)) && deg_u && deg_i && nnz_out, CGX_ERR_ARG,
+              "graph_build: NULL pointer");
+  CGX_REQUIRE(variant >= CGX_VARIANT_CU && variant <= CGX_VARIANT_DA, CGX_ERR_ARG, "graph_build: bad variant %d",
+              variant);
+  CGX_REQUIRE(workspace_bytes >= build_ws_bytes(E, U, I), CGX_ERR_WORKSPACE, "graph_build: workspace too small");
+  if (!deg_only) {
+    CGX_REQUIRE(cred && samp_indptr && samp_idx && user_indptr && user_idx && user_val_fwd && user_val_bwd &&
+                    item_indptr && item_idx && item_val_fwd && item_val_bwd,
+                CGX_ERR_ARG, "graph_build: NULL pointer");
+    CGX_REQUIRE(variant != CGX_VARIANT_DA || alpha != nullptr, CGX_ERR_ARG,
+                "graph_build: the degree-aware variant needs alpha");
+  }
+  const int bits_u = bits_for(U), bits_i = bits_for(I);
+
+  Arena ws(workspace, workspace_bytes);
+  uint64_t* key_ui = ws.take<uint64_t>(E);
+  uint64_t* key_iu = ws.take<uint64_t>(E);
+  uint64_t* alt = ws.take<uint64_t>(E);
+  uint32_t* flags = ws.take<uint32_t>(E + 1);
+  uint32_t* ustart = ws.take<uint32_t>(int64_t(U) + 1);
+  uint32_t* istart = ws.take<uint32_t>(int64_t(I) + 1);
+  size_t sort_bytes = radix_sort_temp_bytes(E);
+  void* sort_tmp = ws.take<char>(sort_bytes);
+  int64_t m = E + 1;
+  if (int64_t(U) + 1 > m) m = int64_t(U) + 1;
+  if (int64_t(I) + 1 > m) m = int64_t(I) + 1;
+  size_t scan_bytes = scan_temp_bytes(m);
+  void* scan_tmp = ws.take<char>(scan_bytes);
+  uint32_t* nnz_dev = ws.take<uint32_t>(2);
+  unsigned long long* bad = ws.take<unsigned long long>(1);
+  CGX_REQUIRE(ws.ok, CGX_ERR_WORKSPACE, "graph_build: workspace too small");
+
+  CGX_CUDA(cudaMemsetAsync(deg_u, 0, size_t(U) * 4, stream));
+  CGX_CUDA(cudaMemsetAsync(deg_i, 0, size_t(I) * 4, stream));
+  CGX_CUDA(cudaMemsetAsync(bad, 0, 8, stream));
+  CGX_CUDA(cudaMemsetAsync(nnz_dev, 0, 8, stream));
+  if (E > 0) {
+    k_pack_and_count<<<grid_for(E), GB_THREADS, 0, stream>>>(edges_u, edges_i, E, U, I, bits_u, bits_i,
+                                                            deg_only ? nullptr : key_ui,
+                                                            deg_only ? nullptr : key_iu, deg_u, deg_i, bad);
+    CGX_LAUNCH_CHECK();
+  }
+  if (deg_only) {
+    k_finish_counts<<<1, 1, 0, stream>>>(nnz_dev, bad, nnz_out);
+    CGX_LAUNCH_CHECK();
+    return CGX_OK;
+  }
+
+  // duplicate-keeping row starts = exclusive scan of the degrees (+ total at [n_rows])
+  CGX_TRY(exclusive_scan_u32(reinterpret_cast<const uint32_t*>(deg_u), ustart, U, ustart + U, scan_tmp,
+                             scan_bytes, stream));
+  CGX_TRY(exclusive_scan_u32(reinterpret_cast<const uint32_t*>(deg_i), istart, I, istart + I, scan_tmp,
+                             scan_bytes, stream));
+  k_widen<<<grid_for(int64_t(U) + 1), GB_THREADS, 0, stream>>>(ustart, samp_indptr, int64_t(U) + 1);
+  CGX_LAUNCH_CHECK();
+
+  WeightArgs wa{deg_u, deg_i, cred, alpha, variant};
+  for (int pass = 0; pass < 2; ++pass) {
+    const bool by_user = pass == 0;
+    uint64_t* keys = by_user ? key_ui : key_iu;
+    const int minor_bits = by_user ? bits_i : bits_u;
+    const int32_t n_rows = by_user ? U : I;
+    uint64_t* sorted = keys;
+    CGX_TRY(radix_sort_u64(keys, alt, E, bits_u + bits_i, sort_tmp, sort_bytes, stream, &sorted));
+    if (by_user && E > 0) {
+      k_unpack_minor<<<grid_for(E), GB_THREADS, 0, stream>>>(sorted, E, minor_bits, samp_idx);
+      CGX_LAUNCH_CHECK();
+    }
+    if (E > 0) {
+      k_head_flags<<<grid_for(E), GB_THREADS, 0, stream>>>(sorted, E, flags);
+      CGX_LAUNCH_CHECK();
+    }
+    CGX_TRY(exclusive_scan_u32(flags, flags, E, nnz_dev, scan_tmp, scan_bytes, stream));
+    if (E > 0) {
+      k_emit<<<grid_for(E), GB_THREADS, 0, stream>>>(sorted, flags, E, minor_bits, by_user ? 1 : 0, wa,
+                                                    by_user ? user_idx : item_idx,
+                                                    by_user ? user_val_fwd : item_val_fwd,
+                                                    by_user ? user_val_bwd : item_val_bwd);
+      CGX_LAUNCH_CHECK();
+    }
+    k_coalesced_indptr<<<grid_for(int64_t(n_rows) + 1), GB_THREADS, 0, stream>>>(
+        by_user ? ustart : istart, flags, nnz_dev, E, n_rows, by_user ? user_indptr : item_indptr);
+    CGX_LAUNCH_CHECK();
+    // if the sort left its result in `alt`, the next pass must not clobber it before use: it does
+    // not -- pass 1 sorts key_iu with `alt` as scratch only after pass 0 has consumed `sorted`.
+  }
+  k_finish_counts<<<1, 1, 0, stream>>>(nnz_dev, bad, nnz_out);
+  CGX_LAUNCH_CHECK();
+  return CGX_OK;
+}
+
+extern "C" int cgx_user_csr(const int32_t* edges_u, const int32_t* edges_i, int64_t E, int32_t U, int32_t I,
+                            int64_t* indptr, int32_t* idx, void* workspace, size_t workspace_bytes,
+                            void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CGX_REQUIRE(E >= 0 && U > 0 && I > 0 && E < (int64_t(1) << 31), CGX_ERR_ARG, "user_csr: bad sizes");
+  CGX_REQUIRE(indptr && (E == 0 || (edges_u && edges_i && idx)), CGX_ERR_ARG, "user_csr: NULL pointer");
+  CGX_REQUIRE(workspace_bytes >= build_ws_bytes(E, U, I), CGX_ERR_WORKSPACE, "user_csr: workspace too small");
+  const int bits_u = bits_for(U), bits_i = bits_for(I);
+  Arena ws(workspace, workspace_bytes);
+  uint64_t* key_ui = ws.take<uint64_t>(E);
+  uint64_t* alt = ws.take<uint64_t>(E);
+  int32_t* deg = ws.take<int32_t>(int64_t(U) + 1);
+  uint32_t* ustart = ws.take<uint32_t>(int64_t(U) + 1);
+  size_t sort_bytes = radix_sort_temp_bytes(E);
+  void* sort_tmp = ws.take<char>(sort_bytes);
+  size_t scan_bytes = scan_temp_bytes(int64_t(U) + 1);
+  void* scan_tmp = ws.take<char>(scan_bytes);
+  unsigned long long* bad = ws.take<unsigned long long>(1);
+  CGX_REQUIRE(ws.ok, CGX_ERR_WORKSPACE, "user_csr: workspace too small");
+  CGX_CUDA(cudaMemsetAsync(deg, 0, size_t(U) * 4, stream));
+  CGX_CUDA(cudaMemsetAsync(bad, 0, 8, stream));
+  if (E > 0) {
+    k_pack_and_count<<<grid_for(E), GB_THREADS, 0, stream>>>(edges_u, edges_i, E, U, I, bits_u, bits_i, key_ui,
+                                                            nullptr, deg, nullptr, bad);
+    CGX_LAUNCH_CHECK();
+  }
+  CGX_TRY(exclusive_scan_u32(reinterpret_cast<const uint32_t*>(deg), ustart, U, ustart + U, scan_tmp, scan_bytes,
+                             stream));
+  k_widen<<<grid_for(int64_t(U) + 1), GB_THREADS, 0, stream>>>(ustart, indptr, int64_t(U) + 1);
+  CGX_LAUNCH_CHECK();
+  uint64_t* sorted = key_ui;
+  CGX_TRY(radix_sort_u64(key_ui, alt, E, bits_u + bits_i, sort_tmp, sort_bytes, stream, &sorted));
+  if (E > 0) {
+    k_unpack_minor<<<grid_for(E), GB_THREADS, 0, stream>>>(sorted, E, bits_i, idx);
+    CGX_LAUNCH_CHECK();
+  }
+  return CGX_OK;
+}
+
+// ---- long rows ---------------------------------------------------------------------------------
+namespace cgx {
+__global__ void k_long_flags(const int64_t* __restrict__ indptr, int32_t n_rows, uint32_t* __restrict__ is_long,
+                             uint32_t* __restrict__ n_chunks) {
+  int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  int64_t len = indptr[r + 1] - indptr[r];
+  bool lg = len > CGX_LONG_ROW;
+  is_long[r] = lg ? 1u : 0u;
+  n_chunks[r] = lg ? uint32_t((len + CGX_CHUNK - 1) / CGX_CHUNK) : 0u;
+}
+__global__ void k_long_scatter(const int64_t* __restrict__ indptr, int32_t n_rows, const uint32_t* __restrict__ lpos,
+                               const uint32_t* __restrict__ cpos, const uint32_t* __restrict__ totals,
+                               int32_t* __restrict__ long_rows, int32_t* __restrict__ chunk_ptr) {
+  int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r == 0) chunk_ptr[totals[0]] = int32_t(totals[1]);
+  if (r >= n_rows) return;
+  if (indptr[r + 1] - indptr[r] > CGX_LONG_ROW) {
+    long_rows[lpos[r]] = int32_t(r);
+    chunk_ptr[lpos[r]] = int32_t(cpos[r]);
+  }
+}
+static int long_rows_scan(const int64_t* indptr, int32_t n_rows, void* workspace, size_t workspace_bytes,
+                          cudaStream_t stream, uint32_t** lpos, uint32_t** cpos, uint32_t** totals) {
+  Arena ws(workspace, workspace_bytes);
+  *lpos = ws.take<uint32_t>(n_rows);
+  *cpos = ws.take<uint32_t>(n_rows);
+  *totals = ws.take<uint32_t>(2);
+  size_t scan_bytes = scan_temp_bytes(n_rows);
+  void* scan_tmp = ws.take<char>(scan_bytes);
+  CGX_REQUIRE(ws.ok, CGX_ERR_WORKSPACE, "long_rows: workspace too small");
+  k_long_flags<<<grid_for(n_rows), GB_THREADS, 0, stream>>>(indptr, n_rows, *lpos, *cpos);
+  CGX_LAUNCH_CHECK();
+  CGX_TRY(exclusive_scan_u32(*lpos, *lpos, n_rows, *totals, scan_tmp, scan_bytes, stream));
+  CGX_TRY(exclusive_scan_u32(*cpos, *cpos, n_rows, *totals + 1, scan_tmp, scan_bytes, stream));
+  return CGX_OK;
+}
+}  // namespace cgx
+
+extern "C" size_t cgx_long_rows_workspace_bytes(int32_t n_rows) {
+  return 2 * align_up(size_t(n_rows) * 4) + 256 + scan_temp_bytes(n_rows) + 512;
+}
+
+extern "C" int cgx_long_rows_count(const int64_t* indptr, int32_t n_rows, int32_t* n_long_host,
+                                   int32_t* n_chunks_host, void* workspace, size_t workspace_bytes,
+                                   void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CGX_REQUIRE(indptr && n_rows > 0 && n_long_host && n_chunks_host, CGX_ERR_ARG, "long_rows_count: bad argument");
+  uint32_t *lpos, *cpos, *totals;
+  CGX_TRY(long_rows_scan(indptr, n_rows, workspace, workspace_bytes, stream, &lpos, &cpos, &totals));
+  uint32_t h[2];
+  CGX_CUDA(cudaMemcpyAsync(h, totals, 8, cudaMemcpyDeviceToHost, stream));
+  CGX_CUDA(cudaStreamSynchronize(stream));
+  *n_long_host = int32_t(h[0]);
+  *n_chunks_host = int32_t(h[1]);
+  return CGX_OK;
+}
+
+extern "C" int cgx_long_rows_fill(const int64_t* indptr, int32_t n_rows, int32_t n_long, int32_t* long_rows,
+                                  int32_t* chunk_ptr, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CGX_REQUIRE(indptr && n_rows > 0 && long_rows && chunk_ptr && n_long >= 0, CGX_ERR_ARG,
+              "long_rows_fill: bad argument");
+  uint32_t *lpos, *cpos, *totals;
+  CGX_TRY(long_rows_scan(indptr, n_rows, workspace, workspace_bytes, stream, &lpos, &cpos, &totals));
+  k_long_scatter<<<grid_for(n_rows), GB_THREADS, 0, stream>>>(indptr, n_rows, lpos, cpos, totals, long_rows,
+                                                             chunk_ptr);
+  CGX_LAUNCH_CHECK();
+  return CGX_OK;
+}

@@ -1,0 +1,211 @@
+"""Evaluation with the reference's entry points: the per-user Python loops of the reference
+become one device top-K (or candidate-scoring) call plus vectorised NumPy metrics.
+
+    metrics_at_k                 lightgcn_cu.py:469-484, Version-2/lighgcn_cu_pop.py:514-530
+    evaluate_sampled             lightgcn_cu.py:487-546, lighgcn_cu_pop.py:536-650
+    evaluate_full_ranking        lighgcn_cu_pop.py:653-752 (version_1/lightgcn_cu_message.py:535-585 short form)
+    compute_item_popularity / novelty_stats_for_items / make_cred_groups   lighgcn_cu_pop.py:382-423
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, config
+from ._lib import check, lib, ptr, stream_ptr, workspace
+from .sampler import user_has_item
+
+
+def metrics_at_k(ranked_items, gt_set, K):
+    topk = ranked_items[:K]
+    hits = [1 if int(x) in gt_set else 0 for x in topk]
+    n_hit = sum(hits)
+    dcg = sum(1.0 / math.log2(r + 2) for r, h in enumerate(hits) if h)
+    idcg = sum(1.0 / math.log2(r + 2) for r in range(min(len(gt_set), K)))
+    return n_hit / K, n_hit / max(len(gt_set), 1), (dcg / idcg) if idcg > 0 else 0.0
+
+
+def compute_item_popularity(train_edges_2xE: np.ndarray, num_items: int):
+    pop = np.bincount(np.asarray(train_edges_2xE[1], dtype=np.int64), minlength=num_items).astype(np.int64)
+    return pop, int(pop.sum())
+
+
+def novelty_stats_for_items(item_ids, pop: np.ndarray, total_train: int, num_items: int):
+    item_ids = np.asarray(item_ids, dtype=np.int64)
+    if item_ids.size == 0:
+        return 0.0, 0.0
+    p = pop[item_ids]
+    return float(np.log(p + 1.0).mean()), float((-np.log2((p + 1.0) / (total_train + num_items))).mean())
+
+
+def make_cred_groups(users: np.ndarray, cred: np.ndarray, pct: float):
+    if users.size == 0:
+        return np.array([], dtype=np.int64), np.array([], dtype=np.int64)
+    k = max(int(round(users.size * pct)), 1)
+    order = np.argsort(cred[users])
+    return users[order[-k:]].astype(np.int64), users[order[:k]].astype(np.int64)
+
+
+# ------------------------------------------------------------------------------------------
+def _device_csr(csr, device):
+    indptr, indices = csr
+    ip = torch.as_tensor(indptr).to(device=device, dtype=torch.int64).contiguous()
+    ix = torch.as_tensor(indices).to(device=device, dtype=torch.int32).contiguous()
+    if ix.numel() == 0:
+        ix = torch.zeros(1, dtype=torch.int32, device=device)
+    return ip, ix
+
+
+def topk_device(f_u, f_i, users, train_csr_dev, K: int, precision: str = "fp32"):
+    """ids int32[n, K], scores float32[n, K] for `users` (int64 CUDA tensor): train items masked to
+    -1e9, order = (score desc, item id asc)."""
+    dev = f_u.device
+    f_u, f_i = f_u.detach().contiguous(), f_i.detach().contiguous()
+    users = torch.as_tensor(users, device=dev).to(torch.int64).contiguous()
+    n, I, d = users.numel(), f_i.shape[0], f_i.shape[1]
+    ids = torch.empty(n, K, dtype=torch.int32, device=dev)
+    sc = torch.empty(n, K, dtype=torch.float32, device=dev)
+    ip, ix = train_csr_dev
+    prec = _lib.PRECISIONS[precision]
+    ws = workspace(lib().cgx_eval_topk_workspace_bytes(n, I, d, K, prec), dev)
+    with torch.cuda.device(dev):
+        check(lib().cgx_eval_topk(ptr(users), n, ptr(f_u), ptr(f_i), I, d, ptr(ip), ptr(ix), K, prec, ptr(ids),
+                                  ptr(sc), ptr(ws), ws.numel(), stream_ptr(dev)))
+    return ids, sc
+
+
+def score_candidates_device(f_u, f_i, users, cands):
+    dev = f_u.device
+    f_u, f_i = f_u.detach().contiguous(), f_i.detach().contiguous()
+    users = torch.as_tensor(users, device=dev).to(torch.int64).contiguous()
+    cands = torch.as_tensor(cands, device=dev).to(torch.int64).contiguous()
+    n, c = cands.shape
+    out = torch.empty(n, c, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().cgx_score_candidates(ptr(users), ptr(cands), n, c, f_i.shape[1], ptr(f_u), ptr(f_i), ptr(out),
+                                         stream_ptr(dev)))
+    return out
+
+
+def _hits_matrix(ranked: np.ndarray, users: np.ndarray, test_csr, num_items: int, gt_single=None) -> np.ndarray:
+    """hits[r, j] = ranked[r, j] is a ground-truth item of users[r]."""
+    if gt_single is not None:
+        return ranked == gt_single[:, None]
+    indptr, indices = test_csr
+    rows = np.repeat(np.arange(len(indptr) - 1, dtype=np.int64), np.diff(indptr))
+    keys = rows * num_items + np.asarray(indices, dtype=np.int64)         # sorted: CSR is (user, item) ordered
+    q = users[:, None].astype(np.int64) * num_items + ranked.astype(np.int64)
+    pos = np.searchsorted(keys, q)
+    pos = np.minimum(pos, max(keys.size - 1, 0))
+    return keys[pos] == q if keys.size else np.zeros_like(q, dtype=bool)
+
+
+def metrics_from_ranked(ranked: np.ndarray, users: np.ndarray, test_csr, num_items: int, Ks, mode: str,
+                        item_pop=None, total_train=0, cred_np=None, group_pct=0.20, gt_single=None, extra_keys=None):
+    """The reference's result dict from a [n_users, >=max(Ks)] matrix of ranked item ids."""
+    n = len(users)
+    hits = _hits_matrix(ranked[:, : max(Ks)], users, test_csr, num_items, gt_single)
+    n_gt = np.ones(n, np.int64) if gt_single is not None else np.diff(test_csr[0])[users]
+    disc = 1.0 / np.log2(np.arange(max(Ks)) + 2.0)
+    idcg_tab = np.concatenate([[0.0], np.cumsum(disc)])
+    extra = item_pop is not None and cred_np is not None
+    if extra:
+        hi, lo = make_cred_groups(users, cred_np, group_pct)
+        in_hi, in_lo = np.isin(users, hi), np.isin(users, lo)
+    out = {}
+    for K in Ks:
+        h = hits[:, :K]
+        nh = h.sum(1)
+        recall = nh / np.maximum(n_gt, 1)
+        idcg = idcg_tab[np.minimum(n_gt, K)]
+        ndcg = np.where(idcg > 0, (h * disc[:K]).sum(1) / np.where(idcg > 0, idcg, 1.0), 0.0)
+        res = {"precision": float((nh / K).mean()), "recall": float(recall.mean()), "ndcg": float(ndcg.mean())}
+        if extra:
+            top = ranked[:, :K].astype(np.int64)
+            p = item_pop[top].astype(np.float64)
+            res.update({
+                "item_coverage": np.unique(top).size / max(num_items, 1),
+                "avg_log_popularity": float(np.log(p + 1.0).mean(1).mean()),
+                "avg_self_information": float((-np.log2((p + 1.0) / (total_train + num_items))).mean(1).mean()),
+                "cred_utility": float(np.asarray(cred_np, np.float64)[users].mean()),
+                "high_cred_recall": float(recall[in_hi].sum() / max(int(in_hi.sum()), 1)),
+                "low_cred_recall": float(recall[in_lo].sum() / max(int(in_lo.sum()), 1)),
+                "high_users": int(in_hi.sum()), "low_users": int(in_lo.sum()),
+            })
+        res.update({"users_eval": n, "mode": mode})
+        if extra_keys:
+            res.update(extra_keys)
+        out[K] = res
+    return out
+
+
+def _final_tables(model):
+    with torch.no_grad():
+        return model.final_embeddings() if hasattr(model, "final_embeddings") else model.get_user_item_emb()
+
+
+@torch.no_grad()
+def evaluate_full_ranking(model, train_csr, test_csr, num_items: int, device=None, item_pop=None,
+                          total_train_interactions: int = 0, cred_np=None, precision: str | None = None):
+    """Full-catalogue ranking of every user with >= 1 test item; train items masked (val items
+    are NOT masked when testing, as in the reference, lighgcn_cu_pop.py:699-702)."""
+    cfg = config.cfg
+    f_u, f_i = _final_tables(model)
+    indptr_te = np.asarray(test_csr[0])
+    users = np.flatnonzero(np.diff(indptr_te) > 0).astype(np.int64)
+    if users.size == 0:
+        raise RuntimeError("No users with test interactions. Check your split or threshold.")
+    K = max(cfg.Ks)
+    ids, _ = topk_device(f_u, f_i, torch.from_numpy(users), _device_csr(train_csr, f_u.device), K,
+                         precision or cfg.score_precision)
+    ranked = ids.cpu().numpy()
+    return metrics_from_ranked(ranked, users, (indptr_te, np.asarray(test_csr[1])), num_items, cfg.Ks, "full",
+                               item_pop, total_train_interactions, cred_np, cfg.cred_group_pct)
+
+
+def sampled_candidates(train_csr, test_csr, num_items: int, n_neg: int, seed: int):
+    """Candidate lists of the sampled protocol, drawn exactly as the reference draws them
+    (default_rng(seed + 999), 1 test positive + n_neg negatives outside test U train;
+    lightgcn_cu.py:496-521) so that both sides rank identical candidates."""
+    indptr_tr, indices_tr = train_csr
+    indptr_te, indices_te = test_csr
+    rng = np.random.default_rng(seed + 999)
+    users = np.flatnonzero(np.diff(indptr_te) > 0).astype(np.int64)
+    cands = np.empty((users.size, 1 + n_neg), dtype=np.int64)
+    for r, u in enumerate(users):
+        gt = indices_te[indptr_te[u]:indptr_te[u + 1]]
+        gt_set = set(map(int, gt.tolist()))
+        cands[r, 0] = int(gt[rng.integers(0, len(gt))])
+        k = 1
+        while k <= n_neg:
+            j = int(rng.integers(0, num_items))
+            if j in gt_set or user_has_item(indptr_tr, indices_tr, int(u), j):
+                continue
+            cands[r, k] = j
+            k += 1
+    return users, cands
+
+
+@torch.no_grad()
+def evaluate_sampled(model, train_csr, test_csr, num_items: int, device=None, item_pop=None,
+                     total_train_interactions: int = 0, cred_np=None, candidates=None):
+    """1 positive + cfg.sampled_negatives negatives per test user, ranked by score.
+    `candidates=(users, cands)` injects a candidate list (parity tests)."""
+    cfg = config.cfg
+    f_u, f_i = _final_tables(model)
+    tr = (np.asarray(train_csr[0]), np.asarray(train_csr[1]))
+    te = (np.asarray(test_csr[0]), np.asarray(test_csr[1]))
+    if candidates is None:
+        users, cands = sampled_candidates(tr, te, num_items, cfg.sampled_negatives, cfg.seed)
+    else:
+        users, cands = candidates
+    if len(users) == 0:
+        raise RuntimeError("No users with test interactions.")
+    scores = score_candidates_device(f_u, f_i, torch.from_numpy(users), torch.from_numpy(cands)).cpu().numpy()
+    order = np.argsort(-scores, axis=1, kind="stable")
+    ranked = np.take_along_axis(cands, order, axis=1)
+    return metrics_from_ranked(ranked, users, te, num_items, cfg.Ks, "sampled(1pos+neg)", item_pop,
+                               total_train_interactions, cred_np, cfg.cred_group_pct, gt_single=cands[:, 0],
+                               extra_keys={"negatives": cfg.sampled_negatives})

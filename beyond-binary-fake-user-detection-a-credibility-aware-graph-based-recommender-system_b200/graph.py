@@ -1,0 +1,300 @@
+"""Graph build: the host-side mirror of the reference's builders over the device kernels.
+
+Reference surface kept (same names, argument meaning, return shapes):
+    edges_to_user_csr(edges_2xE, num_users)                         lightgcn_cu.py:259-276
+    build_cred_weighted_mats(train_edges, U, I, cred_u, device)     lightgcn_cu.py:368-399
+    build_message_passing_mats(train_edges, U, I, cred_u, device)   Version-2/lighgcn_cu_pop.py:429-452
+    build_message_passing_mats_degree_aware(...)                    version_1/lightgcn_cu_pop_Degree-Aware Message.py:349-403
+
+The reference returns two torch.sparse_coo tensors.  Here the two "matrices" are views
+(`Operator`) of one `CredGraph` living in HBM: one coalesced sparsity pattern held in both row
+orders with two value arrays each -- what the forward and the adjoint propagation need without
+ever transposing at run time.  `Operator` still answers `.indices()/.values()/.coalesce()/.shape`
+so that parity checks read like the reference's own code.
+
+HBM layout of a CredGraph (E = train edges incl. duplicates, nnz = distinct (u, i) pairs):
+    deg_u  int32[U], deg_i int32[I]
+    samp_indptr int64[U+1], samp_idx int32[E]        duplicate-keeping user rows (sampler, eval mask)
+    by_user: indptr int64[U+1], idx int32[nnz], val_fwd = A, val_bwd = C^T     float32[nnz]
+    by_item: indptr int64[I+1], idx int32[nnz], val_fwd = C, val_bwd = A^T     float32[nnz]
+    long-row lists per order (rows > 512 non-zeros, chunk table)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import CsrStruct, check, lib, ptr, stream_ptr, workspace
+
+
+def _as_device_edges(edges_2xE, device):
+    if isinstance(edges_2xE, torch.Tensor):
+        e = edges_2xE.to(device=device, dtype=torch.int32)
+    else:
+        a = np.asarray(edges_2xE)
+        if a.ndim != 2 or a.shape[0] != 2:
+            raise ValueError(f"edges must have shape [2, E], got {a.shape}")
+        e = torch.from_numpy(np.ascontiguousarray(a.astype(np.int32, copy=False))).to(device)
+    return e[0].contiguous(), e[1].contiguous()
+
+
+def _cuda_device(device) -> torch.device:
+    dev = torch.device(device if device is not None else "cuda")
+    if dev.type != "cuda":
+        raise _lib.CgxError(f"credgcn runs on CUDA devices only (got device={device!r}); there is no CPU fallback")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+@dataclass
+class Csr:
+    """One row order of the coalesced operator pattern (struct cgx_csr + the tensors it points at)."""
+    n_rows: int
+    n_cols: int
+    nnz: int
+    indptr: torch.Tensor
+    idx: torch.Tensor
+    val_fwd: torch.Tensor
+    val_bwd: torch.Tensor
+    long_rows: torch.Tensor | None = None
+    chunk_ptr: torch.Tensor | None = None
+    n_long: int = 0
+    n_chunks: int = 0
+    _struct: CsrStruct | None = field(default=None, repr=False)
+
+    def struct(self) -> CsrStruct:
+        if self._struct is None:
+            s = CsrStruct()
+            s.n_rows, s.n_cols, s.nnz = self.n_rows, self.n_cols, self.nnz
+            s.indptr, s.idx = self.indptr.data_ptr(), self.idx.data_ptr()
+            s.val_fwd, s.val_bwd = self.val_fwd.data_ptr(), self.val_bwd.data_ptr()
+            s.n_long, s.n_chunks = self.n_long, self.n_chunks
+            s.long_rows = self.long_rows.data_ptr() if self.n_long else None
+            s.chunk_ptr = self.chunk_ptr.data_ptr() if self.n_long else None
+            self._struct = s
+        return self._struct
+
+    def ref(self):
+        return C.byref(self.struct())
+
+    def find_long_rows(self):
+        dev = self.indptr.device
+        ws = workspace(lib().cgx_long_rows_workspace_bytes(self.n_rows), dev)
+        n_long, n_chunks = C.c_int32(0), C.c_int32(0)
+        with torch.cuda.device(dev):
+            check(lib().cgx_long_rows_count(ptr(self.indptr), self.n_rows, C.byref(n_long), C.byref(n_chunks),
+                                            ptr(ws), ws.numel(), stream_ptr(dev)))
+            self.n_long, self.n_chunks = int(n_long.value), int(n_chunks.value)
+            if self.n_long:
+                self.long_rows = torch.empty(self.n_long, dtype=torch.int32, device=dev)
+                self.chunk_ptr = torch.empty(self.n_long + 1, dtype=torch.int32, device=dev)
+                check(lib().cgx_long_rows_fill(ptr(self.indptr), self.n_rows, self.n_long, ptr(self.long_rows),
+                                               ptr(self.chunk_ptr), ptr(ws), ws.numel(), stream_ptr(dev)))
+        self._struct = None
+
+    def row_ids(self) -> torch.Tensor:
+        counts = (self.indptr[1:] - self.indptr[:-1])
+        return torch.repeat_interleave(torch.arange(self.n_rows, device=self.indptr.device), counts)
+
+
+class CredGraph:
+    """Device-resident graph: degrees, sampling CSR and both operator orders."""
+
+    def __init__(self, num_users, num_items, variant, device):
+        self.num_users, self.num_items, self.variant, self.device = int(num_users), int(num_items), variant, device
+        self.num_edges = 0
+        self.nnz = 0
+        self.deg_u = self.deg_i = None
+        self.samp_indptr = self.samp_idx = None
+        self.by_user: Csr | None = None
+        self.by_item: Csr | None = None
+        self._ws_cache: dict = {}
+
+    # operator views in the reference's vocabulary
+    def operator(self, which: str) -> "Operator":
+        return Operator(self, which)
+
+    def deg_i_float(self) -> np.ndarray:
+        """deg_i as the reference returns it: NumPy float32 (lightgcn_cu.py:384, 399)."""
+        return self.deg_i.cpu().numpy().astype(np.float32)
+
+    def user_csr_numpy(self):
+        return self.samp_indptr.cpu().numpy(), self.samp_idx.cpu().numpy().astype(np.int64)
+
+    def propagate_workspace(self, d: int) -> torch.Tensor:
+        key = ("prop", d)
+        if key not in self._ws_cache:
+            n = lib().cgx_propagate_workspace_bytes(self.by_user.ref(), self.by_item.ref(), d)
+            self._ws_cache[key] = workspace(n, self.device)
+        return self._ws_cache[key]
+
+
+class Operator:
+    """Quacks like the coalesced torch.sparse_coo tensor the reference builders return."""
+
+    def __init__(self, graph: CredGraph, which: str):
+        assert which in ("A", "C")
+        self.graph, self.which = graph, which
+
+    @property
+    def shape(self):
+        g = self.graph
+        return (g.num_users, g.num_items) if self.which == "A" else (g.num_items, g.num_users)
+
+    def size(self, dim=None):
+        return self.shape if dim is None else self.shape[dim]
+
+    def coalesce(self):
+        return self
+
+    def is_coalesced(self):
+        return True
+
+    def _csr(self) -> Csr:
+        return self.graph.by_user if self.which == "A" else self.graph.by_item
+
+    def indices(self) -> torch.Tensor:
+        c = self._csr()
+        return torch.stack([c.row_ids(), c.idx[: c.nnz].to(torch.int64)])
+
+    def values(self) -> torch.Tensor:
+        c = self._csr()
+        return c.val_fwd[: c.nnz]
+
+    def _nnz(self) -> int:
+        return self._csr().nnz
+
+    def to_sparse_coo(self) -> torch.Tensor:
+        return torch.sparse_coo_tensor(self.indices(), self.values(), size=self.shape).coalesce()
+
+    def __repr__(self):
+        return f"credgcn.Operator({self.which}, shape={self.shape}, nnz={self._nnz()}, variant={self.graph.variant})"
+
+
+def numpy_damping_alpha(deg_i: np.ndarray) -> np.ndarray:
+    """alpha_i = 1/log1p(max(deg_i, 1)) exactly as the reference evaluates it -- with NumPy on the
+    host (Degree-Aware Message.py:379-380); libdevice's log1pf differs in the last bit."""
+    return (np.float32(1.0) / np.log1p(np.maximum(deg_i.astype(np.float32), np.float32(1.0)))).astype(np.float32)
+
+
+def build_graph(train_edges_2xE, num_users: int, num_items: int, cred_u, variant: str = "v2",
+                device="cuda") -> CredGraph:
+    """Degrees + sampling CSR + both coalesced operators, all on device, bit-exact vs the reference."""
+    if variant not in _lib.VARIANTS:
+        raise ValueError(f"variant must be one of {sorted(_lib.VARIANTS)}")
+    dev = _cuda_device(device)
+    U, I = int(num_users), int(num_items)
+    eu, ei = _as_device_edges(train_edges_2xE, dev)
+    E = eu.numel()
+    if isinstance(cred_u, torch.Tensor):
+        cred = cred_u.detach().reshape(-1).to(device=dev, dtype=torch.float32).contiguous()
+    else:
+        cred = torch.from_numpy(np.ascontiguousarray(np.asarray(cred_u, dtype=np.float32))).to(dev)
+    if cred.numel() != U:
+        raise ValueError(f"cred_u has {cred.numel()} entries, expected num_users={U}")
+
+    g = CredGraph(U, I, variant, dev)
+    g.num_edges = E
+    i32 = dict(dtype=torch.int32, device=dev)
+    f32 = dict(dtype=torch.float32, device=dev)
+    i64 = dict(dtype=torch.int64, device=dev)
+    g.deg_u, g.deg_i = torch.empty(U, **i32), torch.empty(I, **i32)
+    g.samp_indptr, g.samp_idx = torch.empty(U + 1, **i64), torch.empty(max(E, 1), **i32)
+    u_indptr, u_idx = torch.empty(U + 1, **i64), torch.empty(max(E, 1), **i32)
+    u_vf, u_vb = torch.empty(max(E, 1), **f32), torch.empty(max(E, 1), **f32)
+    i_indptr, i_idx = torch.empty(I + 1, **i64), torch.empty(max(E, 1), **i32)
+    i_vf, i_vb = torch.empty(max(E, 1), **f32), torch.empty(max(E, 1), **f32)
+    counts = torch.zeros(2, **i64)
+    ws = workspace(lib().cgx_graph_build_workspace_bytes(E, U, I), dev)
+
+    def run(alpha, deg_only):
+        check(lib().cgx_graph_build(
+            ptr(eu), ptr(ei), E, U, I, ptr(cred), _lib.VARIANTS[variant], ptr(alpha), ptr(g.deg_u), ptr(g.deg_i),
+            ptr(g.samp_indptr), ptr(g.samp_idx), ptr(u_indptr), ptr(u_idx), ptr(u_vf), ptr(u_vb),
+            ptr(i_indptr), ptr(i_idx), ptr(i_vf), ptr(i_vb), ptr(counts), int(deg_only), ptr(ws), ws.numel(),
+            stream_ptr(dev)))
+
+    with torch.cuda.device(dev):
+        alpha = None
+        if variant == "da":
+            run(None, True)                       # degrees first; alpha needs NumPy's log1p
+            alpha = torch.from_numpy(numpy_damping_alpha(g.deg_i.cpu().numpy())).to(dev)
+        run(alpha, False)
+        nnz, bad = (int(x) for x in counts.cpu().tolist())
+    if bad:
+        raise ValueError(f"{bad} edges have a user id outside [0, {U}) or an item id outside [0, {I})")
+    g.nnz = nnz
+    g.samp_idx = g.samp_idx[:E]
+    g.by_user = Csr(U, I, nnz, u_indptr, u_idx[:max(nnz, 1)], u_vf[:max(nnz, 1)], u_vb[:max(nnz, 1)])
+    g.by_item = Csr(I, U, nnz, i_indptr, i_idx[:max(nnz, 1)], i_vf[:max(nnz, 1)], i_vb[:max(nnz, 1)])
+    if nnz < E:   # duplicates were merged: release the over-allocation
+        for c in (g.by_user, g.by_item):
+            c.idx, c.val_fwd, c.val_bwd = c.idx.clone(), c.val_fwd.clone(), c.val_bwd.clone()
+    g.by_user.find_long_rows()
+    g.by_item.find_long_rows()
+    g.alpha = alpha
+    return g
+
+
+def user_csr_device(edges_2xE, num_users: int, num_items: int | None = None, device="cuda"):
+    """edges_to_user_csr on device; returns (indptr int64[U+1], idx int32[E]) CUDA tensors."""
+    dev = _cuda_device(device)
+    eu, ei = _as_device_edges(edges_2xE, dev)
+    E = eu.numel()
+    if num_items is None:
+        num_items = int(ei.max().item()) + 1 if E else 1
+    indptr = torch.empty(num_users + 1, dtype=torch.int64, device=dev)
+    idx = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+    ws = workspace(lib().cgx_graph_build_workspace_bytes(E, num_users, num_items), dev)
+    with torch.cuda.device(dev):
+        check(lib().cgx_user_csr(ptr(eu), ptr(ei), E, num_users, num_items, ptr(indptr), ptr(idx), ptr(ws),
+                                 ws.numel(), stream_ptr(dev)))
+    return indptr, idx[:E]
+
+
+# ------------------------------------------------------------------------------------------
+# reference-named entry points
+# ------------------------------------------------------------------------------------------
+def edges_to_user_csr(edges_2xE, num_users: int, device="cuda"):
+    """Drop-in for lightgcn_cu.py:259: returns NumPy (indptr int64[U+1], indices int64[E])."""
+    indptr, idx = user_csr_device(edges_2xE, num_users, None, device)
+    return indptr.cpu().numpy(), idx.cpu().numpy().astype(np.int64)
+
+
+def build_cred_weighted_mats(train_edges, num_users, num_items, cred_u, device="cuda"):
+    """Drop-in for lightgcn_cu.py:368: returns (M_ui [I x U] credibility operator,
+    M_iu [U x I] base operator, deg_i float32 ndarray)."""
+    g = build_graph(train_edges, num_users, num_items, cred_u, "cu", device)
+    return g.operator("C"), g.operator("A"), g.deg_i_float()
+
+
+def build_message_passing_mats(train_edges_2xE, num_users, num_items, cred_u, device="cuda", degree_aware=False):
+    """Drop-in for Version-2/lighgcn_cu_pop.py:429 (and, with degree_aware=True, for the
+    Method-A builder at Degree-Aware Message.py:349): returns (M_ui [U x I] base operator,
+    M_iu [I x U] credibility operator) -- note the name swap against lightgcn_cu.py."""
+    g = build_graph(train_edges_2xE, num_users, num_items, cred_u, "da" if degree_aware else "v2", device)
+    if degree_aware:
+        deg = g.deg_i_float()
+        a = g.alpha.cpu().numpy()
+        print(f"[POP] item_deg: min={deg.min():.0f} max={deg.max():.0f} mean={deg.mean():.2f} "
+              f"nonzero={int(np.count_nonzero(deg))}/{num_items}")
+        print(f"[POP] alpha_i:  min={a.min():.6f} median={np.median(a):.6f} max={a.max():.6f}")
+    return g.operator("A"), g.operator("C")
+
+
+def build_message_passing_mats_degree_aware(train_edges_2xE, num_users, num_items, cred_u, device="cuda"):
+    return build_message_passing_mats(train_edges_2xE, num_users, num_items, cred_u, device, degree_aware=True)
+
+
+def graph_of(M_a, M_b) -> CredGraph:
+    """The CredGraph behind a pair of operator views (order-insensitive; both must share it)."""
+    if not (isinstance(M_a, Operator) and isinstance(M_b, Operator)):
+        raise TypeError("expected the two operators returned by a credgcn build_*_mats call")
+    if M_a.graph is not M_b.graph or {M_a.which, M_b.which} != {"A", "C"}:
+        raise ValueError("the two operators must be the A and C views of the same graph")
+    return M_a.graph

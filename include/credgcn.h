@@ -1,0 +1,226 @@
+/* credgcn.h -- C ABI of libcredgcn.so, the sm_100a implementation of the credibility-aware
+ * LightGCN hot path (graph build -> K-layer propagation fwd/bwd -> BPR step with
+ * popularity-aware negatives -> full-rank top-K evaluation).
+ *
+ * The reference (/root/reference, pure Python) has no FFI of its own: its de-facto boundary is
+ * "Python names in a script + torch.sparse.mm" (SURVEY.md section 8b).  Each entry point below names
+ * the reference code it replaces (file:line, CU = lightgcn_cu.py, V2 = Version-2/lighgcn_cu_pop.py,
+ * DA = version_1/lightgcn_cu_pop_Degree-Aware Message.py).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative cgx_status on failure; the message is
+ *     available from cgx_last_error() (thread-local);
+ *   - every pointer marked "device" is a CUDA device pointer owned by the caller; the library
+ *     never frees caller memory and keeps no global mutable state (re-entrant per stream);
+ *   - scratch space is caller-provided: ask the matching *_workspace_bytes() first;
+ *   - every op is asynchronous on the cudaStream_t passed as `stream` (a void* here so that the
+ *     header needs no CUDA include); there are no hidden synchronisations except where a
+ *     function documents a host-side result;
+ *   - a NULL device pointer where one is required is CGX_ERR_ARG; there is no CPU fallback.
+ *
+ * Operator naming (the reference swaps M_ui / M_iu between CU and V2, so neither name is used):
+ *     A : [U x I] user-row operator, base weight            (CU `M_iu`, V2 `M_ui`)
+ *     C : [I x U] item-row operator, credibility weighted   (CU `M_ui`, V2 `M_iu`)
+ */
+#ifndef CREDGCN_H_
+#define CREDGCN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  CGX_OK = 0,
+  CGX_ERR_ARG = -1,        /* bad argument (NULL pointer, unsupported emb_dim, size overflow) */
+  CGX_ERR_WORKSPACE = -2,  /* workspace too small */
+  CGX_ERR_CUDA = -3,       /* a CUDA runtime call or launch failed */
+  CGX_ERR_UNSUPPORTED = -4
+} cgx_status;
+
+typedef enum { CGX_VARIANT_CU = 0, CGX_VARIANT_V2 = 1, CGX_VARIANT_DA = 2 } cgx_variant;
+typedef enum { CGX_ORDER_JACOBI = 0, CGX_ORDER_GS = 1 } cgx_order;
+typedef enum { CGX_SCORE_FP32 = 0, CGX_SCORE_BF16X3 = 1, CGX_SCORE_BF16 = 2 } cgx_score_precision;
+
+const char* cgx_last_error(void);
+int cgx_version(void);
+/* Number of CUDA kernels this library has launched in this process (diagnostic tally). */
+uint64_t cgx_launch_count(void);
+/* Supported embedding widths: 16, 32, 64, 128, 256 (reference default emb_dim = 64, CU:53). */
+int cgx_emb_dim_supported(int32_t d);
+
+/* ------------------------------------------------------------------------------------------
+ * Graph build.  Replaces edges_to_user_csr (CU:259-276), build_cred_weighted_mats (CU:368-399),
+ * build_message_passing_mats (V2:429-452, DA:349-403): degree vectors, the user-row CSR used by
+ * samplers/evaluators (neighbours ascending, duplicates kept) and both coalesced operators in
+ * both orders.  Results are bit-exact against the reference's NumPy float32 arithmetic.
+ * ------------------------------------------------------------------------------------------ */
+
+/* One coalesced sparsity pattern in one row order with two value arrays.
+ *   by user rows (n_rows = U): val_fwd = A values, val_bwd = C^T values
+ *   by item rows (n_rows = I): val_fwd = C values, val_bwd = A^T values
+ * long_* describe rows with more than CGX_LONG_ROW non-zeros, which the SpMM splits into chunks. */
+typedef struct {
+  int32_t n_rows;
+  int32_t n_cols;
+  int64_t nnz;
+  const int64_t* indptr;     /* device, [n_rows + 1] */
+  const int32_t* idx;        /* device, [nnz] column ids, ascending inside a row */
+  const float* val_fwd;      /* device, [nnz] */
+  const float* val_bwd;      /* device, [nnz] */
+  int32_t n_long;            /* rows longer than CGX_LONG_ROW */
+  int32_t n_chunks;          /* total chunks over all long rows */
+  const int32_t* long_rows;  /* device, [n_long] row ids, ascending */
+  const int32_t* chunk_ptr;  /* device, [n_long + 1] first chunk of each long row */
+} cgx_csr;
+
+#define CGX_LONG_ROW 512   /* rows above this many non-zeros take the chunked path */
+#define CGX_CHUNK 2048     /* non-zeros per chunk on that path */
+
+size_t cgx_graph_build_workspace_bytes(int64_t num_edges, int32_t num_users, int32_t num_items);
+
+/* edges_u / edges_i: device int32[E] (the reference's on-disk int32 [2, E], CU:211).
+ * cred: device float32[U] already clipped to [0, 1] (CU:359).
+ * alpha: device float32[I], required for CGX_VARIANT_DA only: 1/log1p(max(deg_i,1)) computed with
+ *        the caller's NumPy (libdevice log1pf is not bit-identical to NumPy's; DA:379-380).
+ * Outputs (all device, caller-allocated):
+ *   deg_u int32[U], deg_i int32[I]                      np.bincount, duplicates counted
+ *   samp_indptr int64[U+1], samp_idx int32[E]           edges_to_user_csr
+ *   by_user:  indptr int64[U+1], idx int32[E], val_fwd/val_bwd float32[E]   (first nnz entries valid)
+ *   by_item:  indptr int64[I+1], idx int32[E], val_fwd/val_bwd float32[E]
+ *   nnz_out  int64[2]                                   [0] coalesced non-zero count (<= E),
+ *                                                       [1] number of out-of-range edges (must be 0)
+ * deg_only != 0 stops after the degree vectors (used to compute `alpha` for the DA variant). */
+int cgx_graph_build(const int32_t* edges_u, const int32_t* edges_i, int64_t num_edges,
+                    int32_t num_users, int32_t num_items, const float* cred, int variant,
+                    const float* alpha, int32_t* deg_u, int32_t* deg_i,
+                    int64_t* samp_indptr, int32_t* samp_idx,
+                    int64_t* user_indptr, int32_t* user_idx, float* user_val_fwd, float* user_val_bwd,
+                    int64_t* item_indptr, int32_t* item_idx, float* item_val_fwd, float* item_val_bwd,
+                    int64_t* nnz_out, int deg_only, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Only the user-row CSR of an edge list (val/test splits): edges_to_user_csr, CU:259-276. */
+int cgx_user_csr(const int32_t* edges_u, const int32_t* edges_i, int64_t num_edges, int32_t num_users,
+                 int32_t num_items, int64_t* indptr, int32_t* idx, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
+/* Rows longer than CGX_LONG_ROW: counts first (host results, synchronises `stream`), then lists. */
+int cgx_long_rows_count(const int64_t* indptr, int32_t n_rows, int32_t* n_long_host,
+                        int32_t* n_chunks_host, void* workspace, size_t workspace_bytes, void* stream);
+int cgx_long_rows_fill(const int64_t* indptr, int32_t n_rows, int32_t n_long, int32_t* long_rows,
+                       int32_t* chunk_ptr, void* workspace, size_t workspace_bytes, void* stream);
+size_t cgx_long_rows_workspace_bytes(int32_t n_rows);
+
+/* ------------------------------------------------------------------------------------------
+ * Propagation.  Replaces torch.sparse.mm + stack().mean() (CU:420-448, V2:472-490) and their
+ * autograd (CU:651, V2:862).  fp32, <= 1e-4 relative to the reference.
+ * ------------------------------------------------------------------------------------------ */
+
+/* One CSR SpMM with the fused epilogue, per output row r (y = sum_j val[j] * X[idx[j], :]):
+ *     if Y:       Y[r]       = y
+ *     if ACC_OUT: ACC_OUT[r] = acc_scale * (ACC_IN[r] + y)      (ACC_IN may be NULL -> 0; may alias ACC_OUT)
+ * The forward uses ACC for the running layer sum (last layer: acc_scale = 1/(K+1)); the backward
+ * uses it for "gradient seed + transposed product".  use_bwd_values selects val_bwd.
+ * workspace: cgx_spmm_workspace_bytes() (partials of the long-row chunks). */
+size_t cgx_spmm_workspace_bytes(const cgx_csr* m, int32_t d);
+int cgx_spmm(const cgx_csr* m, int use_bwd_values, int32_t d, const float* X, float* Y,
+             const float* ACC_IN, float* ACC_OUT, float acc_scale,
+             void* workspace, size_t workspace_bytes, void* stream);
+
+size_t cgx_propagate_workspace_bytes(const cgx_csr* by_user, const cgx_csr* by_item, int32_t d);
+
+/* Forward: final = mean over layers 0..K.  order JACOBI = CU:429-437, GS = V2:482-486.
+ * e0_u [U,d], e0_i [I,d] -> out_u [U,d], out_i [I,d].  Nothing is saved for backward (the
+ * operators are constants, so the adjoint needs only the output gradients). */
+int cgx_propagate_fwd(const cgx_csr* by_user, const cgx_csr* by_item, int order, int32_t num_layers,
+                      int32_t d, const float* e0_u, const float* e0_i, float* out_u, float* out_i,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward: (g_u, g_i) = dL/d(out_u, out_i) dense -> (d_e0_u, d_e0_i).  SURVEY.md appendix C. */
+int cgx_propagate_bwd(const cgx_csr* by_user, const cgx_csr* by_item, int order, int32_t num_layers,
+                      int32_t d, const float* g_u, const float* g_i, float* d_e0_u, float* d_e0_i,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * BPR + L2 (+ fairness) on a batch of (user, pos, neg) triples.  Replaces score / l2_reg / the loss
+ * assembly (CU:450-463, 635-648) and bpr_loss (V2:495-508) with their backward.
+ *   L = -mean(log(sigmoid(y+ - y-) + 1e-12)) + fair * mean(pop[pos] * y+)
+ *       + reg * mean(|e0_u[u]|^2 + |e0_i[p]|^2 + |e0_i[n]|^2)
+ * Gradients are scattered without atomics: the 3B (row, triple) pairs are sorted and each distinct
+ * row is summed by one thread group in triple order (deterministic).
+ *   g_u [U,d], g_i [I,d]   dL/d(propagated tables); must be zero-filled by the caller; only the
+ *                          rows named by the batch are written
+ *   ego_rows int32[3B], ego_coef float[3B]   compact L2 gradient: after the backward propagation
+ *                          add ego_coef[k] * e0[row] to d_e0 at row = ego_rows[k] for every k with
+ *                          ego_rows[k] >= 0 (rows >= U are items, offset by U; each row appears once)
+ *                          -- done by cgx_bpr_apply_ego
+ *   loss_out float[1]      NaN if any index of the batch was out of range
+ * ------------------------------------------------------------------------------------------ */
+size_t cgx_bpr_workspace_bytes(int64_t batch, int32_t num_users, int32_t num_items);
+int cgx_bpr_fwd_bwd(const int64_t* users, const int64_t* pos, const int64_t* neg, int64_t batch,
+                    int32_t num_users, int32_t num_items, int32_t d,
+                    const float* f_u, const float* f_i, const float* e0_u, const float* e0_i,
+                    const float* pop, float reg_weight, float fair_weight,
+                    float* loss_out, float* g_u, float* g_i,
+                    int32_t* ego_rows, float* ego_coef,
+                    void* workspace, size_t workspace_bytes, void* stream);
+int cgx_bpr_apply_ego(const int32_t* ego_rows, const float* ego_coef, int64_t n_entries,
+                      int32_t num_users, int32_t d, const float* e0_u, const float* e0_i,
+                      float* d_e0_u, float* d_e0_i, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Samplers.  Replace sample_pos_item / sample_neg_item (CU:288-299) and
+ * sample_neg_item_popmix with its popularity law (V2:349-376, 805-810).  Counter-based Philox4x32-10:
+ * the triple of batch slot k under (seed, offset) never depends on launch geometry.
+ * The popularity law p_i ~ (deg_i + 1)^gamma is held as an alias table over DEGREE CLASSES (all
+ * items of equal degree share one class) plus the item list ordered by degree -- the same
+ * distribution as an alias table over items, with a table small enough to stay cache resident.
+ * ------------------------------------------------------------------------------------------ */
+size_t cgx_sampler_build_workspace_bytes(int32_t num_items);
+/* Outputs (device): items_by_deg int32[I]; class_start int32[I+1], class_prob float[I],
+ * class_alias int32[I] (first n_classes entries valid); n_classes int32[1]. */
+int cgx_sampler_build(const int32_t* deg_i, int32_t num_items, double gamma,
+                      int32_t* items_by_deg, int32_t* class_start, float* class_prob,
+                      int32_t* class_alias, int32_t* n_classes,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* users int64[B]: batch users (each must own >= 1 train item, as CU:592 guarantees).
+ * mix_pop < 0 selects the uniform sampler of CU:295-299 (tables may then be NULL).
+ * After max_tries rejected proposals the kernel falls back to uniform proposals (V2:373-376). */
+int cgx_sample_triples(const int64_t* users, int64_t batch, const int64_t* samp_indptr,
+                       const int32_t* samp_idx, int32_t num_items,
+                       const int32_t* items_by_deg, const int32_t* class_start,
+                       const float* class_prob, const int32_t* class_alias, const int32_t* n_classes,
+                       float mix_pop, int32_t max_tries, uint64_t seed, uint64_t offset,
+                       int64_t* pos_out, int64_t* neg_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Full-rank evaluation.  Replaces the per-user loop of evaluate_full_ranking (V2:691-704):
+ * scores of `users` against every item, train items forced to -1e9, best K by
+ * (score desc, item id asc).  out_ids int32[n, K], out_scores float[n, K].
+ * ------------------------------------------------------------------------------------------ */
+size_t cgx_eval_topk_workspace_bytes(int64_t n_users, int32_t num_items, int32_t d, int32_t k,
+                                     int precision);
+int cgx_eval_topk(const int64_t* users, int64_t n_users, const float* f_u, const float* f_i,
+                  int32_t num_items, int32_t d, const int64_t* train_indptr, const int32_t* train_idx,
+                  int32_t k, int precision, int32_t* out_ids, float* out_scores,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Scores of explicit candidate lists (sampled protocol, CU:521-527): cand int64[n, C] ->
+ * scores float[n, C] = <f_u[users[r]], f_i[cand[r, c]]>. */
+int cgx_score_candidates(const int64_t* users, const int64_t* cand, int64_t n_users, int32_t n_cand,
+                         int32_t d, const float* f_u, const float* f_i, float* scores, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#endif /* CREDGCN_H_ */
