@@ -15,8 +15,8 @@ CSRC_DIR = PKG_DIR / "csrc"
 VARIANTS = {"cu": 0, "v2": 1, "da": 2}
 ORDERS = {"jacobi": 0, "gs": 1}
 PRECISIONS = {"fp32": 0, "bf16x3": 1, "bf16": 2}
-LONG_ROW = 512
-CHUNK = 2048
+LONG_ROW = 256
+CHUNK = 256
 
 
 class CgxError(RuntimeError):
@@ -28,7 +28,8 @@ class CsrStruct(C.Structure):
     _fields_ = [
         ("n_rows", C.c_int32), ("n_cols", C.c_int32), ("nnz", C.c_int64),
         ("indptr", C.c_void_p), ("idx", C.c_void_p), ("val_fwd", C.c_void_p), ("val_bwd", C.c_void_p),
-        ("n_long", C.c_int32), ("n_chunks", C.c_int32), ("long_rows", C.c_void_p), ("chunk_ptr", C.c_void_p),
+        ("perm", C.c_void_p), ("n_long", C.c_int32), ("n_chunks", C.c_int32),
+        ("chunk_ptr", C.c_void_p), ("chunk_row", C.c_void_p),
     ]
 
 
@@ -43,10 +44,10 @@ _SIGNATURES = {
     "cgx_graph_build": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int, _P, _P, _P, _P, _P,
                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P, C.c_size_t, _P]),
     "cgx_user_csr": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
-    "cgx_long_rows_workspace_bytes": (C.c_size_t, [C.c_int32]),
-    "cgx_long_rows_count": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P,
-                                      C.c_size_t, _P]),
-    "cgx_long_rows_fill": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
+    "cgx_row_schedule_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "cgx_row_schedule": (C.c_int, [_P, C.c_int32, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P,
+                                   C.c_size_t, _P]),
+    "cgx_row_schedule_chunks": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
     "cgx_spmm_workspace_bytes": (C.c_size_t, [_CSR, C.c_int32]),
     "cgx_spmm": (C.c_int, [_CSR, C.c_int, C.c_int32, _P, _P, _P, _P, C.c_float, _P, C.c_size_t, _P]),
     "cgx_propagate_workspace_bytes": (C.c_size_t, [_CSR, _CSR, C.c_int32]),

@@ -284,73 +284,107 @@ extern "C" int cgx_user_csr(const int32_t* edges_u, const int32_t* edges_i, int6
   return CGX_OK;
 }
 
-// ---- long rows ---------------------------------------------------------------------------------
+// ---- row schedule -------------------------------------------------------------------------------
+// The SpMM walks rows in DESCENDING degree order (perm): rows of similar length share a warp and a
+// CTA (no intra-block idling), and the expensive rows start first (no tail).  Rows longer than
+// CGX_LONG_ROW come first in perm and are cut into CGX_CHUNK-sized chunks, each a work item of its
+// own; their partial sums are combined in chunk order by a small finishing kernel.
 namespace cgx {
-__global__ void k_long_flags(const int64_t* __restrict__ indptr, int32_t n_rows, uint32_t* __restrict__ is_long,
-                             uint32_t* __restrict__ n_chunks) {
+__global__ void k_sched_keys(const int64_t* __restrict__ indptr, int32_t n_rows, int bits_r,
+                             uint64_t* __restrict__ keys) {
   int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (r >= n_rows) return;
-  int64_t len = indptr[r + 1] - indptr[r];
-  bool lg = len > CGX_LONG_ROW;
-  is_long[r] = lg ? 1u : 0u;
-  n_chunks[r] = lg ? uint32_t((len + CGX_CHUNK - 1) / CGX_CHUNK) : 0u;
+  const uint64_t deg = uint64_t(indptr[r + 1] - indptr[r]);
+  keys[r] = ((uint64_t(0x7fffffff) - deg) << bits_r) | uint64_t(r);   // ascending key = descending degree
 }
-__global__ void k_long_scatter(const int64_t* __restrict__ indptr, int32_t n_rows, const uint32_t* __restrict__ lpos,
-                               const uint32_t* __restrict__ cpos, const uint32_t* __restrict__ totals,
-                               int32_t* __restrict__ long_rows, int32_t* __restrict__ chunk_ptr) {
-  int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (r == 0) chunk_ptr[totals[0]] = int32_t(totals[1]);
-  if (r >= n_rows) return;
-  if (indptr[r + 1] - indptr[r] > CGX_LONG_ROW) {
-    long_rows[lpos[r]] = int32_t(r);
-    chunk_ptr[lpos[r]] = int32_t(cpos[r]);
+__global__ void k_sched_perm(const uint64_t* __restrict__ keys, const int64_t* __restrict__ indptr,
+                             int32_t n_rows, int bits_r, int32_t* __restrict__ perm,
+                             uint32_t* __restrict__ is_long, uint32_t* __restrict__ n_chunks) {
+  int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (k >= n_rows) return;
+  const int32_t r = int32_t(keys[k] & ((uint64_t(1) << bits_r) - 1));
+  perm[k] = r;
+  const int64_t len = indptr[r + 1] - indptr[r];
+  const bool lg = len > CGX_LONG_ROW;
+  is_long[k] = lg ? 1u : 0u;
+  n_chunks[k] = lg ? uint32_t((len + CGX_CHUNK - 1) / CGX_CHUNK) : 0u;
+}
+__global__ void k_sched_chunks(const uint32_t* __restrict__ cpos, const uint32_t* __restrict__ totals,
+                               int32_t n_long, int32_t* __restrict__ chunk_ptr, int32_t* __restrict__ chunk_row) {
+  // cpos = exclusive scan of chunk counts in perm order; long rows are exactly perm[0 .. n_long)
+  int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t n_ch = totals[1];
+  if (c <= n_long) chunk_ptr[c] = (c < n_long) ? int32_t(cpos[c]) : int32_t(n_ch);
+  if (c >= n_ch) return;
+  int lo = 0, hi = n_long;   // largest k with cpos[k] <= c
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (int64_t(cpos[mid]) <= c) lo = mid; else hi = mid;
   }
+  chunk_row[c] = lo;
 }
-static int long_rows_scan(const int64_t* indptr, int32_t n_rows, void* workspace, size_t workspace_bytes,
-                          cudaStream_t stream, uint32_t** lpos, uint32_t** cpos, uint32_t** totals) {
+struct SchedWs {
+  uint64_t *keys, *alt;
+  uint32_t *is_long, *cpos, *totals;
+  void *sort_tmp, *scan_tmp;
+  size_t sort_bytes, scan_bytes;
+};
+static size_t sched_ws_bytes(int32_t n_rows) {
+  return 2 * align_up(size_t(n_rows) * 8) + 2 * align_up(size_t(n_rows) * 4) + 256 + radix_sort_temp_bytes(n_rows) +
+         scan_temp_bytes(n_rows) + 1024;
+}
+static int sched_carve(void* workspace, size_t workspace_bytes, int32_t n_rows, SchedWs* w) {
   Arena ws(workspace, workspace_bytes);
-  *lpos = ws.take<uint32_t>(n_rows);
-  *cpos = ws.take<uint32_t>(n_rows);
-  *totals = ws.take<uint32_t>(2);
-  size_t scan_bytes = scan_temp_bytes(n_rows);
-  void* scan_tmp = ws.take<char>(scan_bytes);
-  CGX_REQUIRE(ws.ok, CGX_ERR_WORKSPACE, "long_rows: workspace too small");
-  k_long_flags<<<grid_for(n_rows), GB_THREADS, 0, stream>>>(indptr, n_rows, *lpos, *cpos);
-  CGX_LAUNCH_CHECK();
-  CGX_TRY(exclusive_scan_u32(*lpos, *lpos, n_rows, *totals, scan_tmp, scan_bytes, stream));
-  CGX_TRY(exclusive_scan_u32(*cpos, *cpos, n_rows, *totals + 1, scan_tmp, scan_bytes, stream));
+  w->keys = ws.take<uint64_t>(n_rows);
+  w->alt = ws.take<uint64_t>(n_rows);
+  w->is_long = ws.take<uint32_t>(n_rows);
+  w->cpos = ws.take<uint32_t>(n_rows);
+  w->totals = ws.take<uint32_t>(2);
+  w->sort_bytes = radix_sort_temp_bytes(n_rows);
+  w->sort_tmp = ws.take<char>(w->sort_bytes);
+  w->scan_bytes = scan_temp_bytes(n_rows);
+  w->scan_tmp = ws.take<char>(w->scan_bytes);
+  CGX_REQUIRE(ws.ok, CGX_ERR_WORKSPACE, "row_schedule: workspace too small");
   return CGX_OK;
 }
 }  // namespace cgx
 
-extern "C" size_t cgx_long_rows_workspace_bytes(int32_t n_rows) {
-  return 2 * align_up(size_t(n_rows) * 4) + 256 + scan_temp_bytes(n_rows) + 512;
-}
+extern "C" size_t cgx_row_schedule_workspace_bytes(int32_t n_rows) { return sched_ws_bytes(n_rows); }
 
-extern "C" int cgx_long_rows_count(const int64_t* indptr, int32_t n_rows, int32_t* n_long_host,
-                                   int32_t* n_chunks_host, void* workspace, size_t workspace_bytes,
-                                   void* stream_) {
+extern "C" int cgx_row_schedule(const int64_t* indptr, int32_t n_rows, int32_t* perm, int32_t* n_long_host,
+                                int32_t* n_chunks_host, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  CGX_REQUIRE(indptr && n_rows > 0 && n_long_host && n_chunks_host, CGX_ERR_ARG, "long_rows_count: bad argument");
-  uint32_t *lpos, *cpos, *totals;
-  CGX_TRY(long_rows_scan(indptr, n_rows, workspace, workspace_bytes, stream, &lpos, &cpos, &totals));
+  CGX_REQUIRE(indptr && n_rows > 0 && perm && n_long_host && n_chunks_host, CGX_ERR_ARG,
+              "row_schedule: bad argument");
+  SchedWs w;
+  CGX_TRY(sched_carve(workspace, workspace_bytes, n_rows, &w));
+  const int bits_r = bits_for(n_rows);
+  k_sched_keys<<<grid_for(n_rows), GB_THREADS, 0, stream>>>(indptr, n_rows, bits_r, w.keys);
+  CGX_LAUNCH_CHECK();
+  uint64_t* sorted = w.keys;
+  CGX_TRY(radix_sort_u64(w.keys, w.alt, n_rows, bits_r + 31, w.sort_tmp, w.sort_bytes, stream, &sorted));
+  k_sched_perm<<<grid_for(n_rows), GB_THREADS, 0, stream>>>(sorted, indptr, n_rows, bits_r, perm, w.is_long, w.cpos);
+  CGX_LAUNCH_CHECK();
+  CGX_TRY(exclusive_scan_u32(w.is_long, w.is_long, n_rows, w.totals, w.scan_tmp, w.scan_bytes, stream));
+  CGX_TRY(exclusive_scan_u32(w.cpos, w.cpos, n_rows, w.totals + 1, w.scan_tmp, w.scan_bytes, stream));
   uint32_t h[2];
-  CGX_CUDA(cudaMemcpyAsync(h, totals, 8, cudaMemcpyDeviceToHost, stream));
+  CGX_CUDA(cudaMemcpyAsync(h, w.totals, 8, cudaMemcpyDeviceToHost, stream));
   CGX_CUDA(cudaStreamSynchronize(stream));
   *n_long_host = int32_t(h[0]);
   *n_chunks_host = int32_t(h[1]);
   return CGX_OK;
 }
 
-extern "C" int cgx_long_rows_fill(const int64_t* indptr, int32_t n_rows, int32_t n_long, int32_t* long_rows,
-                                  int32_t* chunk_ptr, void* workspace, size_t workspace_bytes, void* stream_) {
+extern "C" int cgx_row_schedule_chunks(int32_t n_rows, int32_t n_long, int32_t n_chunks, int32_t* chunk_ptr,
+                                       int32_t* chunk_row, void* workspace, size_t workspace_bytes,
+                                       void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  CGX_REQUIRE(indptr && n_rows > 0 && long_rows && chunk_ptr && n_long >= 0, CGX_ERR_ARG,
-              "long_rows_fill: bad argument");
-  uint32_t *lpos, *cpos, *totals;
-  CGX_TRY(long_rows_scan(indptr, n_rows, workspace, workspace_bytes, stream, &lpos, &cpos, &totals));
-  k_long_scatter<<<grid_for(n_rows), GB_THREADS, 0, stream>>>(indptr, n_rows, lpos, cpos, totals, long_rows,
-                                                             chunk_ptr);
+  CGX_REQUIRE(n_rows > 0 && n_long > 0 && n_chunks > 0 && chunk_ptr && chunk_row, CGX_ERR_ARG,
+              "row_schedule_chunks: bad argument");
+  SchedWs w;   // same workspace, untouched since cgx_row_schedule: cpos / totals are still in place
+  CGX_TRY(sched_carve(workspace, workspace_bytes, n_rows, &w));
+  const int64_t n = n_chunks > n_long + 1 ? n_chunks : n_long + 1;
+  k_sched_chunks<<<grid_for(n), GB_THREADS, 0, stream>>>(w.cpos, w.totals, n_long, chunk_ptr, chunk_row);
   CGX_LAUNCH_CHECK();
   return CGX_OK;
 }

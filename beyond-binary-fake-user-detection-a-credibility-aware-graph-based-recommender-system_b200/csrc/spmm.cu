@@ -5,13 +5,17 @@
 // Version-2/lighgcn_cu_pop.py:483-484, the stack().mean() at lightgcn_cu.py:446-447 /
 // lighgcn_cu_pop.py:488-489, and autograd's SparseAddmmBackward for the same calls.
 //
-// Kernel shape: the path is an HBM/L2-bound gather.  A group of G = d/4 lanes owns one output row
-// (d=64: half a warp, two rows per warp; d=128: one warp); every lane keeps one float4 of the row
-// in registers, column ids/values are fetched coalesced G at a time and broadcast by shuffle, and
-// the embedding-row gathers are issued UNR at a time before any FMA so that each lane keeps UNR
-// independent 16-byte loads in flight.  Rows longer than CGX_LONG_ROW are split into CGX_CHUNK-
-// sized chunks handled by whole CTAs (partials in workspace, summed in chunk order => bitwise
-// reproducible, no atomics).
+// Kernel shape: the path is an HBM/L2-bound gather.  A group of G = d/4 lanes owns one work item
+// (d=64: half a warp, two items per warp; d=128: one warp); every lane keeps one float4 of the
+// output row in registers, column ids/values are fetched coalesced G at a time (the next batch is
+// prefetched while the current one is consumed) and broadcast by shuffle, and the embedding-row
+// gathers are issued UNR at a time before any FMA so that each lane keeps UNR independent 16-byte
+// loads in flight.
+// Work items follow the schedule built by cgx_row_schedule: first the CGX_CHUNK-sized chunks of the
+// rows longer than CGX_LONG_ROW (partials in workspace, summed in chunk order by a finishing
+// kernel), then all other rows in descending degree order.  Neighbouring groups therefore carry
+// equal work (no idle lanes inside a warp or CTA) and the heavy items start first (no tail).
+// No atomics anywhere: results are bitwise reproducible.
 #include "common.cuh"
 
 namespace cgx {
@@ -40,19 +44,25 @@ __device__ __forceinline__ unsigned group_mask() {
   return ((1u << (G & 31)) - 1u) << (lane & ~(G - 1));
 }
 
-// y[v] (v < V) += sum over nnz in [begin, end) of val * X[idx, :]; one group, lane = 0..G-1.
+// acc[v] (v < V) += sum over nnz in [begin, end) of val * X[idx, :]; one group, lane = 0..G-1.
 template <int G, int V>
 __device__ __forceinline__ void gather_range(const int32_t* __restrict__ idx, const float* __restrict__ val,
                                              int64_t begin, int64_t end, const float4* __restrict__ X, int lane,
                                              unsigned mask, float4 (&acc)[V]) {
   constexpr int ROW4 = G * V;  // float4 per embedding row
+  int32_t c_nxt = 0;
+  float w_nxt = 0.f;
+  if (begin + lane < end) {
+    c_nxt = __ldg(idx + begin + lane);
+    w_nxt = __ldg(val + begin + lane);
+  }
   for (int64_t base = begin; base < end; base += G) {
-    const int64_t p = base + lane;
-    int32_t c = 0;
-    float w = 0.f;
-    if (p < end) {
-      c = __ldg(idx + p);
-      w = __ldg(val + p);
+    const int32_t c = c_nxt;
+    const float w = w_nxt;
+    const int64_t pn = base + G + lane;  // prefetch the next batch of column ids / values
+    if (pn < end) {
+      c_nxt = __ldg(idx + pn);
+      w_nxt = __ldg(val + pn);
     }
     const int cnt = (end - base) < G ? int(end - base) : G;
     for (int j0 = 0; j0 < cnt; j0 += SP_UNR) {
@@ -60,7 +70,7 @@ __device__ __forceinline__ void gather_range(const int32_t* __restrict__ idx, co
       float ww[SP_UNR];
 #pragma unroll
       for (int t = 0; t < SP_UNR; ++t) {
-        const int j = j0 + t;                       // j < G always holds when G >= SP_UNR; guard otherwise
+        const int j = j0 + t;
         const int src = (j < G) ? j : (G - 1);
         const int32_t cj = __shfl_sync(mask, c, src, G);
         ww[t] = __shfl_sync(mask, w, src, G);
@@ -97,88 +107,77 @@ __device__ __forceinline__ void epilogue(int64_t row, int lane, const float4 (&y
   }
 }
 
-// one group per row; rows above CGX_LONG_ROW are left to the chunked path
+struct SpmmSched {
+  const int32_t* perm;
+  const int32_t* chunk_ptr;
+  const int32_t* chunk_row;
+  int32_t n_long, n_chunks;
+};
+
+// one group per work item: chunk items first, then rows in descending degree
 template <int G, int V>
-__global__ void __launch_bounds__(SP_THREADS) k_spmm_rows(const int64_t* __restrict__ indptr,
-                                                          const int32_t* __restrict__ idx,
-                                                          const float* __restrict__ val, int32_t n_rows,
-                                                          const float4* __restrict__ X, float4* __restrict__ Y,
-                                                          const float4* ACC_IN, float4* ACC_OUT, float acc_scale) {
+__global__ void __launch_bounds__(SP_THREADS) k_spmm(const int64_t* __restrict__ indptr,
+                                                     const int32_t* __restrict__ idx,
+                                                     const float* __restrict__ val, int32_t n_rows, SpmmSched sc,
+                                                     const float4* __restrict__ X, float4* __restrict__ Y,
+                                                     const float4* ACC_IN, float4* ACC_OUT, float acc_scale,
+                                                     float4* __restrict__ partial) {
+  constexpr int ROW4 = G * V;
   const int lane = threadIdx.x & (G - 1);
-  const int64_t row = (int64_t(blockIdx.x) * SP_THREADS + threadIdx.x) / G;
-  if (row >= n_rows) return;
+  const int64_t item = (int64_t(blockIdx.x) * SP_THREADS + threadIdx.x) / G;
   const unsigned mask = group_mask<G>();
-  const int64_t begin = __ldg(indptr + row), end = __ldg(indptr + row + 1);
-  if (end - begin > CGX_LONG_ROW) return;
   float4 acc[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (item < sc.n_chunks) {
+    const int32_t k = __ldg(sc.chunk_row + item);
+    const int32_t row = __ldg(sc.perm + k);
+    const int64_t rbeg = __ldg(indptr + row), rend = __ldg(indptr + row + 1);
+    const int64_t begin = rbeg + int64_t(int32_t(item) - __ldg(sc.chunk_ptr + k)) * CGX_CHUNK;
+    const int64_t end = begin + CGX_CHUNK < rend ? begin + CGX_CHUNK : rend;
+    gather_range<G, V>(idx, val, begin, end, X, lane, mask, acc);
+#pragma unroll
+    for (int v = 0; v < V; ++v) partial[item * ROW4 + v * G + lane] = acc[v];
+    return;
+  }
+  const int64_t r = item - sc.n_chunks + sc.n_long;
+  if (r >= n_rows) return;
+  const int32_t row = __ldg(sc.perm + r);
+  const int64_t begin = __ldg(indptr + row), end = __ldg(indptr + row + 1);
   gather_range<G, V>(idx, val, begin, end, X, lane, mask, acc);
   epilogue<G, V>(row, lane, acc, Y, ACC_IN, ACC_OUT, acc_scale);
 }
 
-// one CTA per chunk of a long row -> partial[chunk][d]
+// one CTA per long row: groups sum interleaved chunk partials, fixed-order reduction, epilogue
 template <int G, int V>
-__global__ void __launch_bounds__(SP_THREADS) k_spmm_long_partial(const int64_t* __restrict__ indptr,
-                                                                  const int32_t* __restrict__ idx,
-                                                                  const float* __restrict__ val,
-                                                                  const int32_t* __restrict__ long_rows,
-                                                                  const int32_t* __restrict__ chunk_ptr,
-                                                                  int32_t n_long, const float4* __restrict__ X,
-                                                                  float4* __restrict__ partial) {
+__global__ void __launch_bounds__(SP_THREADS) k_spmm_finish(SpmmSched sc, const float4* __restrict__ partial,
+                                                            float4* __restrict__ Y, const float4* ACC_IN,
+                                                            float4* ACC_OUT, float acc_scale) {
   constexpr int GROUPS = SP_THREADS / G;
   constexpr int ROW4 = G * V;
   __shared__ float4 red[GROUPS][ROW4];
-  const int chunk = blockIdx.x;
-  int lo = 0, hi = n_long;  // largest k with chunk_ptr[k] <= chunk
-  while (hi - lo > 1) {
-    int mid = (lo + hi) >> 1;
-    if (__ldg(chunk_ptr + mid) <= chunk) lo = mid; else hi = mid;
-  }
-  const int32_t row = __ldg(long_rows + lo);
-  const int64_t rbeg = __ldg(indptr + row), rend = __ldg(indptr + row + 1);
-  const int64_t cbeg = rbeg + int64_t(chunk - __ldg(chunk_ptr + lo)) * CGX_CHUNK;
-  const int64_t cend = (cbeg + CGX_CHUNK < rend) ? cbeg + CGX_CHUNK : rend;
+  const int k = blockIdx.x;
   const int lane = threadIdx.x & (G - 1), grp = threadIdx.x / G;
-  constexpr int PER = CGX_CHUNK / GROUPS;
-  int64_t gbeg = cbeg + int64_t(grp) * PER;
-  int64_t gend = gbeg + PER < cend ? gbeg + PER : cend;
-  if (gbeg > cend) gbeg = cend;
+  const int c0 = __ldg(sc.chunk_ptr + k), c1 = __ldg(sc.chunk_ptr + k + 1);
   float4 acc[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-  gather_range<G, V>(idx, val, gbeg, gend, X, lane, group_mask<G>(), acc);
+  for (int c = c0 + grp; c < c1; c += GROUPS) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = add4(acc[v], __ldg(partial + int64_t(c) * ROW4 + v * G + lane));
+  }
 #pragma unroll
   for (int v = 0; v < V; ++v) red[grp][v * G + lane] = acc[v];
   __syncthreads();
-  for (int o = threadIdx.x; o < ROW4; o += SP_THREADS) {
-    float4 s = red[0][o];
-#pragma unroll 4
-    for (int g = 1; g < GROUPS; ++g) s = add4(s, red[g][o]);
-    partial[int64_t(chunk) * ROW4 + o] = s;
-  }
-}
-
-// one group per long row: sum chunk partials in order, then the epilogue
-template <int G, int V>
-__global__ void __launch_bounds__(SP_THREADS) k_spmm_long_finish(const int32_t* __restrict__ long_rows,
-                                                                 const int32_t* __restrict__ chunk_ptr,
-                                                                 int32_t n_long, const float4* __restrict__ partial,
-                                                                 float4* __restrict__ Y, const float4* ACC_IN,
-                                                                 float4* ACC_OUT, float acc_scale) {
-  constexpr int ROW4 = G * V;
-  const int lane = threadIdx.x & (G - 1);
-  const int64_t k = (int64_t(blockIdx.x) * SP_THREADS + threadIdx.x) / G;
-  if (k >= n_long) return;
-  const int c0 = __ldg(chunk_ptr + k), c1 = __ldg(chunk_ptr + k + 1);
-  float4 acc[V];
+  if (grp == 0) {
 #pragma unroll
-  for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int c = c0; c < c1; ++c) {
-#pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = add4(acc[v], partial[int64_t(c) * ROW4 + v * G + lane]);
+    for (int v = 0; v < V; ++v) {
+      float4 s = red[0][v * G + lane];
+      for (int g = 1; g < GROUPS; ++g) s = add4(s, red[g][v * G + lane]);
+      acc[v] = s;
+    }
+    epilogue<G, V>(int64_t(__ldg(sc.perm + k)), lane, acc, Y, ACC_IN, ACC_OUT, acc_scale);
   }
-  epilogue<G, V>(int64_t(__ldg(long_rows + k)), lane, acc, Y, ACC_IN, ACC_OUT, acc_scale);
 }
 
 __global__ void k_scale(const float4* __restrict__ in, float4* __restrict__ out, int64_t n4, float s) {
@@ -191,23 +190,23 @@ static int launch_spmm(const cgx_csr* m, const float* val, const float* X, float
                        float* ACC_OUT, float acc_scale, void* workspace, size_t workspace_bytes,
                        cudaStream_t stream) {
   constexpr int GROUPS = SP_THREADS / G;
-  const unsigned grid = (unsigned)ceil_div(m->n_rows, GROUPS);
-  k_spmm_rows<G, V><<<grid, SP_THREADS, 0, stream>>>(
-      m->indptr, m->idx, val, m->n_rows, reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(Y),
-      reinterpret_cast<const float4*>(ACC_IN), reinterpret_cast<float4*>(ACC_OUT), acc_scale);
-  CGX_LAUNCH_CHECK();
+  float4* partial = nullptr;
   if (m->n_long > 0) {
     size_t need = size_t(m->n_chunks) * G * V * sizeof(float4);
     CGX_REQUIRE(workspace != nullptr && workspace_bytes >= need, CGX_ERR_WORKSPACE,
                 "spmm: workspace too small for %d long-row chunks", m->n_chunks);
-    float4* partial = static_cast<float4*>(workspace);
-    k_spmm_long_partial<G, V><<<(unsigned)m->n_chunks, SP_THREADS, 0, stream>>>(
-        m->indptr, m->idx, val, m->long_rows, m->chunk_ptr, m->n_long, reinterpret_cast<const float4*>(X),
-        partial);
-    CGX_LAUNCH_CHECK();
-    k_spmm_long_finish<G, V><<<(unsigned)ceil_div(m->n_long, GROUPS), SP_THREADS, 0, stream>>>(
-        m->long_rows, m->chunk_ptr, m->n_long, partial, reinterpret_cast<float4*>(Y),
-        reinterpret_cast<const float4*>(ACC_IN), reinterpret_cast<float4*>(ACC_OUT), acc_scale);
+    partial = static_cast<float4*>(workspace);
+  }
+  SpmmSched sc{m->perm, m->chunk_ptr, m->chunk_row, m->n_long, m->n_chunks};
+  const int64_t items = int64_t(m->n_chunks) + (m->n_rows - m->n_long);
+  k_spmm<G, V><<<(unsigned)ceil_div(items, GROUPS), SP_THREADS, 0, stream>>>(
+      m->indptr, m->idx, val, m->n_rows, sc, reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(Y),
+      reinterpret_cast<const float4*>(ACC_IN), reinterpret_cast<float4*>(ACC_OUT), acc_scale, partial);
+  CGX_LAUNCH_CHECK();
+  if (m->n_long > 0) {
+    k_spmm_finish<G, V><<<(unsigned)m->n_long, SP_THREADS, 0, stream>>>(
+        sc, partial, reinterpret_cast<float4*>(Y), reinterpret_cast<const float4*>(ACC_IN),
+        reinterpret_cast<float4*>(ACC_OUT), acc_scale);
     CGX_LAUNCH_CHECK();
   }
   return CGX_OK;
@@ -215,9 +214,9 @@ static int launch_spmm(const cgx_csr* m, const float* val, const float* X, float
 
 static int spmm_dispatch(const cgx_csr* m, int use_bwd, int32_t d, const float* X, float* Y, const float* ACC_IN,
                          float* ACC_OUT, float acc_scale, void* ws, size_t ws_bytes, cudaStream_t stream) {
-  CGX_REQUIRE(m && m->indptr && (m->nnz == 0 || (m->idx && m->val_fwd && m->val_bwd)) && X, CGX_ERR_ARG,
+  CGX_REQUIRE(m && m->indptr && m->perm && (m->nnz == 0 || (m->idx && m->val_fwd && m->val_bwd)) && X, CGX_ERR_ARG,
               "spmm: NULL pointer");
-  CGX_REQUIRE(m->n_long == 0 || (m->long_rows && m->chunk_ptr), CGX_ERR_ARG, "spmm: long-row lists missing");
+  CGX_REQUIRE(m->n_long == 0 || (m->chunk_ptr && m->chunk_row), CGX_ERR_ARG, "spmm: chunk tables missing");
   CGX_REQUIRE(Y || ACC_OUT, CGX_ERR_ARG, "spmm: no output requested");
   const float* val = use_bwd ? m->val_bwd : m->val_fwd;
   if (m->n_rows == 0) return CGX_OK;
@@ -250,10 +249,9 @@ extern "C" int cgx_spmm(const cgx_csr* m, int use_bwd_values, int32_t d, const f
 
 extern "C" size_t cgx_propagate_workspace_bytes(const cgx_csr* by_user, const cgx_csr* by_item, int32_t d) {
   if (!by_user || !by_item) return 0;
-  size_t rows = size_t(by_user->n_rows) + size_t(by_item->n_rows);
   size_t long_ws = spmm_ws(by_user, d) > spmm_ws(by_item, d) ? spmm_ws(by_user, d) : spmm_ws(by_item, d);
   return 2 * (align_up(size_t(by_user->n_rows) * d * 4) + align_up(size_t(by_item->n_rows) * d * 4)) + long_ws +
-         256 + 0 * rows;
+         256;
 }
 
 extern "C" int cgx_propagate_fwd(const cgx_csr* by_user, const cgx_csr* by_item, int order, int32_t K, int32_t d,

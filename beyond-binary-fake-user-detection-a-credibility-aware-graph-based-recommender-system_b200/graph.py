@@ -17,7 +17,7 @@ HBM layout of a CredGraph (E = train edges incl. duplicates, nnz = distinct (u, 
     samp_indptr int64[U+1], samp_idx int32[E]        duplicate-keeping user rows (sampler, eval mask)
     by_user: indptr int64[U+1], idx int32[nnz], val_fwd = A, val_bwd = C^T     float32[nnz]
     by_item: indptr int64[I+1], idx int32[nnz], val_fwd = C, val_bwd = A^T     float32[nnz]
-    long-row lists per order (rows > 512 non-zeros, chunk table)
+    work schedule per order: perm int32[n_rows] (degree-descending), chunk tables of rows > 256 nnz
 """
 from __future__ import annotations
 
@@ -61,8 +61,9 @@ class Csr:
     idx: torch.Tensor
     val_fwd: torch.Tensor
     val_bwd: torch.Tensor
-    long_rows: torch.Tensor | None = None
+    perm: torch.Tensor | None = None
     chunk_ptr: torch.Tensor | None = None
+    chunk_row: torch.Tensor | None = None
     n_long: int = 0
     n_chunks: int = 0
     _struct: CsrStruct | None = field(default=None, repr=False)
@@ -74,27 +75,30 @@ class Csr:
             s.indptr, s.idx = self.indptr.data_ptr(), self.idx.data_ptr()
             s.val_fwd, s.val_bwd = self.val_fwd.data_ptr(), self.val_bwd.data_ptr()
             s.n_long, s.n_chunks = self.n_long, self.n_chunks
-            s.long_rows = self.long_rows.data_ptr() if self.n_long else None
+            s.perm = self.perm.data_ptr()
             s.chunk_ptr = self.chunk_ptr.data_ptr() if self.n_long else None
+            s.chunk_row = self.chunk_row.data_ptr() if self.n_long else None
             self._struct = s
         return self._struct
 
     def ref(self):
         return C.byref(self.struct())
 
-    def find_long_rows(self):
+    def schedule(self):
+        """Degree-descending row order + chunk tables of the long rows (cgx_row_schedule)."""
         dev = self.indptr.device
-        ws = workspace(lib().cgx_long_rows_workspace_bytes(self.n_rows), dev)
+        ws = workspace(lib().cgx_row_schedule_workspace_bytes(self.n_rows), dev)
         n_long, n_chunks = C.c_int32(0), C.c_int32(0)
+        self.perm = torch.empty(self.n_rows, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
-            check(lib().cgx_long_rows_count(ptr(self.indptr), self.n_rows, C.byref(n_long), C.byref(n_chunks),
-                                            ptr(ws), ws.numel(), stream_ptr(dev)))
+            check(lib().cgx_row_schedule(ptr(self.indptr), self.n_rows, ptr(self.perm), C.byref(n_long),
+                                         C.byref(n_chunks), ptr(ws), ws.numel(), stream_ptr(dev)))
             self.n_long, self.n_chunks = int(n_long.value), int(n_chunks.value)
             if self.n_long:
-                self.long_rows = torch.empty(self.n_long, dtype=torch.int32, device=dev)
                 self.chunk_ptr = torch.empty(self.n_long + 1, dtype=torch.int32, device=dev)
-                check(lib().cgx_long_rows_fill(ptr(self.indptr), self.n_rows, self.n_long, ptr(self.long_rows),
-                                               ptr(self.chunk_ptr), ptr(ws), ws.numel(), stream_ptr(dev)))
+                self.chunk_row = torch.empty(self.n_chunks, dtype=torch.int32, device=dev)
+                check(lib().cgx_row_schedule_chunks(self.n_rows, self.n_long, self.n_chunks, ptr(self.chunk_ptr),
+                                                    ptr(self.chunk_row), ptr(ws), ws.numel(), stream_ptr(dev)))
         self._struct = None
 
     def row_ids(self) -> torch.Tensor:
@@ -235,8 +239,8 @@ def build_graph(train_edges_2xE, num_users: int, num_items: int, cred_u, variant
     if nnz < E:   # duplicates were merged: release the over-allocation
         for c in (g.by_user, g.by_item):
             c.idx, c.val_fwd, c.val_bwd = c.idx.clone(), c.val_fwd.clone(), c.val_bwd.clone()
-    g.by_user.find_long_rows()
-    g.by_item.find_long_rows()
+    g.by_user.schedule()
+    g.by_item.schedule()
     g.alpha = alpha
     return g
 

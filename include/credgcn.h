@@ -65,7 +65,8 @@ int cgx_emb_dim_supported(int32_t d);
 /* One coalesced sparsity pattern in one row order with two value arrays.
  *   by user rows (n_rows = U): val_fwd = A values, val_bwd = C^T values
  *   by item rows (n_rows = I): val_fwd = C values, val_bwd = A^T values
- * long_* describe rows with more than CGX_LONG_ROW non-zeros, which the SpMM splits into chunks. */
+ * perm / chunk_* are the SpMM work schedule (cgx_row_schedule): rows in descending degree order;
+ * the first n_long of them exceed CGX_LONG_ROW non-zeros and are cut into CGX_CHUNK-sized chunks. */
 typedef struct {
   int32_t n_rows;
   int32_t n_cols;
@@ -74,14 +75,15 @@ typedef struct {
   const int32_t* idx;        /* device, [nnz] column ids, ascending inside a row */
   const float* val_fwd;      /* device, [nnz] */
   const float* val_bwd;      /* device, [nnz] */
-  int32_t n_long;            /* rows longer than CGX_LONG_ROW */
+  const int32_t* perm;       /* device, [n_rows] row ids, descending degree (ties: ascending id) */
+  int32_t n_long;            /* rows longer than CGX_LONG_ROW = perm[0 .. n_long) */
   int32_t n_chunks;          /* total chunks over all long rows */
-  const int32_t* long_rows;  /* device, [n_long] row ids, ascending */
-  const int32_t* chunk_ptr;  /* device, [n_long + 1] first chunk of each long row */
+  const int32_t* chunk_ptr;  /* device, [n_long + 1] first chunk of each long row (perm order) */
+  const int32_t* chunk_row;  /* device, [n_chunks] position in perm of the row a chunk belongs to */
 } cgx_csr;
 
-#define CGX_LONG_ROW 512   /* rows above this many non-zeros take the chunked path */
-#define CGX_CHUNK 2048     /* non-zeros per chunk on that path */
+#define CGX_LONG_ROW 256   /* rows above this many non-zeros are split */
+#define CGX_CHUNK 256      /* non-zeros per chunk of a split row */
 
 size_t cgx_graph_build_workspace_bytes(int64_t num_edges, int32_t num_users, int32_t num_items);
 
@@ -110,12 +112,16 @@ int cgx_user_csr(const int32_t* edges_u, const int32_t* edges_i, int64_t num_edg
                  int32_t num_items, int64_t* indptr, int32_t* idx, void* workspace,
                  size_t workspace_bytes, void* stream);
 
-/* Rows longer than CGX_LONG_ROW: counts first (host results, synchronises `stream`), then lists. */
-int cgx_long_rows_count(const int64_t* indptr, int32_t n_rows, int32_t* n_long_host,
-                        int32_t* n_chunks_host, void* workspace, size_t workspace_bytes, void* stream);
-int cgx_long_rows_fill(const int64_t* indptr, int32_t n_rows, int32_t n_long, int32_t* long_rows,
-                       int32_t* chunk_ptr, void* workspace, size_t workspace_bytes, void* stream);
-size_t cgx_long_rows_workspace_bytes(int32_t n_rows);
+/* SpMM work schedule of one row order.  cgx_row_schedule sorts rows by descending degree into
+ * perm int32[n_rows] and returns (host results; synchronises `stream`) how many rows exceed
+ * CGX_LONG_ROW and how many chunks they make; cgx_row_schedule_chunks then fills
+ * chunk_ptr int32[n_long+1] / chunk_row int32[n_chunks] -- call it with the SAME workspace, untouched
+ * in between, and only when n_long > 0. */
+size_t cgx_row_schedule_workspace_bytes(int32_t n_rows);
+int cgx_row_schedule(const int64_t* indptr, int32_t n_rows, int32_t* perm, int32_t* n_long_host,
+                     int32_t* n_chunks_host, void* workspace, size_t workspace_bytes, void* stream);
+int cgx_row_schedule_chunks(int32_t n_rows, int32_t n_long, int32_t n_chunks, int32_t* chunk_ptr,
+                            int32_t* chunk_row, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Propagation.  Replaces torch.sparse.mm + stack().mean() (CU:420-448, V2:472-490) and their
