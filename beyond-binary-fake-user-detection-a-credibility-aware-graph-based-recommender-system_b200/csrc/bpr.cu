@@ -6,9 +6,12 @@
 // backward autograd runs for them.
 //
 // Scatter scheme: every triple t contributes to three rows (user u, item pos, item neg).  The 3B
-// (row, entry) pairs are packed into 64-bit keys and radix sorted; one thread group per distinct
-// row then walks its run in entry order and writes the row once.  Entry order is fixed by the
-// sort, so the result is bitwise reproducible.
+// (row, entry) pairs are packed into 64-bit keys and sorted by row (cgx_bpr_plan: a stable
+// shared-memory radix sort inside ONE CTA for batches up to 4096 triples, the global radix sort
+// above that); one thread group per distinct row then walks its run in entry order and writes
+// the row once.  Entry order is fixed by the stable sort, so the result is bitwise reproducible.
+// The plan depends on the indices only, so callers may build it on a side stream while the
+// forward propagation runs.
 #include "common.cuh"
 
 namespace cgx {
@@ -33,6 +36,111 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
   return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
 }
 
+__device__ __forceinline__ int64_t clamp_id(int64_t x, int64_t n) { return (x < 0 || x >= n) ? 0 : x; }
+
+// key of entry e (0..3B): row in the high bits (items offset by U), entry id in the low bits
+__device__ __forceinline__ uint64_t plan_key(const int64_t* __restrict__ users, const int64_t* __restrict__ pos,
+                                             const int64_t* __restrict__ neg, int64_t B, int32_t U, int32_t I,
+                                             int entry_bits, int64_t e) {
+  const int type = int(e / B);
+  const int64_t t = e - int64_t(type) * B;
+  const int64_t row = type == 0 ? clamp_id(users[t], U) : int64_t(U) + clamp_id(type == 1 ? pos[t] : neg[t], I);
+  return (uint64_t(row) << entry_bits) | uint64_t(e);
+}
+
+__global__ void k_plan_keys(const int64_t* __restrict__ users, const int64_t* __restrict__ pos,
+                            const int64_t* __restrict__ neg, int64_t B, int32_t U, int32_t I, int entry_bits,
+                            uint64_t* __restrict__ keys) {
+  const int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e < 3 * B) keys[e] = plan_key(users, pos, neg, B, U, I, entry_bits, e);
+}
+
+// ---- single-CTA stable radix sort of up to PS_MAX keys on the row bits -------------------------
+constexpr int PS_THREADS = 1024;
+constexpr int PS_WARPS = PS_THREADS / 32;
+constexpr int PS_STEPS = 12;
+constexpr int PS_MAX = PS_THREADS * PS_STEPS;  // 12288 keys = 3 * 4096
+
+__global__ void __launch_bounds__(PS_THREADS, 1) k_plan_small(const int64_t* __restrict__ users,
+                                                              const int64_t* __restrict__ pos,
+                                                              const int64_t* __restrict__ neg, int64_t B, int32_t U,
+                                                              int32_t I, int entry_bits, int row_bits,
+                                                              uint64_t* __restrict__ sorted) {
+  extern __shared__ __align__(16) unsigned char ps_smem[];
+  uint64_t* buf0 = reinterpret_cast<uint64_t*>(ps_smem);
+  uint64_t* buf1 = buf0 + PS_MAX;
+  uint16_t(*cnt)[256] = reinterpret_cast<uint16_t(*)[256]>(buf1 + PS_MAX);  // [PS_WARPS][256]
+  uint32_t* tot = reinterpret_cast<uint32_t*>(cnt + PS_WARPS);              // [256]
+  const int n = int(3 * B);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  for (int e = threadIdx.x; e < n; e += PS_THREADS) buf0[e] = plan_key(users, pos, neg, B, U, I, entry_bits, e);
+  __syncthreads();
+  uint64_t* src = buf0;
+  uint64_t* dst = buf1;
+  const int wbase = warp * (PS_STEPS * 32);
+  for (int shift = entry_bits; shift < entry_bits + row_bits; shift += 8) {
+    for (int b = lane; b < 256; b += 32) cnt[warp][b] = 0;
+    __syncwarp();
+    uint64_t key[PS_STEPS];
+#pragma unroll
+    for (int j = 0; j < PS_STEPS; ++j) {
+      const int p = wbase + j * 32 + lane;
+      const bool valid = p < n;
+      key[j] = valid ? src[p] : 0ull;
+      const uint32_t d = valid ? uint32_t((key[j] >> shift) & 0xff) : 256u;
+      const uint32_t m = __match_any_sync(0xffffffffu, d);
+      if (valid && (m & lt) == 0) cnt[warp][d] += uint16_t(__popc(m));
+      __syncwarp();
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) {  // digit totals, and per-warp exclusive prefix inside the digit
+      uint32_t run = 0;
+#pragma unroll 8
+      for (int w = 0; w < PS_WARPS; ++w) {
+        const uint32_t c = cnt[w][threadIdx.x];
+        cnt[w][threadIdx.x] = uint16_t(run);
+        run += c;
+      }
+      tot[threadIdx.x] = run;
+    }
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan of the 256 digit totals: 8 per lane
+      uint32_t v[8], s = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { v[q] = tot[lane * 8 + q]; s += v[q]; }
+      uint32_t inc = s;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      uint32_t ex = inc - s;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { tot[lane * 8 + q] = ex; ex += v[q]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PS_STEPS; ++j) {
+      const int p = wbase + j * 32 + lane;
+      const bool valid = p < n;
+      const uint32_t d = valid ? uint32_t((key[j] >> shift) & 0xff) : 256u;
+      const uint32_t m = __match_any_sync(0xffffffffu, d);
+      uint32_t q = 0;
+      if (valid) q = tot[d] + cnt[warp][d] + __popc(m & lt);
+      __syncwarp();
+      if (valid && (m & lt) == 0) cnt[warp][d] += uint16_t(__popc(m));
+      __syncwarp();
+      if (valid) dst[q] = key[j];
+    }
+    __syncthreads();
+    uint64_t* t = src; src = dst; dst = t;
+  }
+  for (int e = threadIdx.x; e < n; e += PS_THREADS) sorted[e] = src[e];
+}
+
+static size_t plan_small_smem() { return size_t(2) * PS_MAX * 8 + size_t(PS_WARPS) * 256 * 2 + 256 * 4; }
+
 struct BprArgs {
   const int64_t* users;
   const int64_t* pos;
@@ -47,12 +155,11 @@ struct BprArgs {
   float reg, fair;
 };
 
-// per triple: scores, loss term, coefficients, and the three sort keys
+// per triple: scores, loss term, coefficients
 template <int G, int V>
-__global__ void __launch_bounds__(BP_THREADS) k_bpr_triple(BprArgs a, int entry_bits, float* __restrict__ coef_pos,
+__global__ void __launch_bounds__(BP_THREADS) k_bpr_triple(BprArgs a, float* __restrict__ coef_pos,
                                                            float* __restrict__ coef_neg,
                                                            float* __restrict__ loss_term,
-                                                           uint64_t* __restrict__ keys,
                                                            unsigned long long* __restrict__ bad) {
   constexpr int ROW4 = G * V;
   const int lane = threadIdx.x & (G - 1);
@@ -62,7 +169,7 @@ __global__ void __launch_bounds__(BP_THREADS) k_bpr_triple(BprArgs a, int entry_
   int64_t u = a.users[t], p = a.pos[t], n = a.neg[t];
   if (u < 0 || u >= a.U || p < 0 || p >= a.I || n < 0 || n >= a.I) {
     if (lane == 0) atomicAdd(bad, 1ull);
-    u = 0; p = 0; n = 0;
+    u = clamp_id(u, a.U); p = clamp_id(p, a.I); n = clamp_id(n, a.I);
   }
   float yp = 0.f, yn = 0.f, l2 = 0.f;
 #pragma unroll
@@ -91,10 +198,6 @@ __global__ void __launch_bounds__(BP_THREADS) k_bpr_triple(BprArgs a, int entry_
     coef_pos[t] = gx + pw * invB;
     coef_neg[t] = -gx;
     loss_term[t] = (term + pw * yp + a.reg * l2) * invB;
-    const uint64_t B = uint64_t(a.B);
-    keys[t] = (uint64_t(u) << entry_bits) | uint64_t(t);
-    keys[B + t] = (uint64_t(a.U + p) << entry_bits) | (B + uint64_t(t));
-    keys[2 * B + t] = (uint64_t(a.U + n) << entry_bits) | (2 * B + uint64_t(t));
   }
 }
 
@@ -128,14 +231,12 @@ __global__ void __launch_bounds__(BP_THREADS) k_bpr_scatter(BprArgs a, int entry
     const uint64_t kq = keys[q];
     if (int64_t(kq >> entry_bits) != row) break;
     const int64_t e = int64_t(kq & emask);
-    const int64_t t = e % a.B;
     const int type = int(e / a.B);
+    const int64_t t = e - int64_t(type) * a.B;
     ++mult;
     if (type == 0) {  // user row: cp * f_i[pos] + cn * f_i[neg]
       const float cp = coef_pos[t], cn = coef_neg[t];
-      int64_t p = a.pos[t], ng = a.neg[t];
-      if (p < 0 || p >= a.I) p = 0;      // flagged by k_bpr_triple; keep the gather in bounds
-      if (ng < 0 || ng >= a.I) ng = 0;
+      const int64_t p = clamp_id(a.pos[t], a.I), ng = clamp_id(a.neg[t], a.I);
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         const float4 fp = __ldg(a.f_i + p * ROW4 + v * G + lane);
@@ -147,8 +248,7 @@ __global__ void __launch_bounds__(BP_THREADS) k_bpr_scatter(BprArgs a, int entry
       }
     } else {  // item row: coefficient * f_u[user]
       const float c = type == 1 ? coef_pos[t] : coef_neg[t];
-      int64_t u = a.users[t];
-      if (u < 0 || u >= a.U) u = 0;
+      const int64_t u = clamp_id(a.users[t], a.U);
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         const float4 fu = __ldg(a.f_u + u * ROW4 + v * G + lane);
@@ -168,8 +268,9 @@ __global__ void __launch_bounds__(BP_THREADS) k_bpr_scatter(BprArgs a, int entry
   }
 }
 
-// deterministic sum of B terms by one CTA (fixed tree)
+// deterministic sum of B terms by one CTA (fixed tree); NaN if any index was out of range
 __global__ void __launch_bounds__(1024) k_sum_terms(const float* __restrict__ terms, int64_t n,
+                                                    const unsigned long long* __restrict__ bad,
                                                     float* __restrict__ out) {
   __shared__ double sh[1024];
   double s = 0.0;
@@ -180,7 +281,7 @@ __global__ void __launch_bounds__(1024) k_sum_terms(const float* __restrict__ te
     if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) *out = float(sh[0]);
+  if (threadIdx.x == 0) *out = (*bad != 0ull) ? __int_as_float(0x7fc00000) : float(sh[0]);
 }
 
 template <int G, int V>
@@ -207,45 +308,33 @@ __global__ void __launch_bounds__(BP_THREADS) k_apply_ego(const int32_t* __restr
   }
 }
 
-__global__ void k_check_bad(const unsigned long long* bad, float* loss_out) {
-  if (*bad != 0ull) *loss_out = __int_as_float(0x7fc00000);  // NaN: an index was out of range
-}
-
-static size_t bpr_ws(int64_t B) {
+static size_t plan_ws(int64_t B) {
   const int64_t n = 3 * B;
-  return 2 * align_up(size_t(n) * 8) + 3 * align_up(size_t(B) * 4) + radix_sort_temp_bytes(n) + 512;
+  if (n <= PS_MAX) return 256;
+  return align_up(size_t(n) * 8) + radix_sort_temp_bytes(n) + 256;
 }
+static size_t bpr_ws(int64_t B) { return 3 * align_up(size_t(B) * 4) + 512; }
 
 template <int G, int V>
-static int bpr_run(const BprArgs& a, float* loss_out, float* g_u, float* g_i, int32_t* ego_rows, float* ego_coef,
-                   void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+static int bpr_run(const BprArgs& a, const uint64_t* plan, float* loss_out, float* g_u, float* g_i,
+                   int32_t* ego_rows, float* ego_coef, void* workspace, size_t workspace_bytes,
+                   cudaStream_t stream) {
   const int64_t B = a.B, n = 3 * B;
   Arena ws(workspace, workspace_bytes);
-  uint64_t* keys = ws.take<uint64_t>(n);
-  uint64_t* alt = ws.take<uint64_t>(n);
   float* coef_pos = ws.take<float>(B);
   float* coef_neg = ws.take<float>(B);
   float* terms = ws.take<float>(B);
-  size_t sort_bytes = radix_sort_temp_bytes(n);
-  void* sort_tmp = ws.take<char>(sort_bytes);
   unsigned long long* bad = ws.take<unsigned long long>(1);
   CGX_REQUIRE(ws.ok, CGX_ERR_WORKSPACE, "bpr: workspace too small");
-  const int entry_bits = bits_for(n);
-  const int row_bits = bits_for(int64_t(a.U) + a.I);
   constexpr int GROUPS = BP_THREADS / G;
   CGX_CUDA(cudaMemsetAsync(bad, 0, 8, stream));
-  k_bpr_triple<G, V><<<(unsigned)ceil_div(B, GROUPS), BP_THREADS, 0, stream>>>(a, entry_bits, coef_pos, coef_neg,
-                                                                             terms, keys, bad);
+  k_bpr_triple<G, V><<<(unsigned)ceil_div(B, GROUPS), BP_THREADS, 0, stream>>>(a, coef_pos, coef_neg, terms, bad);
   CGX_LAUNCH_CHECK();
-  uint64_t* sorted = keys;
-  CGX_TRY(radix_sort_u64(keys, alt, n, entry_bits + row_bits, sort_tmp, sort_bytes, stream, &sorted));
   k_bpr_scatter<G, V><<<(unsigned)ceil_div(n, GROUPS), BP_THREADS, 0, stream>>>(
-      a, entry_bits, sorted, coef_pos, coef_neg, reinterpret_cast<float4*>(g_u), reinterpret_cast<float4*>(g_i),
+      a, bits_for(n), plan, coef_pos, coef_neg, reinterpret_cast<float4*>(g_u), reinterpret_cast<float4*>(g_i),
       ego_rows, ego_coef);
   CGX_LAUNCH_CHECK();
-  k_sum_terms<<<1, 1024, 0, stream>>>(terms, B, loss_out);
-  CGX_LAUNCH_CHECK();
-  k_check_bad<<<1, 1, 0, stream>>>(bad, loss_out);
+  k_sum_terms<<<1, 1024, 0, stream>>>(terms, B, bad, loss_out);
   CGX_LAUNCH_CHECK();
   return CGX_OK;
 }
@@ -254,15 +343,48 @@ static int bpr_run(const BprArgs& a, float* loss_out, float* g_u, float* g_i, in
 
 using namespace cgx;
 
+extern "C" size_t cgx_bpr_plan_workspace_bytes(int64_t batch) { return plan_ws(batch); }
+
+extern "C" int cgx_bpr_plan(const int64_t* users, const int64_t* pos, const int64_t* neg, int64_t batch, int32_t U,
+                            int32_t I, uint64_t* plan, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CGX_REQUIRE(users && pos && neg && plan, CGX_ERR_ARG, "bpr_plan: NULL pointer");
+  CGX_REQUIRE(batch > 0 && batch < (int64_t(1) << 29), CGX_ERR_ARG, "bpr_plan: bad batch size %lld",
+              (long long)batch);
+  CGX_REQUIRE(workspace_bytes >= plan_ws(batch), CGX_ERR_WORKSPACE, "bpr_plan: workspace too small");
+  const int64_t n = 3 * batch;
+  const int entry_bits = bits_for(n), row_bits = bits_for(int64_t(U) + I);
+  if (n <= PS_MAX) {
+    const size_t smem = plan_small_smem();
+    CGX_CUDA(cudaFuncSetAttribute(k_plan_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_plan_small<<<1, PS_THREADS, smem, stream>>>(users, pos, neg, batch, U, I, entry_bits, row_bits, plan);
+    CGX_LAUNCH_CHECK();
+    return CGX_OK;
+  }
+  Arena ws(workspace, workspace_bytes);
+  uint64_t* alt = ws.take<uint64_t>(n);
+  size_t sort_bytes = radix_sort_temp_bytes(n);
+  void* sort_tmp = ws.take<char>(sort_bytes);
+  CGX_REQUIRE(ws.ok, CGX_ERR_WORKSPACE, "bpr_plan: workspace too small");
+  k_plan_keys<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(users, pos, neg, batch, U, I, entry_bits, plan);
+  CGX_LAUNCH_CHECK();
+  uint64_t* sorted = plan;
+  CGX_TRY(radix_sort_u64(plan, alt, n, entry_bits + row_bits, sort_tmp, sort_bytes, stream, &sorted));
+  if (sorted != plan) CGX_CUDA(cudaMemcpyAsync(plan, sorted, size_t(n) * 8, cudaMemcpyDeviceToDevice, stream));
+  return CGX_OK;
+}
+
 extern "C" size_t cgx_bpr_workspace_bytes(int64_t batch, int32_t, int32_t) { return bpr_ws(batch); }
 
 extern "C" int cgx_bpr_fwd_bwd(const int64_t* users, const int64_t* pos, const int64_t* neg, int64_t batch,
-                               int32_t U, int32_t I, int32_t d, const float* f_u, const float* f_i,
-                               const float* e0_u, const float* e0_i, const float* pop, float reg_weight,
-                               float fair_weight, float* loss_out, float* g_u, float* g_i, int32_t* ego_rows,
-                               float* ego_coef, void* workspace, size_t workspace_bytes, void* stream_) {
+                               const uint64_t* plan, int32_t U, int32_t I, int32_t d, const float* f_u,
+                               const float* f_i, const float* e0_u, const float* e0_i, const float* pop,
+                               float reg_weight, float fair_weight, float* loss_out, float* g_u, float* g_i,
+                               int32_t* ego_rows, float* ego_coef, void* workspace, size_t workspace_bytes,
+                               void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  CGX_REQUIRE(users && pos && neg && f_u && f_i && e0_u && e0_i && loss_out && g_u && g_i && ego_rows && ego_coef,
+  CGX_REQUIRE(users && pos && neg && plan && f_u && f_i && e0_u && e0_i && loss_out && g_u && g_i && ego_rows &&
+                  ego_coef,
               CGX_ERR_ARG, "bpr: NULL pointer");
   CGX_REQUIRE(batch > 0 && batch < (int64_t(1) << 29), CGX_ERR_ARG, "bpr: bad batch size %lld", (long long)batch);
   CGX_REQUIRE(workspace_bytes >= bpr_ws(batch), CGX_ERR_WORKSPACE, "bpr: workspace too small");
@@ -270,11 +392,11 @@ extern "C" int cgx_bpr_fwd_bwd(const int64_t* users, const int64_t* pos, const i
             reinterpret_cast<const float4*>(f_i), reinterpret_cast<const float4*>(e0_u),
             reinterpret_cast<const float4*>(e0_i), pop, reg_weight, fair_weight};
   switch (d) {
-    case 16: return bpr_run<4, 1>(a, loss_out, g_u, g_i, ego_rows, ego_coef, workspace, workspace_bytes, stream);
-    case 32: return bpr_run<8, 1>(a, loss_out, g_u, g_i, ego_rows, ego_coef, workspace, workspace_bytes, stream);
-    case 64: return bpr_run<16, 1>(a, loss_out, g_u, g_i, ego_rows, ego_coef, workspace, workspace_bytes, stream);
-    case 128: return bpr_run<32, 1>(a, loss_out, g_u, g_i, ego_rows, ego_coef, workspace, workspace_bytes, stream);
-    case 256: return bpr_run<32, 2>(a, loss_out, g_u, g_i, ego_rows, ego_coef, workspace, workspace_bytes, stream);
+    case 16: return bpr_run<4, 1>(a, plan, loss_out, g_u, g_i, ego_rows, ego_coef, workspace, workspace_bytes, stream);
+    case 32: return bpr_run<8, 1>(a, plan, loss_out, g_u, g_i, ego_rows, ego_coef, workspace, workspace_bytes, stream);
+    case 64: return bpr_run<16, 1>(a, plan, loss_out, g_u, g_i, ego_rows, ego_coef, workspace, workspace_bytes, stream);
+    case 128: return bpr_run<32, 1>(a, plan, loss_out, g_u, g_i, ego_rows, ego_coef, workspace, workspace_bytes, stream);
+    case 256: return bpr_run<32, 2>(a, plan, loss_out, g_u, g_i, ego_rows, ego_coef, workspace, workspace_bytes, stream);
     default:
       set_error("bpr: emb_dim %d unsupported (16, 32, 64, 128, 256)", d);
       return CGX_ERR_UNSUPPORTED;

@@ -66,29 +66,51 @@ def spmm(csr, x, use_bwd_values=False):
     return y
 
 
+def bpr_plan(graph: CredGraph, users, pos, neg, plan=None):
+    """Sorted (row, entry) keys of a triple batch: the scatter plan of the fused loss (indices only)."""
+    dev = graph.device
+    users, pos, neg = _i64c(users, dev), _i64c(pos, dev), _i64c(neg, dev)
+    B = users.numel()
+    if plan is None:
+        plan = torch.empty(3 * B, dtype=torch.int64, device=dev)      # uint64 keys, stored as int64 bits
+    ws = workspace(lib().cgx_bpr_plan_workspace_bytes(B), dev)
+    with torch.cuda.device(dev):
+        check(lib().cgx_bpr_plan(ptr(users), ptr(pos), ptr(neg), B, graph.num_users, graph.num_items, ptr(plan),
+                                 ptr(ws), ws.numel(), stream_ptr(dev)))
+    return plan
+
+
 def bpr_fused(graph: CredGraph, f_u, f_i, e0_u, e0_i, users, pos, neg, reg_weight, fair_weight=0.0, pop=None,
-              g_u=None, g_i=None):
+              g_u=None, g_i=None, plan=None, bufs=None):
     """Loss value + gradients w.r.t. the propagated tables + compact ego (L2) gradient.
-    g_u / g_i, when given, must be zero-filled [U,d] / [I,d] buffers."""
+    g_u / g_i, when given, must be zero-filled [U,d] / [I,d] buffers; `plan` = bpr_plan(...) of the
+    same batch (built here when absent); `bufs` = reusable (loss, ego_rows, ego_coef, ws)."""
     dev = f_u.device
     f_u, f_i, e0_u, e0_i = _f32c(f_u), _f32c(f_i), _f32c(e0_u), _f32c(e0_i)
     users, pos, neg = _i64c(users, dev), _i64c(pos, dev), _i64c(neg, dev)
     B, d = users.numel(), f_u.shape[1]
+    if plan is None:
+        plan = bpr_plan(graph, users, pos, neg)
     if g_u is None:
         g_u = torch.zeros_like(f_u)
     if g_i is None:
         g_i = torch.zeros_like(f_i)
-    loss = torch.empty(1, dtype=torch.float32, device=dev)
-    ego_rows = torch.empty(3 * B, dtype=torch.int32, device=dev)
-    ego_coef = torch.empty(3 * B, dtype=torch.float32, device=dev)
-    ws = workspace(lib().cgx_bpr_workspace_bytes(B, graph.num_users, graph.num_items), dev)
+    if bufs is None:
+        bufs = bpr_buffers(graph, B, dev)
+    loss, ego_rows, ego_coef, ws = bufs
     pop_t = None if pop is None else _f32c(torch.as_tensor(pop, device=dev))
     with torch.cuda.device(dev):
-        check(lib().cgx_bpr_fwd_bwd(ptr(users), ptr(pos), ptr(neg), B, graph.num_users, graph.num_items, d,
-                                    ptr(f_u), ptr(f_i), ptr(e0_u), ptr(e0_i), ptr(pop_t), float(reg_weight),
+        check(lib().cgx_bpr_fwd_bwd(ptr(users), ptr(pos), ptr(neg), B, ptr(plan), graph.num_users, graph.num_items,
+                                    d, ptr(f_u), ptr(f_i), ptr(e0_u), ptr(e0_i), ptr(pop_t), float(reg_weight),
                                     float(fair_weight), ptr(loss), ptr(g_u), ptr(g_i), ptr(ego_rows),
                                     ptr(ego_coef), ptr(ws), ws.numel(), stream_ptr(dev)))
     return loss, g_u, g_i, ego_rows, ego_coef
+
+
+def bpr_buffers(graph: CredGraph, B: int, dev):
+    return (torch.empty(1, dtype=torch.float32, device=dev), torch.empty(3 * B, dtype=torch.int32, device=dev),
+            torch.empty(3 * B, dtype=torch.float32, device=dev),
+            workspace(lib().cgx_bpr_workspace_bytes(B, graph.num_users, graph.num_items), dev))
 
 
 def apply_ego(graph: CredGraph, ego_rows, ego_coef, e0_u, e0_i, d_e0_u, d_e0_i):
@@ -245,12 +267,19 @@ class TrainStep:
         self.g_u, self.g_i = torch.empty_like(eu), torch.empty_like(ei)
         eu.grad, ei.grad = torch.empty_like(eu), torch.empty_like(ei)
         self.phase_events = None      # set to a list to collect (start, fwd_end, loss_end, bwd_end) CUDA events
+        self.side = torch.cuda.Stream(device=dev)     # plan + gradient-buffer clearing overlap the forward
+        self._bufs = {}
 
     def _mark(self, marks):
         if self.phase_events is not None:
             ev = torch.cuda.Event(enable_timing=True)
             ev.record(torch.cuda.current_stream(self.graph.device))
             marks.append(ev)
+
+    def _batch_bufs(self, B, dev):
+        if B not in self._bufs:
+            self._bufs[B] = (torch.empty(3 * B, dtype=torch.int64, device=dev), bpr_buffers(self.graph, B, dev))
+        return self._bufs[B]
 
     @torch.no_grad()
     def forward_backward(self, users, pos, neg):
@@ -259,17 +288,24 @@ class TrainStep:
         d, K, order = eu.shape[1], m.num_layers, _lib.ORDERS[m.ORDER]
         ws = g.propagate_workspace(d)
         dev = eu.device
+        users, pos, neg = _i64c(users, dev), _i64c(pos, dev), _i64c(neg, dev)
+        plan, bufs = self._batch_bufs(users.numel(), dev)
         marks = []
         with torch.cuda.device(dev):
-            st = stream_ptr(dev)
+            main = torch.cuda.current_stream(dev)
             self._mark(marks)
+            self.side.wait_stream(main)                 # indices (and last step's use of g_u/g_i) are ready
+            with torch.cuda.stream(self.side):
+                bpr_plan(g, users, pos, neg, plan)
+                self.g_u.zero_()
+                self.g_i.zero_()
+            st = stream_ptr(dev)
             check(lib().cgx_propagate_fwd(g.by_user.ref(), g.by_item.ref(), order, K, d, ptr(eu), ptr(ei),
                                           ptr(self.f_u), ptr(self.f_i), ptr(ws), ws.numel(), st))
             self._mark(marks)
-            self.g_u.zero_()
-            self.g_i.zero_()
+            main.wait_stream(self.side)
             loss, _, _, ego_rows, ego_coef = bpr_fused(g, self.f_u, self.f_i, eu, ei, users, pos, neg, self.reg,
-                                                       self.fair, self.pop, self.g_u, self.g_i)
+                                                       self.fair, self.pop, self.g_u, self.g_i, plan, bufs)
             self._mark(marks)
             check(lib().cgx_propagate_bwd(g.by_user.ref(), g.by_item.ref(), order, K, d, ptr(self.g_u),
                                           ptr(self.g_i), ptr(eu.grad), ptr(ei.grad), ptr(ws), ws.numel(), st))

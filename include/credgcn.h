@@ -158,8 +158,8 @@ int cgx_propagate_bwd(const cgx_csr* by_user, const cgx_csr* by_item, int order,
  * assembly (CU:450-463, 635-648) and bpr_loss (V2:495-508) with their backward.
  *   L = -mean(log(sigmoid(y+ - y-) + 1e-12)) + fair * mean(pop[pos] * y+)
  *       + reg * mean(|e0_u[u]|^2 + |e0_i[p]|^2 + |e0_i[n]|^2)
- * Gradients are scattered without atomics: the 3B (row, triple) pairs are sorted and each distinct
- * row is summed by one thread group in triple order (deterministic).
+ * Gradients are scattered without atomics: the 3B (row, triple) pairs are sorted (cgx_bpr_plan) and
+ * each distinct row is summed by one thread group in triple order (deterministic).
  *   g_u [U,d], g_i [I,d]   dL/d(propagated tables); must be zero-filled by the caller; only the
  *                          rows named by the batch are written
  *   ego_rows int32[3B], ego_coef float[3B]   compact L2 gradient: after the backward propagation
@@ -168,9 +168,15 @@ int cgx_propagate_bwd(const cgx_csr* by_user, const cgx_csr* by_item, int order,
  *                          -- done by cgx_bpr_apply_ego
  *   loss_out float[1]      NaN if any index of the batch was out of range
  * ------------------------------------------------------------------------------------------ */
+/* Scatter plan: the 3B (row, entry) keys of a batch sorted by row, uint64[3B] (device).  Depends on
+ * the indices only -- build it on a side stream while the forward propagation runs. */
+size_t cgx_bpr_plan_workspace_bytes(int64_t batch);
+int cgx_bpr_plan(const int64_t* users, const int64_t* pos, const int64_t* neg, int64_t batch,
+                 int32_t num_users, int32_t num_items, uint64_t* plan,
+                 void* workspace, size_t workspace_bytes, void* stream);
 size_t cgx_bpr_workspace_bytes(int64_t batch, int32_t num_users, int32_t num_items);
 int cgx_bpr_fwd_bwd(const int64_t* users, const int64_t* pos, const int64_t* neg, int64_t batch,
-                    int32_t num_users, int32_t num_items, int32_t d,
+                    const uint64_t* plan, int32_t num_users, int32_t num_items, int32_t d,
                     const float* f_u, const float* f_i, const float* e0_u, const float* e0_i,
                     const float* pop, float reg_weight, float fair_weight,
                     float* loss_out, float* g_u, float* g_i,
