@@ -174,6 +174,77 @@ def make_graph(
     )
 
 
+def make_graph_device(name: str = "C4", device="cuda", *, num_users=None, num_items=None, num_edges=None,
+                      seed: int | None = None, fake_frac: float = 0.05, split=(0.8, 0.1, 0.1)) -> SynthGraph:
+    """Same law as make_graph, generated with torch on `device` for the shapes NumPy is too slow for
+    (C4: 200M edges, C5: 1B edges).  Edge count is approximate (+-1 %): de-duplication is done by one
+    sort instead of top-up rounds.  Edge arrays stay on the device (SynthGraph fields hold tensors)."""
+    import torch
+    shp = dict(SHAPES.get(name, SHAPES["C4"]))
+    U = int(num_users if num_users is not None else shp["num_users"])
+    I = int(num_items if num_items is not None else shp["num_items"])
+    E = int(num_edges if num_edges is not None else shp["num_edges"])
+    cl = int(shp["cluster"]) or 1000
+    dev = torch.device(device)
+    gen = torch.Generator(device=dev).manual_seed(20240 + _CFG_ID.get(name, 9) if seed is None else seed)
+    rnd = lambda n: torch.rand(n, device=dev, generator=gen)
+
+    # fake clusters: `cl` consecutive ids each, spread over the id range
+    n_cl = max(int(round(U * fake_frac)) // cl, 1)
+    starts = torch.randperm(max(U // cl, 1), device=dev, generator=gen)[:n_cl] * cl
+    is_fake = torch.zeros(U, dtype=torch.bool, device=dev)
+    fake_ids = (starts[:, None] + torch.arange(cl, device=dev)[None, :]).reshape(-1)
+    fake_ids = fake_ids[fake_ids < U]
+    is_fake[fake_ids] = True
+    n_fake = int(fake_ids.numel())
+    E_fake = int(E * fake_frac)
+    E_gen = E - E_fake
+
+    # genuine edges: log-normal activity x Zipf(0.8) items
+    ranks = torch.arange(1, I + 1, device=dev, dtype=torch.float64)
+    cdf = torch.cumsum(ranks.pow(-0.8), 0)
+    cdf = (cdf / cdf[-1]).to(torch.float32)
+    perm = torch.randperm(I, device=dev, generator=gen)
+    act = torch.exp(torch.randn(U, device=dev, generator=gen))
+    act[is_fake] = 0.0
+    cnt = torch.floor(act * (E_gen * 1.12 / act.sum())).to(torch.int64)
+    cnt[~is_fake] = cnt[~is_fake].clamp(min=1)
+    uu = torch.repeat_interleave(torch.arange(U, device=dev), cnt)
+    del act, cnt
+    ii = perm[torch.searchsorted(cdf, rnd(uu.numel())).clamp(max=I - 1)]
+    keys = torch.unique(uu * I + ii)
+    del uu, ii
+    if keys.numel() > E_gen:
+        keys = keys[rnd(keys.numel()) < (E_gen / keys.numel())]
+
+    # fake edges: each cluster hammers its own 50..500 target items
+    per_user = max(E_fake // max(n_fake, 1), 1)
+    t_c = torch.randint(50, 501, (n_cl,), device=dev, generator=gen)
+    targets = torch.randint(0, I, (n_cl, 500), device=dev, generator=gen)
+    fu = torch.repeat_interleave(fake_ids, per_user)
+    fc = torch.repeat_interleave(torch.arange(n_cl, device=dev).repeat_interleave(cl)[: fake_ids.numel()], per_user)
+    fj = (rnd(fu.numel()) * t_c[fc]).to(torch.int64)
+    fkeys = torch.unique(fu * I + targets[fc, fj])
+    del fu, fc, fj
+
+    all_keys = torch.cat([keys, fkeys])
+    del keys, fkeys
+    all_keys = all_keys[torch.randperm(all_keys.numel(), device=dev, generator=gen)]
+    edges = torch.stack([(all_keys // I).to(torch.int32), (all_keys % I).to(torch.int32)])
+    del all_keys
+    n = edges.shape[1]
+    n_tr, n_va = int(n * split[0]), int(n * split[1])
+
+    g1 = torch._standard_gamma(torch.where(is_fake, 1.0, 5.0).to(torch.float32))
+    g2 = torch._standard_gamma(torch.where(is_fake, 8.0, 2.0).to(torch.float32))
+    cred = (g1 / (g1 + g2)).clamp(0.0, 1.0).to(torch.float32)
+    cred[0], cred[-1] = 1.0, 0.0
+    return SynthGraph(name=name, num_users=U, num_items=I, train_edges=edges[:, :n_tr].contiguous(),
+                      val_edges=edges[:, n_tr:n_tr + n_va].contiguous(), test_edges=edges[:, n_tr + n_va:].contiguous(),
+                      cred=cred, is_fake=is_fake,
+                      meta=dict(shp, num_users=U, num_items=I, num_edges=int(n), fake_users=n_fake, on_device=True))
+
+
 def make_triples(graph: SynthGraph, batch: int, seed: int = 7):
     """An injected (user, pos, neg) list: users with >=1 train edge, pos from their row,
     neg uniform outside the row.  Used wherever parity needs identical triples on both sides."""
