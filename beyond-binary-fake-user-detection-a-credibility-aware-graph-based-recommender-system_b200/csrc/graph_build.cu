@@ -299,7 +299,8 @@ __global__ void k_sched_keys(const int64_t* __restrict__ indptr, int32_t n_rows,
 }
 __global__ void k_sched_perm(const uint64_t* __restrict__ keys, const int64_t* __restrict__ indptr,
                              int32_t n_rows, int bits_r, int32_t* __restrict__ perm,
-                             uint32_t* __restrict__ is_long, uint32_t* __restrict__ n_chunks) {
+                             uint32_t* __restrict__ is_long, uint32_t* __restrict__ n_chunks,
+                             unsigned int* __restrict__ n_huge) {
   int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (k >= n_rows) return;
   const int32_t r = int32_t(keys[k] & ((uint64_t(1) << bits_r) - 1));
@@ -308,6 +309,7 @@ __global__ void k_sched_perm(const uint64_t* __restrict__ keys, const int64_t* _
   const bool lg = len > CGX_LONG_ROW;
   is_long[k] = lg ? 1u : 0u;
   n_chunks[k] = lg ? uint32_t((len + CGX_CHUNK - 1) / CGX_CHUNK) : 0u;
+  if (len > CGX_HUGE_ROW) atomicAdd(n_huge, 1u);   // integer count: order independent
 }
 __global__ void k_sched_chunks(const uint32_t* __restrict__ cpos, const uint32_t* __restrict__ totals,
                                int32_t n_long, int32_t* __restrict__ chunk_ptr, int32_t* __restrict__ chunk_row) {
@@ -339,7 +341,7 @@ static int sched_carve(void* workspace, size_t workspace_bytes, int32_t n_rows, 
   w->alt = ws.take<uint64_t>(n_rows);
   w->is_long = ws.take<uint32_t>(n_rows);
   w->cpos = ws.take<uint32_t>(n_rows);
-  w->totals = ws.take<uint32_t>(2);
+  w->totals = ws.take<uint32_t>(4);
   w->sort_bytes = radix_sort_temp_bytes(n_rows);
   w->sort_tmp = ws.take<char>(w->sort_bytes);
   w->scan_bytes = scan_temp_bytes(n_rows);
@@ -352,9 +354,10 @@ static int sched_carve(void* workspace, size_t workspace_bytes, int32_t n_rows, 
 extern "C" size_t cgx_row_schedule_workspace_bytes(int32_t n_rows) { return sched_ws_bytes(n_rows); }
 
 extern "C" int cgx_row_schedule(const int64_t* indptr, int32_t n_rows, int32_t* perm, int32_t* n_long_host,
-                                int32_t* n_chunks_host, void* workspace, size_t workspace_bytes, void* stream_) {
+                                int32_t* n_chunks_host, int32_t* n_huge_host, void* workspace,
+                                size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  CGX_REQUIRE(indptr && n_rows > 0 && perm && n_long_host && n_chunks_host, CGX_ERR_ARG,
+  CGX_REQUIRE(indptr && n_rows > 0 && perm && n_long_host && n_chunks_host && n_huge_host, CGX_ERR_ARG,
               "row_schedule: bad argument");
   SchedWs w;
   CGX_TRY(sched_carve(workspace, workspace_bytes, n_rows, &w));
@@ -363,15 +366,18 @@ extern "C" int cgx_row_schedule(const int64_t* indptr, int32_t n_rows, int32_t* 
   CGX_LAUNCH_CHECK();
   uint64_t* sorted = w.keys;
   CGX_TRY(radix_sort_u64(w.keys, w.alt, n_rows, bits_r + 31, w.sort_tmp, w.sort_bytes, stream, &sorted));
-  k_sched_perm<<<grid_for(n_rows), GB_THREADS, 0, stream>>>(sorted, indptr, n_rows, bits_r, perm, w.is_long, w.cpos);
+  CGX_CUDA(cudaMemsetAsync(w.totals, 0, 16, stream));
+  k_sched_perm<<<grid_for(n_rows), GB_THREADS, 0, stream>>>(sorted, indptr, n_rows, bits_r, perm, w.is_long, w.cpos,
+                                                           w.totals + 2);
   CGX_LAUNCH_CHECK();
   CGX_TRY(exclusive_scan_u32(w.is_long, w.is_long, n_rows, w.totals, w.scan_tmp, w.scan_bytes, stream));
   CGX_TRY(exclusive_scan_u32(w.cpos, w.cpos, n_rows, w.totals + 1, w.scan_tmp, w.scan_bytes, stream));
-  uint32_t h[2];
-  CGX_CUDA(cudaMemcpyAsync(h, w.totals, 8, cudaMemcpyDeviceToHost, stream));
+  uint32_t h[4];
+  CGX_CUDA(cudaMemcpyAsync(h, w.totals, 16, cudaMemcpyDeviceToHost, stream));
   CGX_CUDA(cudaStreamSynchronize(stream));
   *n_long_host = int32_t(h[0]);
   *n_chunks_host = int32_t(h[1]);
+  *n_huge_host = int32_t(h[2]);
   return CGX_OK;
 }
 

@@ -12,18 +12,40 @@
 // gathers are issued UNR at a time before any FMA so that each lane keeps UNR independent 16-byte
 // loads in flight.
 // Work items follow the schedule built by cgx_row_schedule: first the CGX_CHUNK-sized chunks of the
-// rows longer than CGX_LONG_ROW (partials in workspace, summed in chunk order by a finishing
-// kernel), then all other rows in descending degree order.  Neighbouring groups therefore carry
-// equal work (no idle lanes inside a warp or CTA) and the heavy items start first (no tail).
-// No atomics anywhere: results are bitwise reproducible.
+// rows longer than CGX_LONG_ROW (partials in workspace, summed IN CHUNK ORDER by the chunk that
+// arrives last, or by a finishing kernel for rows above CGX_HUGE_ROW), then all other rows in
+// descending degree order.  Neighbouring groups therefore carry equal work (no idle lanes inside a
+// warp or CTA) and the heavy items start first (no tail).
+// No floating-point atomics anywhere (the only atomic is an integer arrival counter): results are
+// bitwise reproducible.
+// Tuning (profiles/r1_spmm_variants.txt): 8 gathers in flight per lane with the register budget
+// capped for 4 CTAs/SM is within 3 % of the best variant on both the L2-resident C2 shape and the
+// HBM-bound 64M-edge shape; higher unrolls lose occupancy (d=128: 86 registers -> 2 CTAs/SM).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cgx {
 
 constexpr int SP_THREADS = 256;
-constexpr int SP_UNR = 8;
 
-__device__ __forceinline__ float4 ld_f4(const float4* p) { return __ldg(p); }
+// Tuning knobs of the gather loop (selected per width in spmm_dispatch; CGX_SPMM_VARIANT overrides
+// them for experiments): UNR = embedding-row gathers in flight per lane, HINT = cache policy of
+// those gathers, MINB = CTAs per SM the register allocation must allow.
+enum { HINT_NC = 0, HINT_CG = 1, HINT_NC_NOALLOC = 2 };
+
+template <int HINT>
+__device__ __forceinline__ float4 ld_row(const float4* p) {
+  if (HINT == HINT_CG) return __ldcg(p);
+  if (HINT == HINT_NC_NOALLOC) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+  }
+  return __ldg(p);
+}
 __device__ __forceinline__ void fma4(float4& a, float v, const float4& x) {
   a.x = fmaf(v, x.x, a.x);
   a.y = fmaf(v, x.y, a.y);
@@ -45,7 +67,7 @@ __device__ __forceinline__ unsigned group_mask() {
 }
 
 // acc[v] (v < V) += sum over nnz in [begin, end) of val * X[idx, :]; one group, lane = 0..G-1.
-template <int G, int V>
+template <int G, int V, int UNR, int HINT>
 __device__ __forceinline__ void gather_range(const int32_t* __restrict__ idx, const float* __restrict__ val,
                                              int64_t begin, int64_t end, const float4* __restrict__ X, int lane,
                                              unsigned mask, float4 (&acc)[V]) {
@@ -65,18 +87,18 @@ __device__ __forceinline__ void gather_range(const int32_t* __restrict__ idx, co
       w_nxt = __ldg(val + pn);
     }
     const int cnt = (end - base) < G ? int(end - base) : G;
-    for (int j0 = 0; j0 < cnt; j0 += SP_UNR) {
-      float4 x[SP_UNR][V];
-      float ww[SP_UNR];
+    for (int j0 = 0; j0 < cnt; j0 += UNR) {
+      float4 x[UNR][V];
+      float ww[UNR];
 #pragma unroll
-      for (int t = 0; t < SP_UNR; ++t) {
+      for (int t = 0; t < UNR; ++t) {
         const int j = j0 + t;
         const int src = (j < G) ? j : (G - 1);
         const int32_t cj = __shfl_sync(mask, c, src, G);
         ww[t] = __shfl_sync(mask, w, src, G);
         if (j < cnt) {
 #pragma unroll
-          for (int v = 0; v < V; ++v) x[t][v] = ld_f4(X + int64_t(cj) * ROW4 + v * G + lane);
+          for (int v = 0; v < V; ++v) x[t][v] = ld_row<HINT>(X + int64_t(cj) * ROW4 + v * G + lane);
         } else {
           ww[t] = 0.f;
 #pragma unroll
@@ -84,7 +106,7 @@ __device__ __forceinline__ void gather_range(const int32_t* __restrict__ idx, co
         }
       }
 #pragma unroll
-      for (int t = 0; t < SP_UNR; ++t) {
+      for (int t = 0; t < UNR; ++t) {
 #pragma unroll
         for (int v = 0; v < V; ++v) fma4(acc[v], ww[t], x[t][v]);
       }
@@ -111,17 +133,21 @@ struct SpmmSched {
   const int32_t* perm;
   const int32_t* chunk_ptr;
   const int32_t* chunk_row;
-  int32_t n_long, n_chunks;
+  int32_t* arrive;
+  int32_t n_long, n_chunks, n_huge;
 };
 
-// one group per work item: chunk items first, then rows in descending degree
-template <int G, int V>
-__global__ void __launch_bounds__(SP_THREADS) k_spmm(const int64_t* __restrict__ indptr,
-                                                     const int32_t* __restrict__ idx,
-                                                     const float* __restrict__ val, int32_t n_rows, SpmmSched sc,
-                                                     const float4* __restrict__ X, float4* __restrict__ Y,
-                                                     const float4* ACC_IN, float4* ACC_OUT, float acc_scale,
-                                                     float4* __restrict__ partial) {
+// One group per work item: chunk items first, then rows in descending degree.  A chunk stores its
+// partial sum; for rows up to CGX_HUGE_ROW the chunk that arrives last (per-row counter, release /
+// acquire through __threadfence) adds the partials IN CHUNK ORDER and runs the epilogue, so the
+// result does not depend on which chunk happened to be last.
+template <int G, int V, int UNR, int HINT, int MINB>
+__global__ void __launch_bounds__(SP_THREADS, MINB) k_spmm(const int64_t* __restrict__ indptr,
+                                                           const int32_t* __restrict__ idx,
+                                                           const float* __restrict__ val, int32_t n_rows,
+                                                           SpmmSched sc, const float4* __restrict__ X,
+                                                           float4* __restrict__ Y, const float4* ACC_IN,
+                                                           float4* ACC_OUT, float acc_scale, float4* partial) {
   constexpr int ROW4 = G * V;
   const int lane = threadIdx.x & (G - 1);
   const int64_t item = (int64_t(blockIdx.x) * SP_THREADS + threadIdx.x) / G;
@@ -132,23 +158,41 @@ __global__ void __launch_bounds__(SP_THREADS) k_spmm(const int64_t* __restrict__
   if (item < sc.n_chunks) {
     const int32_t k = __ldg(sc.chunk_row + item);
     const int32_t row = __ldg(sc.perm + k);
+    const int32_t c0 = __ldg(sc.chunk_ptr + k);
     const int64_t rbeg = __ldg(indptr + row), rend = __ldg(indptr + row + 1);
-    const int64_t begin = rbeg + int64_t(int32_t(item) - __ldg(sc.chunk_ptr + k)) * CGX_CHUNK;
+    const int64_t begin = rbeg + int64_t(int32_t(item) - c0) * CGX_CHUNK;
     const int64_t end = begin + CGX_CHUNK < rend ? begin + CGX_CHUNK : rend;
-    gather_range<G, V>(idx, val, begin, end, X, lane, mask, acc);
+    gather_range<G, V, UNR, HINT>(idx, val, begin, end, X, lane, mask, acc);
 #pragma unroll
-    for (int v = 0; v < V; ++v) partial[item * ROW4 + v * G + lane] = acc[v];
+    for (int v = 0; v < V; ++v) __stcg(partial + item * ROW4 + v * G + lane, acc[v]);
+    if (k < sc.n_huge) return;            // combined by k_spmm_finish
+    const int32_t c1 = __ldg(sc.chunk_ptr + k + 1);
+    __threadfence();                       // release: this group's partial is visible device-wide
+    __syncwarp(mask);
+    int prev = 0;
+    if (lane == 0) prev = atomicAdd(sc.arrive + k, 1);
+    prev = __shfl_sync(mask, prev, 0, G);
+    if (prev != c1 - c0 - 1) return;
+    __threadfence();                       // acquire: every other chunk's partial is visible
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = c0; c < c1; ++c) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[v] = add4(acc[v], __ldcg(partial + int64_t(c) * ROW4 + v * G + lane));
+    }
+    epilogue<G, V>(row, lane, acc, Y, ACC_IN, ACC_OUT, acc_scale);
+    if (lane == 0) sc.arrive[k] = 0;       // self-resetting for the next launch
     return;
   }
   const int64_t r = item - sc.n_chunks + sc.n_long;
   if (r >= n_rows) return;
   const int32_t row = __ldg(sc.perm + r);
   const int64_t begin = __ldg(indptr + row), end = __ldg(indptr + row + 1);
-  gather_range<G, V>(idx, val, begin, end, X, lane, mask, acc);
+  gather_range<G, V, UNR, HINT>(idx, val, begin, end, X, lane, mask, acc);
   epilogue<G, V>(row, lane, acc, Y, ACC_IN, ACC_OUT, acc_scale);
 }
 
-// one CTA per long row: groups sum interleaved chunk partials, fixed-order reduction, epilogue
+// one CTA per huge row: groups sum interleaved chunk partials, fixed-order reduction, epilogue
 template <int G, int V>
 __global__ void __launch_bounds__(SP_THREADS) k_spmm_finish(SpmmSched sc, const float4* __restrict__ partial,
                                                             float4* __restrict__ Y, const float4* ACC_IN,
@@ -185,7 +229,7 @@ __global__ void k_scale(const float4* __restrict__ in, float4* __restrict__ out,
   if (p < n4) out[p] = scale4(in[p], s);
 }
 
-template <int G, int V>
+template <int G, int V, int UNR, int HINT, int MINB>
 static int launch_spmm(const cgx_csr* m, const float* val, const float* X, float* Y, const float* ACC_IN,
                        float* ACC_OUT, float acc_scale, void* workspace, size_t workspace_bytes,
                        cudaStream_t stream) {
@@ -197,14 +241,14 @@ static int launch_spmm(const cgx_csr* m, const float* val, const float* X, float
                 "spmm: workspace too small for %d long-row chunks", m->n_chunks);
     partial = static_cast<float4*>(workspace);
   }
-  SpmmSched sc{m->perm, m->chunk_ptr, m->chunk_row, m->n_long, m->n_chunks};
+  SpmmSched sc{m->perm, m->chunk_ptr, m->chunk_row, m->arrive, m->n_long, m->n_chunks, m->n_huge};
   const int64_t items = int64_t(m->n_chunks) + (m->n_rows - m->n_long);
-  k_spmm<G, V><<<(unsigned)ceil_div(items, GROUPS), SP_THREADS, 0, stream>>>(
+  k_spmm<G, V, UNR, HINT, MINB><<<(unsigned)ceil_div(items, GROUPS), SP_THREADS, 0, stream>>>(
       m->indptr, m->idx, val, m->n_rows, sc, reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(Y),
       reinterpret_cast<const float4*>(ACC_IN), reinterpret_cast<float4*>(ACC_OUT), acc_scale, partial);
   CGX_LAUNCH_CHECK();
-  if (m->n_long > 0) {
-    k_spmm_finish<G, V><<<(unsigned)m->n_long, SP_THREADS, 0, stream>>>(
+  if (m->n_huge > 0) {
+    k_spmm_finish<G, V><<<(unsigned)m->n_huge, SP_THREADS, 0, stream>>>(
         sc, partial, reinterpret_cast<float4*>(Y), reinterpret_cast<const float4*>(ACC_IN),
         reinterpret_cast<float4*>(ACC_OUT), acc_scale);
     CGX_LAUNCH_CHECK();
@@ -212,20 +256,52 @@ static int launch_spmm(const cgx_csr* m, const float* val, const float* X, float
   return CGX_OK;
 }
 
+static int spmm_variant() {
+  static int v = [] {
+    const char* e = getenv("CGX_SPMM_VARIANT");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
+
+#define CGX_SPMM_ARGS m, val, X, Y, ACC_IN, ACC_OUT, acc_scale, ws, ws_bytes, stream
+
 static int spmm_dispatch(const cgx_csr* m, int use_bwd, int32_t d, const float* X, float* Y, const float* ACC_IN,
                          float* ACC_OUT, float acc_scale, void* ws, size_t ws_bytes, cudaStream_t stream) {
   CGX_REQUIRE(m && m->indptr && m->perm && (m->nnz == 0 || (m->idx && m->val_fwd && m->val_bwd)) && X, CGX_ERR_ARG,
               "spmm: NULL pointer");
-  CGX_REQUIRE(m->n_long == 0 || (m->chunk_ptr && m->chunk_row), CGX_ERR_ARG, "spmm: chunk tables missing");
+  CGX_REQUIRE(m->n_long == 0 || (m->chunk_ptr && m->chunk_row && m->arrive), CGX_ERR_ARG,
+              "spmm: chunk tables missing");
   CGX_REQUIRE(Y || ACC_OUT, CGX_ERR_ARG, "spmm: no output requested");
   const float* val = use_bwd ? m->val_bwd : m->val_fwd;
   if (m->n_rows == 0) return CGX_OK;
+  const int variant = spmm_variant();
   switch (d) {
-    case 16: return launch_spmm<4, 1>(m, val, X, Y, ACC_IN, ACC_OUT, acc_scale, ws, ws_bytes, stream);
-    case 32: return launch_spmm<8, 1>(m, val, X, Y, ACC_IN, ACC_OUT, acc_scale, ws, ws_bytes, stream);
-    case 64: return launch_spmm<16, 1>(m, val, X, Y, ACC_IN, ACC_OUT, acc_scale, ws, ws_bytes, stream);
-    case 128: return launch_spmm<32, 1>(m, val, X, Y, ACC_IN, ACC_OUT, acc_scale, ws, ws_bytes, stream);
-    case 256: return launch_spmm<32, 2>(m, val, X, Y, ACC_IN, ACC_OUT, acc_scale, ws, ws_bytes, stream);
+    case 16: return launch_spmm<4, 1, 4, HINT_NC, 4>(CGX_SPMM_ARGS);
+    case 32: return launch_spmm<8, 1, 8, HINT_NC, 4>(CGX_SPMM_ARGS);
+#define CGX_VARIANTS(GG)                                                                   \
+      switch (variant) {                                                                   \
+        case 1: return launch_spmm<GG, 1, 16, HINT_NC, 1>(CGX_SPMM_ARGS);                  \
+        case 2: return launch_spmm<GG, 1, 8, HINT_CG, 1>(CGX_SPMM_ARGS);                   \
+        case 3: return launch_spmm<GG, 1, 8, HINT_NC_NOALLOC, 1>(CGX_SPMM_ARGS);           \
+        case 4: return launch_spmm<GG, 1, 4, HINT_NC, 6>(CGX_SPMM_ARGS);                   \
+        case 5: return launch_spmm<GG, 1, 8, HINT_NC, 5>(CGX_SPMM_ARGS);                   \
+        case 6: return launch_spmm<GG, 1, 16, HINT_NC_NOALLOC, 1>(CGX_SPMM_ARGS);          \
+        case 7: return launch_spmm<GG, 1, 4, HINT_NC, 8>(CGX_SPMM_ARGS);                   \
+        case 8: return launch_spmm<GG, 1, 2, HINT_NC, 8>(CGX_SPMM_ARGS);                   \
+        case 9: return launch_spmm<GG, 1, 4, HINT_NC_NOALLOC, 6>(CGX_SPMM_ARGS);           \
+        case 10: return launch_spmm<GG, 1, 4, HINT_CG, 6>(CGX_SPMM_ARGS);                  \
+        case 11: return launch_spmm<GG, 1, 2, HINT_NC, 6>(CGX_SPMM_ARGS);                  \
+        case 12: return launch_spmm<GG, 1, 8, HINT_NC, 3>(CGX_SPMM_ARGS);                  \
+        case 13: return launch_spmm<GG, 1, 16, HINT_NC, 2>(CGX_SPMM_ARGS);                 \
+        case 14: return launch_spmm<GG, 1, 4, HINT_NC, 4>(CGX_SPMM_ARGS);                  \
+        case 15: return launch_spmm<GG, 1, 8, HINT_NC, 4>(CGX_SPMM_ARGS);                  \
+        case 16: return launch_spmm<GG, 1, 8, HINT_NC, 1>(CGX_SPMM_ARGS);                  \
+        default: return launch_spmm<GG, 1, 8, HINT_NC, 4>(CGX_SPMM_ARGS);                  \
+      }
+    case 64: CGX_VARIANTS(16)
+    case 128: CGX_VARIANTS(32)
+    case 256: return launch_spmm<32, 2, 4, HINT_NC, 4>(CGX_SPMM_ARGS);
     default:
       set_error("spmm: emb_dim %d unsupported (16, 32, 64, 128, 256)", d);
       return CGX_ERR_UNSUPPORTED;

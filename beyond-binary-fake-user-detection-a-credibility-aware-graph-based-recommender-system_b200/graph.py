@@ -66,6 +66,8 @@ class Csr:
     chunk_row: torch.Tensor | None = None
     n_long: int = 0
     n_chunks: int = 0
+    n_huge: int = 0
+    arrive: torch.Tensor | None = None
     _struct: CsrStruct | None = field(default=None, repr=False)
 
     def struct(self) -> CsrStruct:
@@ -78,6 +80,8 @@ class Csr:
             s.perm = self.perm.data_ptr()
             s.chunk_ptr = self.chunk_ptr.data_ptr() if self.n_long else None
             s.chunk_row = self.chunk_row.data_ptr() if self.n_long else None
+            s.n_huge = self.n_huge
+            s.arrive = self.arrive.data_ptr() if self.n_long else None
             self._struct = s
         return self._struct
 
@@ -88,13 +92,14 @@ class Csr:
         """Degree-descending row order + chunk tables of the long rows (cgx_row_schedule)."""
         dev = self.indptr.device
         ws = workspace(lib().cgx_row_schedule_workspace_bytes(self.n_rows), dev)
-        n_long, n_chunks = C.c_int32(0), C.c_int32(0)
+        n_long, n_chunks, n_huge = C.c_int32(0), C.c_int32(0), C.c_int32(0)
         self.perm = torch.empty(self.n_rows, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             check(lib().cgx_row_schedule(ptr(self.indptr), self.n_rows, ptr(self.perm), C.byref(n_long),
-                                         C.byref(n_chunks), ptr(ws), ws.numel(), stream_ptr(dev)))
-            self.n_long, self.n_chunks = int(n_long.value), int(n_chunks.value)
+                                         C.byref(n_chunks), C.byref(n_huge), ptr(ws), ws.numel(), stream_ptr(dev)))
+            self.n_long, self.n_chunks, self.n_huge = int(n_long.value), int(n_chunks.value), int(n_huge.value)
             if self.n_long:
+                self.arrive = torch.zeros(self.n_long, dtype=torch.int32, device=dev)
                 self.chunk_ptr = torch.empty(self.n_long + 1, dtype=torch.int32, device=dev)
                 self.chunk_row = torch.empty(self.n_chunks, dtype=torch.int32, device=dev)
                 check(lib().cgx_row_schedule_chunks(self.n_rows, self.n_long, self.n_chunks, ptr(self.chunk_ptr),

@@ -80,10 +80,16 @@ typedef struct {
   int32_t n_chunks;          /* total chunks over all long rows */
   const int32_t* chunk_ptr;  /* device, [n_long + 1] first chunk of each long row (perm order) */
   const int32_t* chunk_row;  /* device, [n_chunks] position in perm of the row a chunk belongs to */
+  int32_t n_huge;            /* rows longer than CGX_HUGE_ROW = perm[0 .. n_huge): combined by a finishing
+                                kernel; the other long rows are combined by their last-arriving chunk */
+  int32_t reserved_;
+  int32_t* arrive;           /* device, [n_long] arrival counters, zero between launches (self-resetting);
+                                mutable: at most one SpMM per cgx_csr may be in flight at a time */
 } cgx_csr;
 
-#define CGX_LONG_ROW 256   /* rows above this many non-zeros are split */
-#define CGX_CHUNK 256      /* non-zeros per chunk of a split row */
+#define CGX_LONG_ROW 256     /* rows above this many non-zeros are split */
+#define CGX_CHUNK 256        /* non-zeros per chunk of a split row */
+#define CGX_HUGE_ROW 16384   /* rows above this (64 chunks) use the separate finishing kernel */
 
 size_t cgx_graph_build_workspace_bytes(int64_t num_edges, int32_t num_users, int32_t num_items);
 
@@ -119,7 +125,8 @@ int cgx_user_csr(const int32_t* edges_u, const int32_t* edges_i, int64_t num_edg
  * in between, and only when n_long > 0. */
 size_t cgx_row_schedule_workspace_bytes(int32_t n_rows);
 int cgx_row_schedule(const int64_t* indptr, int32_t n_rows, int32_t* perm, int32_t* n_long_host,
-                     int32_t* n_chunks_host, void* workspace, size_t workspace_bytes, void* stream);
+                     int32_t* n_chunks_host, int32_t* n_huge_host, void* workspace, size_t workspace_bytes,
+                     void* stream);
 int cgx_row_schedule_chunks(int32_t n_rows, int32_t n_long, int32_t n_chunks, int32_t* chunk_ptr,
                             int32_t* chunk_row, void* workspace, size_t workspace_bytes, void* stream);
 
