@@ -42,7 +42,7 @@ _SIGNATURES = {
     "cgx_launch_count": (C.c_uint64, []),
     "cgx_emb_dim_supported": (C.c_int, [C.c_int32]),
     "cgx_graph_build_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
-    "cgx_graph_build": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int, _P, _P, _P, _P, _P,
+    "cgx_graph_build": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int, _P, _P, _P, _P, _P, _P,
                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P, C.c_size_t, _P]),
     "cgx_user_csr": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
     "cgx_row_schedule_workspace_bytes": (C.c_size_t, [C.c_int32]),
@@ -59,7 +59,8 @@ _SIGNATURES = {
     "cgx_bpr_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
     "cgx_bpr_plan_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "cgx_bpr_plan": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P, C.c_size_t, _P]),
-    "cgx_bpr_fwd_bwd": (C.c_int, [_P, _P, _P, C.c_int64, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P,
+    "cgx_bpr_fwd_bwd": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P,
+                                  _P, _P,
                                   C.c_float, C.c_float, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "cgx_bpr_apply_ego": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
     "cgx_sampler_build_workspace_bytes": (C.c_size_t, [C.c_int32]),

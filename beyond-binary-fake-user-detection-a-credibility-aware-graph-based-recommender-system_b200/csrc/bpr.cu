@@ -146,6 +146,7 @@ struct BprArgs {
   const int64_t* pos;
   const int64_t* neg;
   int64_t B;
+  int64_t B_total;   // denominator of the means (== B unless the batch is sharded over ranks)
   int32_t U, I;
   const float4* f_u;
   const float4* f_i;
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(BP_THREADS) k_bpr_triple(BprArgs a, float* __r
   yn = group_sum<G>(yn, mask);
   l2 = group_sum<G>(l2, mask);
   if (lane == 0) {
-    const float invB = 1.0f / float(a.B);
+    const float invB = 1.0f / float(a.B_total);
     const float x = yp - yn;
     const float sig = 1.0f / (1.0f + expf(-x));
     const float term = -logf(sig + 1e-12f);                      // lightgcn_cu.py:637 (epsilon form)
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(BP_THREADS) k_bpr_scatter(BprArgs a, int entry
   for (int v = 0; v < V; ++v) dst[v * G + lane] = acc[v];
   if (lane == 0) {
     ego_rows[k] = int32_t(row);
-    ego_coef[k] = float(mult) * 2.0f * a.reg / float(a.B);
+    ego_coef[k] = float(mult) * 2.0f * a.reg / float(a.B_total);
   }
 }
 
@@ -377,7 +378,8 @@ extern "C" int cgx_bpr_plan(const int64_t* users, const int64_t* pos, const int6
 extern "C" size_t cgx_bpr_workspace_bytes(int64_t batch, int32_t, int32_t) { return bpr_ws(batch); }
 
 extern "C" int cgx_bpr_fwd_bwd(const int64_t* users, const int64_t* pos, const int64_t* neg, int64_t batch,
-                               const uint64_t* plan, int32_t U, int32_t I, int32_t d, const float* f_u,
+                               int64_t batch_total, const uint64_t* plan, int32_t U, int32_t I, int32_t d,
+                               const float* f_u,
                                const float* f_i, const float* e0_u, const float* e0_i, const float* pop,
                                float reg_weight, float fair_weight, float* loss_out, float* g_u, float* g_i,
                                int32_t* ego_rows, float* ego_coef, void* workspace, size_t workspace_bytes,
@@ -388,7 +390,8 @@ extern "C" int cgx_bpr_fwd_bwd(const int64_t* users, const int64_t* pos, const i
               CGX_ERR_ARG, "bpr: NULL pointer");
   CGX_REQUIRE(batch > 0 && batch < (int64_t(1) << 29), CGX_ERR_ARG, "bpr: bad batch size %lld", (long long)batch);
   CGX_REQUIRE(workspace_bytes >= bpr_ws(batch), CGX_ERR_WORKSPACE, "bpr: workspace too small");
-  BprArgs a{users, pos, neg, batch, U, I, reinterpret_cast<const float4*>(f_u),
+  BprArgs a{users, pos, neg, batch, batch_total > 0 ? batch_total : batch, U, I,
+            reinterpret_cast<const float4*>(f_u),
             reinterpret_cast<const float4*>(f_i), reinterpret_cast<const float4*>(e0_u),
             reinterpret_cast<const float4*>(e0_i), pop, reg_weight, fair_weight};
   switch (d) {

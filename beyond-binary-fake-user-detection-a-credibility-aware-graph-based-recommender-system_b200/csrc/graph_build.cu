@@ -145,7 +145,8 @@ extern "C" size_t cgx_graph_build_workspace_bytes(int64_t num_edges, int32_t num
 }
 
 extern "C" int cgx_graph_build(const int32_t* edges_u, const int32_t* edges_i, int64_t E, int32_t U, int32_t I,
-                               const float* cred, int variant, const float* alpha, int32_t* deg_u,
+                               const float* cred, int variant, const float* alpha,
+                               const int32_t* deg_i_weights, int32_t* deg_u,
                                int32_t* deg_i, int64_t* samp_indptr, int32_t* samp_idx,
                                int64_t* user_indptr, int32_t* user_idx, float* user_val_fwd,
                                float* user_val_bwd, int64_t* item_indptr, int32_t* item_idx,
@@ -210,7 +211,9 @@ extern "C" int cgx_graph_build(const int32_t* edges_u, const int32_t* edges_i, i
   k_widen<<<grid_for(int64_t(U) + 1), GB_THREADS, 0, stream>>>(ustart, samp_indptr, int64_t(U) + 1);
   CGX_LAUNCH_CHECK();
 
-  WeightArgs wa{deg_u, deg_i, cred, alpha, variant};
+  // item degrees entering the weight formulas: the local histogram, or (user-sharded builds) the
+  // degrees over ALL shards supplied by the caller
+  WeightArgs wa{deg_u, deg_i_weights ? deg_i_weights : deg_i, cred, alpha, variant};
   for (int pass = 0; pass < 2; ++pass) {
     const bool by_user = pass == 0;
     uint64_t* keys = by_user ? key_ui : key_iu;

@@ -192,8 +192,12 @@ def numpy_damping_alpha(deg_i: np.ndarray) -> np.ndarray:
 
 
 def build_graph(train_edges_2xE, num_users: int, num_items: int, cred_u, variant: str = "v2",
-                device="cuda") -> CredGraph:
-    """Degrees + sampling CSR + both coalesced operators, all on device, bit-exact vs the reference."""
+                device="cuda", reduce_item_degrees=None) -> CredGraph:
+    """Degrees + sampling CSR + both coalesced operators, all on device, bit-exact vs the reference.
+
+    reduce_item_degrees: for a user-sharded build -- a callable that turns this shard's int32 item
+    degree histogram into the degrees over all shards (an all-reduce); `deg_i` of the result then
+    holds the GLOBAL degrees (what the weights, the popularity law and alpha_i use)."""
     if variant not in _lib.VARIANTS:
         raise ValueError(f"variant must be one of {sorted(_lib.VARIANTS)}")
     dev = _cuda_device(device)
@@ -221,20 +225,30 @@ def build_graph(train_edges_2xE, num_users: int, num_items: int, cred_u, variant
     counts = torch.zeros(2, **i64)
     ws = workspace(lib().cgx_graph_build_workspace_bytes(E, U, I), dev)
 
+    deg_i_global = None
+
     def run(alpha, deg_only):
         check(lib().cgx_graph_build(
-            ptr(eu), ptr(ei), E, U, I, ptr(cred), _lib.VARIANTS[variant], ptr(alpha), ptr(g.deg_u), ptr(g.deg_i),
+            ptr(eu), ptr(ei), E, U, I, ptr(cred), _lib.VARIANTS[variant], ptr(alpha), ptr(deg_i_global),
+            ptr(g.deg_u), ptr(g.deg_i),
             ptr(g.samp_indptr), ptr(g.samp_idx), ptr(u_indptr), ptr(u_idx), ptr(u_vf), ptr(u_vb),
             ptr(i_indptr), ptr(i_idx), ptr(i_vf), ptr(i_vb), ptr(counts), int(deg_only), ptr(ws), ws.numel(),
             stream_ptr(dev)))
 
     with torch.cuda.device(dev):
         alpha = None
-        if variant == "da":
-            run(None, True)                       # degrees first; alpha needs NumPy's log1p
-            alpha = torch.from_numpy(numpy_damping_alpha(g.deg_i.cpu().numpy())).to(dev)
+        if variant == "da" or reduce_item_degrees is not None:
+            run(None, True)                       # degrees first
+            if reduce_item_degrees is not None:
+                deg_i_global = reduce_item_degrees(g.deg_i.clone()).to(torch.int32).contiguous()
+            if variant == "da":                   # alpha needs NumPy's log1p
+                dsrc = deg_i_global if deg_i_global is not None else g.deg_i
+                alpha = torch.from_numpy(numpy_damping_alpha(dsrc.cpu().numpy())).to(dev)
         run(alpha, False)
         nnz, bad = (int(x) for x in counts.cpu().tolist())
+        g.deg_i_local = g.deg_i
+        if deg_i_global is not None:
+            g.deg_i = deg_i_global
     if bad:
         raise ValueError(f"{bad} edges have a user id outside [0, {U}) or an item id outside [0, {I})")
     g.nnz = nnz

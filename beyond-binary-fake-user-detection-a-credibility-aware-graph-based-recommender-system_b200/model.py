@@ -81,7 +81,7 @@ def bpr_plan(graph: CredGraph, users, pos, neg, plan=None):
 
 
 def bpr_fused(graph: CredGraph, f_u, f_i, e0_u, e0_i, users, pos, neg, reg_weight, fair_weight=0.0, pop=None,
-              g_u=None, g_i=None, plan=None, bufs=None):
+              g_u=None, g_i=None, plan=None, bufs=None, batch_total=0):
     """Loss value + gradients w.r.t. the propagated tables + compact ego (L2) gradient.
     g_u / g_i, when given, must be zero-filled [U,d] / [I,d] buffers; `plan` = bpr_plan(...) of the
     same batch (built here when absent); `bufs` = reusable (loss, ego_rows, ego_coef, ws)."""
@@ -100,7 +100,8 @@ def bpr_fused(graph: CredGraph, f_u, f_i, e0_u, e0_i, users, pos, neg, reg_weigh
     loss, ego_rows, ego_coef, ws = bufs
     pop_t = None if pop is None else _f32c(torch.as_tensor(pop, device=dev))
     with torch.cuda.device(dev):
-        check(lib().cgx_bpr_fwd_bwd(ptr(users), ptr(pos), ptr(neg), B, ptr(plan), graph.num_users, graph.num_items,
+        check(lib().cgx_bpr_fwd_bwd(ptr(users), ptr(pos), ptr(neg), B, int(batch_total), ptr(plan), graph.num_users,
+                                    graph.num_items,
                                     d, ptr(f_u), ptr(f_i), ptr(e0_u), ptr(e0_i), ptr(pop_t), float(reg_weight),
                                     float(fair_weight), ptr(loss), ptr(g_u), ptr(g_i), ptr(ego_rows),
                                     ptr(ego_coef), ptr(ws), ws.numel(), stream_ptr(dev)))

@@ -1,0 +1,257 @@
+"""User-sharded propagation / training over several GPUs of one node (one process per GPU).
+
+The reference is single-device; this is the row partition BASELINE.json names:
+
+  * users are split into contiguous ranges balanced by non-zeros; each rank owns the user table,
+    the user rows of the operator pattern and the sampling CSR of its range;
+  * the item table is replicated;
+  * user <- item products (A x_i, C^T x_i) read the replicated item table: no communication;
+  * item <- user products (C x_u, A^T x_u) give every rank a PARTIAL item table (the sum over its own
+    users); one all-reduce (NCCL over NVLink; reduce-scatter + all-gather inside) per layer makes
+    it whole again.  Forward: K all-reduces of [I, d]; backward: K + 1.
+  * evaluation is user-sharded with no exchange (only metric sums are reduced).
+
+`ShardedPropagation` is written against a two-method backend so that the host-side schedule can
+be exercised on CPU with the gloo backend (tests/test_sharded_gloo.py injects an oracle backend);
+the product backend is `CudaBackend` (libcredgcn.so) and there is no CPU backend in this package.
+"""
+from __future__ import annotations
+
+import json
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import check, lib, ptr, stream_ptr, workspace
+from .graph import CredGraph, build_graph
+from .model import apply_ego, bpr_buffers, bpr_fused, bpr_plan
+from .sampler import TripleSampler
+
+
+def partition_users(deg_u: np.ndarray, world: int) -> np.ndarray:
+    """bounds[world + 1]: contiguous user ranges with (nearly) equal numbers of non-zeros."""
+    deg_u = np.asarray(deg_u, dtype=np.int64)
+    csum = np.concatenate([[0], np.cumsum(deg_u)])
+    targets = csum[-1] * np.arange(1, world, dtype=np.float64) / world
+    cuts = np.searchsorted(csum, targets, side="left")
+    bounds = np.concatenate([[0], cuts, [deg_u.size]]).astype(np.int64)
+    return np.maximum.accumulate(bounds)
+
+
+def shard_edges(edges_2xE: np.ndarray, bounds: np.ndarray, rank: int) -> np.ndarray:
+    """Edges of the users owned by `rank`, user ids rebased to the shard."""
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    u = edges_2xE[0]
+    keep = (u >= lo) & (u < hi)
+    out = edges_2xE[:, keep].copy()
+    out[0] -= lo
+    return out
+
+
+def _world(group=None) -> int:
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+def all_reduce_sum(t: torch.Tensor, group=None) -> torch.Tensor:
+    if _world(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+class CudaBackend:
+    """The two products of one shard, on libcredgcn.so."""
+
+    def __init__(self, graph: CredGraph):
+        self.graph = graph
+        self._ws = {}
+
+    def _spmm(self, csr, x, bwd, y=None, acc_in=None, acc_out=None, scale=1.0):
+        x = x.contiguous()
+        d = x.shape[1]
+        if y is None and acc_out is None:
+            y = torch.empty(csr.n_rows, d, dtype=torch.float32, device=x.device)
+        key = (id(csr), d)
+        if key not in self._ws:
+            self._ws[key] = workspace(lib().cgx_spmm_workspace_bytes(csr.ref(), d), x.device)
+        ws = self._ws[key]
+        with torch.cuda.device(x.device):
+            check(lib().cgx_spmm(csr.ref(), int(bwd), d, ptr(x), ptr(y), ptr(acc_in), ptr(acc_out), float(scale),
+                                 ptr(ws), ws.numel(), stream_ptr(x.device)))
+        return y if y is not None else acc_out
+
+    def item_rows(self, x_u, bwd=False):
+        """Partial [I, d]: C x_u (bwd: A^T x_u) summed over THIS shard's users."""
+        return self._spmm(self.graph.by_item, x_u, bwd)
+
+    def user_rows(self, x_i, bwd=False):
+        """[U_local, d]: A x_i (bwd: C^T x_i) for this shard's users."""
+        return self._spmm(self.graph.by_user, x_i, bwd)
+
+
+class ShardedPropagation:
+    """K-layer propagation and its adjoint over user shards (lightgcn_cu.py:420-448 /
+    Version-2/lighgcn_cu_pop.py:472-490 and their autograd)."""
+
+    def __init__(self, backend, num_layers: int, order: str, group=None):
+        if order not in ("jacobi", "gs"):
+            raise ValueError(order)
+        self.b, self.K, self.order, self.group = backend, int(num_layers), order, group
+
+    def forward(self, e0_u: torch.Tensor, e0_i: torch.Tensor):
+        """e0_u: this shard's user rows; e0_i: the replicated item table.  Returns (final_u shard, final_i)."""
+        s = 1.0 / (self.K + 1)
+        acc_u, acc_i = e0_u.clone(), e0_i.clone()
+        u, i = e0_u, e0_i
+        for _ in range(self.K):
+            i_new = all_reduce_sum(self.b.item_rows(u, False), self.group)
+            u_new = self.b.user_rows(i if self.order == "jacobi" else i_new, False)
+            acc_i += i_new
+            acc_u += u_new
+            u, i = u_new, i_new
+        return acc_u.mul_(s), acc_i.mul_(s)
+
+    def backward(self, g_u: torch.Tensor, g_i_total: torch.Tensor):
+        """g_u: dL/d(final_u) rows of this shard; g_i_total: dL/d(final_i) already summed over ranks.
+        Returns (dL/dE0_u shard, dL/dE0_i replicated)."""
+        s = 1.0 / (self.K + 1)
+        if self.order == "gs":
+            bu = g_u
+            for _ in range(self.K):
+                bi = all_reduce_sum(self.b.item_rows(bu, True), self.group).add_(g_i_total)
+                bu = self.b.user_rows(bi, True).add_(g_u)
+            return bu.mul(s), g_i_total.mul(s)
+        bu, bi = g_u, g_i_total
+        for _ in range(self.K):
+            nu = self.b.user_rows(bi, True).add_(g_u)
+            ni = all_reduce_sum(self.b.item_rows(bu, True), self.group).add_(g_i_total)
+            bu, bi = nu, ni
+        return bu.mul(s), bi.mul(s)
+
+
+def build_local_graph(local_edges, num_local_users, num_items, cred_local, variant, device, group=None) -> CredGraph:
+    """One shard's CredGraph; item degrees (weights, popularity law, alpha_i) are all-reduced."""
+    return build_graph(local_edges, num_local_users, num_items, cred_local, variant, device,
+                       reduce_item_degrees=lambda d: all_reduce_sum(d, group))
+
+
+class ShardedTrainStep:
+    """One training step over user shards: local sampling, sharded forward, fused loss on the local
+    triples (means over the GLOBAL batch), sharded backward, Adam on (local users, replicated items)."""
+
+    def __init__(self, graph: CredGraph, user_emb: torch.Tensor, item_emb: torch.Tensor, num_layers, order,
+                 lr=1e-3, reg_weight=1e-4, mix_pop=0.7, gamma=0.75, max_tries=50, seed=42, group=None):
+        self.graph, self.group = graph, group
+        self.eu = torch.nn.Parameter(user_emb.contiguous())
+        self.ei = torch.nn.Parameter(item_emb.contiguous())
+        self.prop = ShardedPropagation(CudaBackend(graph), num_layers, order, group)
+        self.sampler = TripleSampler(graph, mix_pop, gamma, max_tries, seed)
+        self.opt = torch.optim.Adam([self.eu, self.ei], lr=lr, fused=True)
+        self.reg = float(reg_weight)
+        self.eu.grad, self.ei.grad = torch.zeros_like(self.eu), torch.zeros_like(self.ei)
+        self.g_u = torch.empty_like(self.eu)
+        self.gi2 = torch.empty(2, *self.ei.shape, dtype=torch.float32, device=self.ei.device)   # [seed ; ego]
+        self.ego_u = torch.empty_like(self.eu)
+        self._bufs = {}
+
+    @torch.no_grad()
+    def __call__(self, users_local: torch.Tensor, batch_total: int | None = None):
+        """batch_total: global batch size (default: every rank holds a batch of this size)."""
+        g, dev = self.graph, self.eu.device
+        B = users_local.numel()
+        B_total = int(batch_total) if batch_total is not None else B * _world(self.group)
+        if B not in self._bufs:
+            self._bufs[B] = (torch.empty(3 * B, dtype=torch.int64, device=dev), bpr_buffers(g, B, dev))
+        plan, bufs = self._bufs[B]
+        pos, neg = self.sampler.sample(users_local)
+        bpr_plan(g, users_local, pos, neg, plan)
+        f_u, f_i = self.prop.forward(self.eu.data, self.ei.data)
+        self.g_u.zero_()
+        self.gi2.zero_()
+        self.ego_u.zero_()
+        loss, _, _, ego_rows, ego_coef = bpr_fused(g, f_u, f_i, self.eu.data, self.ei.data, users_local, pos, neg,
+                                                   self.reg, 0.0, None, self.g_u, self.gi2[0], plan, bufs, B_total)
+        apply_ego(g, ego_rows, ego_coef, self.eu.data, self.ei.data, self.ego_u, self.gi2[1])
+        all_reduce_sum(self.gi2, self.group)               # item seed and item L2 gradient in ONE collective
+        d_u, d_i = self.prop.backward(self.g_u, self.gi2[0])
+        self.eu.grad.copy_(d_u.add_(self.ego_u))
+        self.ei.grad.copy_(d_i.add_(self.gi2[1]))
+        self.opt.step()
+        return all_reduce_sum(loss.clone(), self.group)
+
+
+# ------------------------------------------------------------------------------------------
+# bench.py --gpus N (N > 1): weak scaling, one C2-shaped user shard per rank
+# ------------------------------------------------------------------------------------------
+def bench_main(args, rank: int, world: int, dev: torch.device):
+    from . import synth
+    shp = synth.SHAPES[args.workload]
+    sg = synth.make_graph(args.workload, seed=20240 + 1000 * (rank + 1), item_seed=20242)
+    U, I, d, K = sg.num_users, sg.num_items, shp["emb_dim"], shp["num_layers"]
+    E_local = sg.train_edges.shape[1]
+    gr = build_local_graph(sg.train_edges, U, I, sg.cred, shp["variant"], dev)
+    torch.manual_seed(42)
+    item_emb = torch.nn.init.xavier_uniform_(torch.empty(I, d)).to(dev)          # identical on every rank
+    torch.manual_seed(1000 + rank)
+    user_emb = torch.nn.init.xavier_uniform_(torch.empty(U, d)).to(dev)
+    step = ShardedTrainStep(gr, user_emb, item_emb, K, shp["order"], mix_pop=None if shp["variant"] == "cu" else 0.7)
+    train_users = torch.nonzero(gr.deg_u > 0).reshape(-1).cpu().numpy()
+    np.random.default_rng(42 + rank).shuffle(train_users)
+    nb = len(train_users) // args.batch
+    host_batches = [train_users[s * args.batch:(s + 1) * args.batch] for s in range(max(nb, 1))]
+    dev_batches = [torch.from_numpy(b).to(dev) for b in host_batches]
+    pinned = [torch.from_numpy(b).pin_memory() for b in host_batches]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    for s in range(max(args.warmup, 3)):
+        step(dev_batches[s % len(dev_batches)])
+    torch.cuda.synchronize()
+    dist.barrier()
+    launches0 = lib().cgx_launch_count()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    for s in range(args.steps):
+        flush.fill_(s & 0xff)
+        starts[s].record()
+        step(dev_batches[s % len(dev_batches)])
+        ends[s].record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    launches = lib().cgx_launch_count() - launches0
+    total_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in zip(starts, ends))], device=dev)
+    dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    loss_host = 0.0
+    for s in range(args.steps):
+        ub = pinned[s % len(pinned)].to(dev, non_blocking=True)
+        loss_host = float(step(ub).item())
+    torch.cuda.synchronize()
+    e2e = torch.tensor([1e3 * (time.perf_counter() - t0)], device=dev)
+    dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    edges = torch.tensor([E_local], dtype=torch.int64, device=dev)
+    dist.all_reduce(edges)
+    if rank == 0:
+        ms = float(total_ms.item()) / args.steps
+        e2e_ms = float(e2e.item()) / args.steps
+        E = int(edges.item())
+        print(json.dumps({
+            "metric": "edges/sec (3-layer cred-weighted LightGCN fwd+bwd)", "value": E / (ms / 1e3), "unit": "edges/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload} x {world}: one {U:,}-user shard per GPU ({E:,} train edges in "
+                                   f"total), {I:,} items replicated, user-sharded rows, item table all-reduced per layer",
+                       "emb_dim": d, "num_layers": K, "batch_users": args.batch * world,
+                       "step": "sample+fwd+loss+bwd+adam", "parallelism": f"user-shard x{world}",
+                       "l2": "flushed between timed steps (256 MiB write)"},
+            "e2e": {"value": E / (e2e_ms / 1e3), "unit": "edges/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(host_batches[0].nbytes) * world, "d2h_bytes_per_step": 4 * world},
+            "gpu_launches": int(launches), "loss": loss_host,
+            "collectives_per_step": 2 * K + 2,
+        }))
+    dist.barrier()
+    dist.destroy_process_group()

@@ -79,6 +79,7 @@ def make_graph(
     cluster: int | None = None,
     duplicate_edges: int = 0,
     split=(0.8, 0.1, 0.1),
+    item_seed: int | None = None,
 ) -> SynthGraph:
     """Build one synthetic graph.  `name` picks a BASELINE shape; explicit sizes override it.
 
@@ -111,7 +112,8 @@ def make_graph(
     E_gen = E - E_fake
 
     # genuine edges: log-normal activity x Zipf item choice, de-duplicated
-    cdf, perm = _zipf_cdf(I, 0.8, rng)
+    # item_seed fixes the popularity ranking independently of `seed` (user shards of one catalogue)
+    cdf, perm = _zipf_cdf(I, 0.8, rng if item_seed is None else np.random.default_rng(item_seed))
     keys = np.empty(0, dtype=np.int64)
     want = E_gen
     for _ in range(8):

@@ -97,6 +97,9 @@ size_t cgx_graph_build_workspace_bytes(int64_t num_edges, int32_t num_users, int
  * cred: device float32[U] already clipped to [0, 1] (CU:359).
  * alpha: device float32[I], required for CGX_VARIANT_DA only: 1/log1p(max(deg_i,1)) computed with
  *        the caller's NumPy (libdevice log1pf is not bit-identical to NumPy's; DA:379-380).
+ * deg_i_weights: NULL, or device int32[I] item degrees to use in the weight formulas instead of the
+ *        histogram of these edges -- for a user-sharded build, where `edges` holds one shard's users
+ *        but an item's degree counts its edges on every shard.
  * Outputs (all device, caller-allocated):
  *   deg_u int32[U], deg_i int32[I]                      np.bincount, duplicates counted
  *   samp_indptr int64[U+1], samp_idx int32[E]           edges_to_user_csr
@@ -107,7 +110,7 @@ size_t cgx_graph_build_workspace_bytes(int64_t num_edges, int32_t num_users, int
  * deg_only != 0 stops after the degree vectors (used to compute `alpha` for the DA variant). */
 int cgx_graph_build(const int32_t* edges_u, const int32_t* edges_i, int64_t num_edges,
                     int32_t num_users, int32_t num_items, const float* cred, int variant,
-                    const float* alpha, int32_t* deg_u, int32_t* deg_i,
+                    const float* alpha, const int32_t* deg_i_weights, int32_t* deg_u, int32_t* deg_i,
                     int64_t* samp_indptr, int32_t* samp_idx,
                     int64_t* user_indptr, int32_t* user_idx, float* user_val_fwd, float* user_val_bwd,
                     int64_t* item_indptr, int32_t* item_idx, float* item_val_fwd, float* item_val_bwd,
@@ -174,6 +177,8 @@ int cgx_propagate_bwd(const cgx_csr* by_user, const cgx_csr* by_item, int order,
  *                          ego_rows[k] >= 0 (rows >= U are items, offset by U; each row appears once)
  *                          -- done by cgx_bpr_apply_ego
  *   loss_out float[1]      NaN if any index of the batch was out of range
+ *   batch_total            the mean's denominator: `batch`, or -- when the batch is sharded over ranks -- the
+ *                          global batch size (the rank losses then add up to the global loss)
  * ------------------------------------------------------------------------------------------ */
 /* Scatter plan: the 3B (row, entry) keys of a batch sorted by row, uint64[3B] (device).  Depends on
  * the indices only -- build it on a side stream while the forward propagation runs. */
@@ -183,7 +188,7 @@ int cgx_bpr_plan(const int64_t* users, const int64_t* pos, const int64_t* neg, i
                  void* workspace, size_t workspace_bytes, void* stream);
 size_t cgx_bpr_workspace_bytes(int64_t batch, int32_t num_users, int32_t num_items);
 int cgx_bpr_fwd_bwd(const int64_t* users, const int64_t* pos, const int64_t* neg, int64_t batch,
-                    const uint64_t* plan, int32_t num_users, int32_t num_items, int32_t d,
+                    int64_t batch_total, const uint64_t* plan, int32_t num_users, int32_t num_items, int32_t d,
                     const float* f_u, const float* f_i, const float* e0_u, const float* e0_i,
                     const float* pop, float reg_weight, float fair_weight,
                     float* loss_out, float* g_u, float* g_i,

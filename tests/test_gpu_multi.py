@@ -1,0 +1,87 @@
+"""2-GPU check of the user-sharded path over NCCL: sharded forward / loss / backward on two
+ranks == the single-GPU path on the whole graph (<= 1e-4 relative).  Skipped with < 2 GPUs
+(`gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`)."""
+import os
+import pathlib
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from credgcn import graph, model, synth
+        from credgcn.sharded import (CudaBackend, ShardedPropagation, all_reduce_sum, build_local_graph,
+                                     partition_users, shard_edges)
+        sg = synth.make_graph("C1", duplicate_edges=100)
+        U, I, d, K = sg.num_users, sg.num_items, 64, 3
+        deg_u = np.bincount(sg.train_edges[0], minlength=U)
+        bounds = partition_users(deg_u, world)
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        users, pos, neg = synth.make_triples(sg, 2048)
+        mine = (users >= lo) & (users < hi)
+        torch.manual_seed(0)
+        eu = torch.nn.init.xavier_uniform_(torch.empty(U, d))
+        ei = torch.nn.init.xavier_uniform_(torch.empty(I, d))
+        res = {}
+        for variant, order in (("v2", "gs"), ("cu", "jacobi"), ("da", "gs")):
+            gl = build_local_graph(shard_edges(sg.train_edges, bounds, rank), hi - lo, I, sg.cred[lo:hi], variant, dev)
+            prop = ShardedPropagation(CudaBackend(gl), K, order)
+            eu_l, ei_d = eu[lo:hi].to(dev).contiguous(), ei.to(dev)
+            f_u, f_i = prop.forward(eu_l, ei_d)
+            g_u = torch.zeros_like(eu_l)
+            gi2 = torch.zeros(2, I, d, device=dev)
+            ego_u = torch.zeros_like(eu_l)
+            loss, _, _, ego_rows, ego_coef = model.bpr_fused(gl, f_u, f_i, eu_l, ei_d, users[mine] - lo, pos[mine],
+                                                             neg[mine], 1e-4, 0.0, None, g_u, gi2[0],
+                                                             batch_total=len(users))
+            model.apply_ego(gl, ego_rows, ego_coef, eu_l, ei_d, ego_u, gi2[1])
+            all_reduce_sum(gi2)
+            all_reduce_sum(loss)
+            d_u, d_i = prop.backward(g_u, gi2[0])
+            d_u, d_i = d_u + ego_u, d_i + gi2[1]
+            if rank == 0:      # single-GPU truth on the whole graph
+                gr = graph.build_graph(sg.train_edges, U, I, sg.cred, variant, dev)
+                Net = model.CredLightGCN if variant == "cu" else model.LightGCN
+                ops = (gr.operator("C"), gr.operator("A")) if variant == "cu" else (gr.operator("A"), gr.operator("C"))
+                net = Net(U, I, d, K, *ops)
+                net.load_state_dict({"user_emb.weight": eu, "item_emb.weight": ei})
+                net = net.to(dev)
+                st = model.TrainStep(net, reg_weight=1e-4)
+                want = st.forward_backward(users, pos, neg)
+                rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+                res[variant] = dict(
+                    loss=abs(loss.item() - want.item()) / abs(want.item()),
+                    f_u=rel(f_u, st.f_u[lo:hi]), f_i=rel(f_i, st.f_i),
+                    d_u=rel(d_u, net.user_emb.weight.grad[lo:hi]), d_i=rel(d_i, net.item_emb.weight.grad),
+                    deg=int((gl.deg_i != gr.deg_i).sum().item()))
+        if rank == 0:
+            out[0] = res
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_gpu_sharded_equals_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    port = 29600 + (os.getpid() % 2000)
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+        res = dict(out)[0]
+    for variant, e in res.items():
+        assert e.pop("deg") == 0, variant
+        assert max(e.values()) < 1e-4, (variant, e)

@@ -1,0 +1,112 @@
+"""Host-side logic of the user-sharded path on CPU: world_size-2 gloo process group, with an
+oracle-backed stand-in for the two per-shard products (the product backend is CUDA only).
+Checks that the sharded forward / adjoint schedules with their all-reduces reproduce the
+single-process oracle, for both layer orders."""
+import os
+import sys
+import pathlib
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+for p in (ROOT, ROOT / "oracle"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+
+
+def test_partition_users_balances_nonzeros():
+    from credgcn.sharded import partition_users, shard_edges
+    rng = np.random.default_rng(0)
+    deg = rng.zipf(1.6, size=5000).clip(max=3000)
+    for world in (1, 2, 3, 8):
+        b = partition_users(deg, world)
+        assert b[0] == 0 and b[-1] == deg.size and (np.diff(b) >= 0).all() and len(b) == world + 1
+        loads = np.array([deg[b[r]:b[r + 1]].sum() for r in range(world)])
+        assert loads.sum() == deg.sum()
+        assert loads.max() <= deg.sum() / world + deg.max()          # within one row of the ideal split
+    edges = np.stack([rng.integers(0, 100, 1000), rng.integers(0, 50, 1000)]).astype(np.int32)
+    b = partition_users(np.bincount(edges[0], minlength=100), 4)
+    parts = [shard_edges(edges, b, r) for r in range(4)]
+    assert sum(p.shape[1] for p in parts) == 1000
+    for r, p in enumerate(parts):
+        assert p.shape[1] == 0 or (p[0].min() >= 0 and p[0].max() < b[r + 1] - b[r])
+
+
+class OracleShardBackend:
+    """Test double of sharded.CudaBackend: SciPy products of one user shard, weights from GLOBAL degrees."""
+
+    def __init__(self, edges, lo, hi, num_items, cred, variant, deg_i_global):
+        import credgcn_oracle as orc
+        u = edges[0].astype(np.int64)
+        keep = (u >= lo) & (u < hi)
+        ul, il = u[keep] - lo, edges[1].astype(np.int64)[keep]
+        deg_u = np.bincount(ul, minlength=hi - lo).astype(np.float32)
+        w_a, w_c = orc.edge_weights(variant, ul, il, deg_u, deg_i_global, cred[lo:hi])
+        import scipy.sparse as sp
+        ar, ac, av = orc.coalesce(ul, il, w_a)
+        cr, cc, cv = orc.coalesce(il, ul, w_c)
+        self.A = sp.csr_matrix((av, (ar, ac)), shape=(hi - lo, num_items), dtype=np.float32)
+        self.C = sp.csr_matrix((cv, (cr, cc)), shape=(num_items, hi - lo), dtype=np.float32)
+
+    def item_rows(self, x_u, bwd=False):
+        m = self.A.T if bwd else self.C
+        return torch.from_numpy(np.asarray(m @ x_u.numpy(), dtype=np.float32))
+
+    def user_rows(self, x_i, bwd=False):
+        m = self.C.T if bwd else self.A
+        return torch.from_numpy(np.asarray(m @ x_i.numpy(), dtype=np.float32))
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import credgcn_oracle as orc
+        from credgcn import synth
+        from credgcn.sharded import ShardedPropagation, partition_users
+        sg = synth.make_graph("C1", num_users=240, num_items=150, num_edges=6000, duplicate_edges=30)
+        U, I, d, K = sg.num_users, sg.num_items, 16, 3
+        deg_u, deg_i = orc.degrees(sg.train_edges, U, I)
+        bounds = partition_users(deg_u, world)
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        rng = np.random.default_rng(5)
+        eu = (rng.standard_normal((U, d)) * 0.1).astype(np.float32)
+        ei = (rng.standard_normal((I, d)) * 0.1).astype(np.float32)
+        gu = rng.standard_normal((U, d)).astype(np.float32)
+        gi = rng.standard_normal((I, d)).astype(np.float32)
+        errs = {}
+        for variant, order in (("cu", "jacobi"), ("v2", "gs"), ("da", "gs")):
+            ops = orc.Operators(sg.train_edges, U, I, sg.cred, variant)
+            be = OracleShardBackend(sg.train_edges, lo, hi, I, sg.cred, variant, deg_i)
+            prop = ShardedPropagation(be, K, order)
+            fu, fi = prop.forward(torch.from_numpy(eu[lo:hi].copy()), torch.from_numpy(ei.copy()))
+            wu, wi = orc.propagate(ops, eu, ei, K, order)
+            # each rank contributes gi / world to the item seed; the caller reduces it
+            g_i_total = torch.from_numpy(gi / world)
+            dist.all_reduce(g_i_total)
+            bu, bi = prop.backward(torch.from_numpy(gu[lo:hi].copy()), g_i_total)
+            ou, oi = orc.propagate_backward(ops, gu, gi, K, order)
+            rel = lambda a, b: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+            errs[variant] = (rel(fu.numpy(), wu[lo:hi]), rel(fi.numpy(), wi), rel(bu.numpy(), ou[lo:hi]),
+                             rel(bi.numpy(), oi))
+        out[rank] = errs
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_sharded_propagation_matches_single_process_world2():
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+        res = dict(out)
+    assert set(res) == {0, 1}
+    for rank, errs in res.items():
+        for variant, e in errs.items():
+            assert max(e) < 1e-5, (rank, variant, e)
