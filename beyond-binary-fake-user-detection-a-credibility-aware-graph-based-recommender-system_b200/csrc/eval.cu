@@ -70,7 +70,11 @@ __device__ __forceinline__ void merge_candidates(int lane, int K, float* ls, int
   __syncwarp();
 }
 
+// row_list / n_rows_dev (both optional): evaluate only the rows row_list[0 .. *n_rows_dev) of `users`
+// (used to redo the rows the tensor-core path could not prove complete); outputs go to those rows.
 __global__ void __launch_bounds__(EV_THREADS) k_eval_fp32(const int64_t* __restrict__ users, int64_t n_users,
+                                                          const int32_t* __restrict__ row_list,
+                                                          const int32_t* __restrict__ n_rows_dev,
                                                           const float* __restrict__ f_u,
                                                           const float* __restrict__ f_i, int32_t I, int32_t d,
                                                           const int64_t* __restrict__ tr_indptr,
@@ -87,16 +91,21 @@ __global__ void __launch_bounds__(EV_THREADS) k_eval_fp32(const int64_t* __restr
   float* thr = reinterpret_cast<float*>(list_i + EV_TU * K);    // [EV_TU]
   int* cnt = reinterpret_cast<int*>(thr + EV_TU);               // [EV_TU]
   int64_t* urow = reinterpret_cast<int64_t*>(cnt + EV_TU);      // [EV_TU] global user ids (8-byte aligned by layout)
+  int64_t* orow = urow + EV_TU;                                 // [EV_TU] output rows
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ty = tid >> 4, tx = tid & 15;  // 16 x 16 threads: 4 users x 8 items each
   const int64_t u0 = int64_t(blockIdx.x) * EV_TU;
+  if (n_rows_dev != nullptr) n_users = *n_rows_dev;
+  if (u0 >= n_users) return;
 
   for (int p = tid; p < EV_TU * K; p += EV_THREADS) { list_s[p] = -FLT_MAX; list_i[p] = INT32_MAX; }
   if (tid < EV_TU) {
     thr[tid] = -FLT_MAX;
     cnt[tid] = 0;
-    urow[tid] = (u0 + tid < n_users) ? users[u0 + tid] : -1;
+    const int64_t r = (u0 + tid < n_users) ? (row_list ? int64_t(row_list[u0 + tid]) : u0 + tid) : -1;
+    orow[tid] = r;
+    urow[tid] = r >= 0 ? users[r] : -1;
   }
   __syncthreads();
 
@@ -175,16 +184,16 @@ __global__ void __launch_bounds__(EV_THREADS) k_eval_fp32(const int64_t* __restr
 
   for (int p = tid; p < EV_TU * K; p += EV_THREADS) {
     const int ul = p / K, r = p % K;
-    if (u0 + ul < n_users) {
-      out_ids[(u0 + ul) * K + r] = list_i[p];
-      out_scores[(u0 + ul) * K + r] = list_s[p];
+    if (orow[ul] >= 0) {
+      out_ids[orow[ul] * K + r] = list_i[p];
+      out_scores[orow[ul] * K + r] = list_s[p];
     }
   }
 }
 
 static size_t eval_smem_bytes(int K) {
   return size_t(EV_KC * EV_TU + EV_KC * EV_TIP) * 4 + size_t(EV_TU) * EV_TI * 8 + size_t(EV_TU) * K * 8 +
-         size_t(EV_TU) * 8 + size_t(EV_TU) * 8 + 64;
+         size_t(EV_TU) * 8 + size_t(EV_TU) * 16 + 64;
 }
 
 template <int G, int V>
@@ -215,6 +224,18 @@ int eval_topk_tc(const int64_t* users, int64_t n_users, const float* f_u, const 
                  float* out_scores, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t eval_topk_tc_workspace(int64_t n_users, int32_t I, int32_t d, int32_t K, int precision);
 
+// exact path on (a subset of) the rows; grid sized for max_rows, CTAs past *n_rows_dev exit at once
+int eval_fp32_rows(const int64_t* users, const int32_t* row_list, const int32_t* n_rows_dev, int64_t max_rows,
+                   const float* f_u, const float* f_i, int32_t I, int32_t d, const int64_t* tr_indptr,
+                   const int32_t* tr_idx, int32_t K, int32_t* out_ids, float* out_scores, cudaStream_t stream) {
+  const size_t smem = eval_smem_bytes(K);
+  CGX_CUDA(cudaFuncSetAttribute(k_eval_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_eval_fp32<<<(unsigned)ceil_div(max_rows, EV_TU), EV_THREADS, smem, stream>>>(
+      users, max_rows, row_list, n_rows_dev, f_u, f_i, I, d, tr_indptr, tr_idx, K, out_ids, out_scores);
+  CGX_LAUNCH_CHECK();
+  return CGX_OK;
+}
+
 }  // namespace cgx
 
 using namespace cgx;
@@ -237,12 +258,8 @@ extern "C" int cgx_eval_topk(const int64_t* users, int64_t n_users, const float*
   if (precision != CGX_SCORE_FP32)
     return eval_topk_tc(users, n_users, f_u, f_i, I, d, train_indptr, train_idx, k, precision, out_ids, out_scores,
                         workspace, workspace_bytes, stream);
-  const size_t smem = eval_smem_bytes(k);
-  CGX_CUDA(cudaFuncSetAttribute(k_eval_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_eval_fp32<<<(unsigned)ceil_div(n_users, EV_TU), EV_THREADS, smem, stream>>>(
-      users, n_users, f_u, f_i, I, d, train_indptr, train_idx, k, out_ids, out_scores);
-  CGX_LAUNCH_CHECK();
-  return CGX_OK;
+  return eval_fp32_rows(users, nullptr, nullptr, n_users, f_u, f_i, I, d, train_indptr, train_idx, k, out_ids,
+                        out_scores, stream);
 }
 
 extern "C" int cgx_score_candidates(const int64_t* users, const int64_t* cand, int64_t n_users, int32_t n_cand,

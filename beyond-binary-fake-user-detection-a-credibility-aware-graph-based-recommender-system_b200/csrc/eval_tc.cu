@@ -1,15 +1,492 @@
-// Tensor-core (tcgen05) score path for full-rank evaluation -- placeholder until the UMMA kernel
-// lands; the fp32 path in eval.cu is complete and exact.
+// Tensor-core score path of the full-rank evaluation: tcgen05.mma (UMMA) user x item score tiles
+// with accumulators in TMEM, fused with the train-item mask and a per-row running top-K', then an
+// exact fp32 re-scoring of the K' candidates.
+//
+// Replaces (reference, /root/reference): the per-user score + mask + argsort loop of
+// evaluate_full_ranking, Version-2/lighgcn_cu_pop.py:691-704 -- the only dense contraction on the
+// path (2 * U_eval * I * d FLOPs).
+//
+// Numerics.  The reference scores in fp32.  precision = BF16X3 splits every fp32 value into
+// hi + lo bf16 parts and contracts [a_hi | a_hi | a_lo] . [b_hi | b_lo | b_hi] (K' = 3d) on the
+// tensor cores: |error| <= ~2^-16 |a||b|.  The tensor-core pass only SELECTS K' = K + margin
+// candidates per user; k_rescore then recomputes their scores exactly as the fp32 kernel does (same
+// fmaf order -> same bits), sorts by (score desc, id asc) and proves the top K complete:
+// if exact_score[K-1] > approx_score[K'-1] + eps(user) no item outside the candidate list can reach
+// the top K.  Rows that fail the proof are redone by the exact fp32 kernel (eval.cu).  The result
+// is therefore identical to CGX_SCORE_FP32.  precision = BF16 is the single-pass variant (K' = d,
+// error ~2^-8 relative, no proof, no redo) for callers that accept approximate ranking.
+//
+// Kernel anatomy (one CTA per 128 users, 288 threads):
+//   warp 0      TMEM allocation, then one elected lane issues tcgen05.mma (M=128, N=128, K=16 per
+//               instruction, K'/16 instructions per item tile), tcgen05.commit -> mbarriers
+//   warps 1-4   epilogue: tcgen05.ld 32x32b.x16 -> registers, predicated append of scores >= the row
+//               threshold, warp-uniform drain into the row's K' kept candidates (one thread per user)
+//   warps 5-8   producers: cp.async (16 B, L2-only) the next 128-item tile of the bf16 item table into
+//               shared memory in the canonical K-major SWIZZLE_128B UMMA layout (64-column k-blocks,
+//               128-byte rows, 16-byte chunks XOR-ed with row%8 -- what TMA would write), so that a
+//               row's 8 chunks are one coalesced 128-byte global read AND one conflict-free shared
+//               write; then fence to the async proxy and arrive on the stage's mbarrier
+// Two smem stages for B and two 128-column TMEM accumulators: the MMA of tile j+1 overlaps the
+// epilogue of tile j.
+#include <cuda_bf16.h>
+#include <float.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cgx {
 
-size_t eval_topk_tc_workspace(int64_t, int32_t, int32_t, int32_t, int) { return 256; }
+int eval_fp32_rows(const int64_t* users, const int32_t* row_list, const int32_t* n_rows_dev, int64_t max_rows,
+                   const float* f_u, const float* f_i, int32_t I, int32_t d, const int64_t* tr_indptr,
+                   const int32_t* tr_idx, int32_t K, int32_t* out_ids, float* out_scores, cudaStream_t stream);
 
-int eval_topk_tc(const int64_t*, int64_t, const float*, const float*, int32_t, int32_t, const int64_t*,
-                 const int32_t*, int32_t, int precision, int32_t*, float*, void*, size_t, cudaStream_t) {
-  set_error("eval_topk: score precision %d is not implemented yet (use CGX_SCORE_FP32)", precision);
-  return CGX_ERR_UNSUPPORTED;
+constexpr int TC_M = 128;          // users per CTA
+constexpr int TC_N = 128;          // items per tile
+constexpr int TC_THREADS = 288;    // 9 warps
+constexpr int TC_STAGES = 2;
+constexpr float TC_MASKED = -1e9f;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major SWIZZLE_128B operand tile: k-block kb (64 bf16 = 128 B per row) at kb * rows * 128; inside
+// a k-block row r occupies bytes [r*128, r*128+128) with its 16-byte chunk c stored at chunk c ^ (r % 8).
+// Descriptor: start address >> 4, LBO field 1 (unused for swizzled K-major), SBO = 1024 B (8 rows),
+// version 1 (Blackwell), layout type 2 (SWIZZLE_128B).  A K=16 step inside a k-block advances the
+// start address by 32 bytes.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return uint64_t((smem_addr & 0x3FFFF) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) |
+         (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gmem_src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(r[q]);   // valid after tmem_wait_ld()
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ bool tc_better(float sa, int32_t ia, float sb, int32_t ib) {
+  return sa > sb || (sa == sb && ia < ib);
+}
+__device__ __forceinline__ bool tc_in_row(const int32_t* __restrict__ idx, int64_t lo, const int64_t end,
+                                          int32_t item) {
+  int64_t hi = end;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (__ldg(idx + mid) < item) lo = mid + 1; else hi = mid;
+  }
+  return lo < end && __ldg(idx + lo) == item;
+}
+
+// ---- operand preparation: fp32 rows -> bf16 [hi | hi | lo] (users) / [hi | lo | hi] (items) ------
+__global__ void k_tc_convert(const float* __restrict__ src, const int64_t* __restrict__ rows, int64_t n_rows,
+                             int32_t d, int parts, int Kp, int is_item, __nv_bfloat16* __restrict__ dst,
+                             float* __restrict__ norms, unsigned int* __restrict__ max_norm_bits) {
+  const int64_t r = int64_t(blockIdx.x) * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= n_rows) return;
+  const int64_t sr = rows ? rows[r] : r;
+  for (int c = parts * d + lane; c < Kp; c += 32) dst[r * Kp + c] = __float2bfloat16_rn(0.f);   // pad to 64 columns
+  float ss = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    const float x = src[sr * d + c];
+    ss = fmaf(x, x, ss);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    dst[r * Kp + c] = hi;
+    if (parts == 3) {
+      const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+      dst[r * Kp + d + c] = is_item ? lo : hi;
+      dst[r * Kp + 2 * d + c] = is_item ? hi : lo;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane == 0) {
+    const float nrm = sqrtf(ss);
+    if (norms) norms[r] = nrm;
+    if (max_norm_bits) atomicMax(max_norm_bits, __float_as_uint(nrm));   // non-negative floats order as uints
+  }
+}
+
+// ---- the UMMA kernel ---------------------------------------------------------------------------
+template <int KC, int BC>   // kept candidates per user, arrival-buffer slots per user
+__global__ void __launch_bounds__(TC_THREADS, 1) k_eval_umma(const __nv_bfloat16* __restrict__ Au,   // [n_users, Kp]
+                                                             const __nv_bfloat16* __restrict__ Bi,   // [I, Kp]
+                                                             const int64_t* __restrict__ users, int64_t n_users,
+                                                             int32_t I, int32_t Kp,
+                                                             const int64_t* __restrict__ tr_indptr,
+                                                             const int32_t* __restrict__ tr_idx,
+                                                             int32_t* __restrict__ cand_ids,       // [n_users, KC]
+                                                             float* __restrict__ cand_thr) {        // [n_users]
+  extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+  // SWIZZLE_128B atoms must start on 1024-byte boundaries of the shared window
+  unsigned char* tc_smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
+  const uint32_t tile_bytes = uint32_t(TC_M) * Kp * 2;           // one operand tile (128 rows x Kp bf16)
+  unsigned char* smem_a = tc_smem;
+  unsigned char* smem_b = tc_smem + tile_bytes;                   // TC_STAGES tiles
+  float* list_s = reinterpret_cast<float*>(smem_b + TC_STAGES * tile_bytes);   // [KC][128]  unsorted candidates
+  int32_t* list_i = reinterpret_cast<int32_t*>(list_s + KC * TC_M);           // [KC][128]
+  float* buf_s = reinterpret_cast<float*>(list_i + KC * TC_M);                // [BC][128]  arrivals not yet merged
+  int32_t* buf_i = reinterpret_cast<int32_t*>(buf_s + BC * TC_M);             // [BC][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(buf_i + BC * TC_M);
+  uint64_t* full_bar = bars;                 // [TC_STAGES]  producers -> MMA
+  uint64_t* empty_bar = bars + TC_STAGES;    // [TC_STAGES]  MMA (commit) -> producers
+  uint64_t* tfull_bar = bars + 2 * TC_STAGES;   // [2]       MMA (commit) -> epilogue
+  uint64_t* tempty_bar = bars + 2 * TC_STAGES + 2;  // [2]   epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t u0 = int64_t(blockIdx.x) * TC_M;
+  const int n_tiles = (I + TC_N - 1) / TC_N;
+  const int n_kb = Kp / 64;                      // 64-column k-blocks (Kp is padded to a multiple of 64)
+  const int chunks = TC_M * n_kb * 8;            // 16-byte chunks per operand tile
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar + s, 128); mbar_init(empty_bar + s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + a, 1); mbar_init(tempty_bar + a, 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // A tile: this CTA's 128 users, staged once by every thread (rows past n_users are zero)
+  for (int q = threadIdx.x; q < chunks; q += TC_THREADS) {
+    const int c = q & 7, r = (q >> 3) & (TC_M - 1), kb = q >> 10;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (u0 + r < n_users) v = *reinterpret_cast<const uint4*>(Au + (u0 + r) * Kp + kb * 64 + c * 8);
+    *reinterpret_cast<uint4*>(smem_a + kb * (TC_M * 128) + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== MMA issuer =====
+    // idesc: c=F32 (1<<4), a=BF16 (1<<7), b=BF16 (1<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(TC_N >> 3) << 17) | (uint32_t(TC_M >> 4) << 24);
+    const uint32_t a_addr = smem_u32(smem_a);
+    for (int j = 0; j < n_tiles; ++j) {
+      const int s = j % TC_STAGES, a = j & 1;
+      mbar_wait(full_bar + s, (j / TC_STAGES) & 1);
+      mbar_wait(tempty_bar + a, ((j >> 1) & 1) ^ 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t b_addr = smem_u32(smem_b + s * tile_bytes);
+        for (int kb = 0; kb < n_kb; ++kb) {
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            umma_bf16(tmem_base + a * TC_N, umma_desc_sw128(a_addr + kb * (TC_M * 128) + k4 * 32),
+                      umma_desc_sw128(b_addr + kb * (TC_N * 128) + k4 * 32), idesc, (kb | k4) ? 1u : 0u);
+          }
+        }
+        umma_commit(empty_bar + s);    // smem stage reusable once these MMAs have read it
+        umma_commit(tfull_bar + a);    // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 5) {
+    // ===== producers: stage item tiles with cp.async, one group per tile, two tiles in flight =====
+    const int pt = threadIdx.x - 5 * 32;   // 0..127
+    for (int j = 0; j <= n_tiles; ++j) {
+      if (j < n_tiles) {
+        const int s = j % TC_STAGES;
+        mbar_wait(empty_bar + s, ((j / TC_STAGES) & 1) ^ 1);
+        const uint32_t dstb = smem_u32(smem_b + s * tile_bytes);
+        const int64_t i0 = int64_t(j) * TC_N;
+        for (int q = pt; q < chunks; q += 128) {
+          const int c = q & 7, r = (q >> 3) & (TC_N - 1), kb = q >> 10;
+          const bool ok = i0 + r < I;
+          const __nv_bfloat16* src = Bi + (ok ? (i0 + r) : 0) * Kp + kb * 64 + c * 8;
+          cp_async16(dstb + kb * (TC_N * 128) + r * 128 + ((c ^ (r & 7)) << 4), src, ok ? 16u : 0u);   // 0 -> zero fill
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (j > 0) {   // tile j-1 has landed (at most the newest group may still be in flight)
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(full_bar + (j - 1) % TC_STAGES);
+      }
+    }
+  } else {
+    // ===== epilogue: one thread per user row =====
+    // Scores >= the row's threshold are appended (predicated store, no branch) to a BC-slot buffer; when
+    // some lane's buffer could overflow in the next 16-column chunk the WARP drains with all lanes
+    // active: train-item mask by a cursor over the sorted train row (arrivals come in increasing item
+    // order), then "replace the weakest of the K' kept candidates and rescan for the new weakest" -- a
+    // loop of fixed length, so lanes do not diverge on data.  Batching arrivals over several chunks
+    // keeps most lanes busy in a drain (a lane sees ~0.8 arrivals per 128-item tile in steady state).
+    // The kept list stays unsorted; k_rescore ranks it.  TMEM loads are software pipelined.
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;
+    const int64_t ug = u0 + row;
+    const bool live = ug < n_users;
+    int64_t tr_cur = 0, tr_hi = 0;
+    if (live) {
+      const int64_t uid = users[ug];
+      tr_cur = __ldg(tr_indptr + uid);
+      tr_hi = __ldg(tr_indptr + uid + 1);
+    }
+    int32_t next_masked = tr_cur < tr_hi ? __ldg(tr_idx + tr_cur) : INT32_MAX;
+    for (int p = 0; p < KC; ++p) { list_s[p * TC_M + row] = -FLT_MAX; list_i[p * TC_M + row] = INT32_MAX; }
+    float thr = -FLT_MAX;      // score of the weakest kept candidate
+    int32_t thr_id = INT32_MAX;
+    int weakest = 0;           // its slot
+    int cnt = 0;               // arrivals waiting in the buffer
+
+    auto drain = [&]() {
+      for (int e = 0; e < cnt; ++e) {
+        float sc = buf_s[e * TC_M + row];
+        const int32_t item = buf_i[e * TC_M + row];
+        while (next_masked < item) {
+          ++tr_cur;
+          next_masked = tr_cur < tr_hi ? __ldg(tr_idx + tr_cur) : INT32_MAX;
+        }
+        if (next_masked == item) sc = TC_MASKED;
+        if (tc_better(sc, item, thr, thr_id)) {
+          list_s[weakest * TC_M + row] = sc;
+          list_i[weakest * TC_M + row] = item;
+          thr = sc;
+          thr_id = item;
+#pragma unroll 8
+          for (int p = 0; p < KC; ++p) {   // new weakest
+            const float ps = list_s[p * TC_M + row];
+            const int32_t pi = list_i[p * TC_M + row];
+            if (tc_better(thr, thr_id, ps, pi)) { thr = ps; thr_id = pi; weakest = p; }
+          }
+        }
+      }
+      cnt = 0;
+    };
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const int a = j & 1;
+      mbar_wait(tfull_bar + a, (j >> 1) & 1);
+      tc_fence_after();
+      const int32_t i0 = j * TC_N;
+      const uint32_t tbase = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(a * TC_N);
+      float v[2][16];
+      tmem_ld16(tbase, v[0]);
+      tmem_wait_ld();
+#pragma unroll
+      for (int ch = 0; ch < TC_N / 16; ++ch) {
+        if (ch + 1 < TC_N / 16) tmem_ld16(tbase + (ch + 1) * 16, v[(ch + 1) & 1]);   // in flight during the scan below
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int32_t item = i0 + ch * 16 + q;
+          if (live && v[ch & 1][q] >= thr && item < I) {
+            buf_s[cnt * TC_M + row] = v[ch & 1][q];
+            buf_i[cnt * TC_M + row] = item;
+            ++cnt;
+          }
+        }
+        if (__any_sync(0xffffffffu, cnt > BC - 16)) drain();
+        if (ch + 1 < TC_N / 16) tmem_wait_ld();
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar + a);
+    }
+    drain();
+    if (live) {
+      for (int p = 0; p < KC; ++p) cand_ids[ug * KC + p] = list_i[p * TC_M + row];
+      cand_thr[ug] = thr;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+  }
+}
+
+// ---- exact re-scoring of the candidates: one warp per user --------------------------------------
+template <int KC>
+__global__ void __launch_bounds__(256) k_rescore(const int64_t* __restrict__ users, int64_t n_users,
+                                                 const float* __restrict__ f_u, const float* __restrict__ f_i,
+                                                 int32_t d, const int64_t* __restrict__ tr_indptr,
+                                                 const int32_t* __restrict__ tr_idx,
+                                                 const int32_t* __restrict__ cand_ids, const float* __restrict__ cand_thr,
+                                                 const float* __restrict__ u_norm, const unsigned int* __restrict__ max_norm_bits,
+                                                 float eps_rel, int32_t K, int32_t* __restrict__ out_ids,
+                                                 float* __restrict__ out_scores, int32_t* __restrict__ redo_rows,
+                                                 int32_t* __restrict__ n_redo) {
+  constexpr int PER = KC / 32;
+  const int lane = threadIdx.x & 31;
+  const int64_t r = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= n_users) return;
+  const int64_t uid = users[r];
+  const int64_t lo = __ldg(tr_indptr + uid), hi = __ldg(tr_indptr + uid + 1);
+  const float* urow = f_u + uid * d;
+  float sc[PER];
+  int32_t id[PER];
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    id[q] = cand_ids[r * KC + q * 32 + lane];
+    if (id[q] == INT32_MAX) { sc[q] = -FLT_MAX; continue; }
+    const float* irow = f_i + int64_t(id[q]) * d;
+    float acc = 0.f;
+    for (int k = 0; k < d; ++k) acc = fmaf(__ldg(urow + k), __ldg(irow + k), acc);   // same order as k_eval_fp32
+    sc[q] = tc_in_row(tr_idx, lo, hi, id[q]) ? TC_MASKED : acc;
+  }
+  // rank of every candidate under (score desc, id asc)
+  int rank[PER];
+#pragma unroll
+  for (int q = 0; q < PER; ++q) rank[q] = 0;
+#pragma unroll
+  for (int q2 = 0; q2 < PER; ++q2) {
+    for (int l = 0; l < 32; ++l) {
+      const float os = __shfl_sync(0xffffffffu, sc[q2], l);
+      const int32_t oi = __shfl_sync(0xffffffffu, id[q2], l);
+#pragma unroll
+      for (int q = 0; q < PER; ++q) rank[q] += tc_better(os, oi, sc[q], id[q]) ? 1 : 0;
+    }
+  }
+  float kth = -FLT_MAX;
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    if (rank[q] < K) {
+      out_ids[r * K + rank[q]] = id[q];
+      out_scores[r * K + rank[q]] = sc[q];
+    }
+    if (rank[q] == K - 1) kth = sc[q];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) kth = fmaxf(kth, __shfl_xor_sync(0xffffffffu, kth, o));
+  if (lane == 0 && redo_rows != nullptr) {
+    // proof of completeness: nothing outside the list can have an exact score >= kth
+    const float thr = cand_thr[r];            // approx score of the weakest candidate (-FLT_MAX: list not full)
+    const float eps = eps_rel * u_norm[r] * __uint_as_float(*max_norm_bits);
+    if (thr > -FLT_MAX && !(kth > thr + eps)) redo_rows[atomicAdd(n_redo, 1)] = int32_t(r);
+  }
+}
+
+size_t eval_topk_tc_workspace(int64_t n_users, int32_t I, int32_t d, int32_t K, int precision) {
+  const int parts = precision == CGX_SCORE_BF16X3 ? 3 : 1;
+  const size_t Kp = size_t((parts * d + 63) / 64) * 64;
+  const int KC = K + 12 <= 32 ? 32 : 64;
+  return align_up(size_t(n_users) * Kp * 2) + align_up(size_t(I) * Kp * 2) + align_up(size_t(n_users) * KC * 4) +
+         3 * align_up(size_t(n_users) * 4) + 1024;
+}
+
+static bool tc_supported(int32_t d, int32_t K, int parts) {
+  const int Kp = (parts * d + 63) / 64 * 64;
+  const int KC = K + 12 <= 32 ? 32 : 64;
+  if (K + 12 > 64) return false;
+  const size_t smem = size_t(1 + TC_STAGES) * TC_M * Kp * 2 + size_t(KC + (KC == 32 ? 32 : 16)) * TC_M * 8 + 128;
+  return smem + 1024 <= 227 * 1024;
+}
+
+int eval_topk_tc(const int64_t* users, int64_t n_users, const float* f_u, const float* f_i, int32_t I, int32_t d,
+                 const int64_t* tr_indptr, const int32_t* tr_idx, int32_t K, int precision, int32_t* out_ids,
+                 float* out_scores, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  const int parts = precision == CGX_SCORE_BF16X3 ? 3 : 1;
+  CGX_REQUIRE(precision == CGX_SCORE_BF16X3 || precision == CGX_SCORE_BF16, CGX_ERR_ARG, "eval_topk: bad precision %d",
+              precision);
+  if (!tc_supported(d, K, parts)) {   // shapes the UMMA tile cannot hold: the exact kernel is always valid
+    return eval_fp32_rows(users, nullptr, nullptr, n_users, f_u, f_i, I, d, tr_indptr, tr_idx, K, out_ids, out_scores,
+                          stream);
+  }
+  CGX_REQUIRE(workspace_bytes >= eval_topk_tc_workspace(n_users, I, d, K, precision), CGX_ERR_WORKSPACE,
+              "eval_topk: workspace too small");
+  const int Kp = (parts * d + 63) / 64 * 64;
+  const int KC = K + 12 <= 32 ? 32 : 64;
+  Arena ws(workspace, workspace_bytes);
+  __nv_bfloat16* Au = ws.take<__nv_bfloat16>(size_t(n_users) * Kp);
+  __nv_bfloat16* Bi = ws.take<__nv_bfloat16>(size_t(I) * Kp);
+  int32_t* cand = ws.take<int32_t>(size_t(n_users) * KC);
+  float* thr = ws.take<float>(n_users);
+  float* unorm = ws.take<float>(n_users);
+  int32_t* redo = ws.take<int32_t>(n_users);
+  unsigned int* scal = ws.take<unsigned int>(4);   // [0] max item norm bits, [1] redo count
+  CGX_REQUIRE(ws.ok, CGX_ERR_WORKSPACE, "eval_topk: workspace too small");
+  CGX_CUDA(cudaMemsetAsync(scal, 0, 16, stream));
+  k_tc_convert<<<(unsigned)ceil_div(n_users, 8), 256, 0, stream>>>(f_u, users, n_users, d, parts, Kp, 0, Au, unorm, nullptr);
+  CGX_LAUNCH_CHECK();
+  k_tc_convert<<<(unsigned)ceil_div(I, 8), 256, 0, stream>>>(f_i, nullptr, I, d, parts, Kp, 1, Bi, nullptr, scal);
+  CGX_LAUNCH_CHECK();
+  const size_t smem = size_t(1 + TC_STAGES) * TC_M * Kp * 2 + size_t(KC + (KC == 32 ? 32 : 16)) * TC_M * 8 + 128 + 1024;
+  const unsigned grid = (unsigned)ceil_div(n_users, TC_M);
+  // bf16x3: dropped lo*lo term, bf16 rounding of lo, fp32 accumulation inside the MMA: 2^-13 |a||b| is a safe cap
+  const float eps_rel = 1.0f / 8192.0f;
+  int32_t* redo_rows = precision == CGX_SCORE_BF16X3 ? redo : nullptr;
+  if (KC == 32) {
+    CGX_CUDA(cudaFuncSetAttribute(k_eval_umma<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_eval_umma<32, 32><<<grid, TC_THREADS, smem, stream>>>(Au, Bi, users, n_users, I, Kp, tr_indptr, tr_idx, cand, thr);
+    CGX_LAUNCH_CHECK();
+    k_rescore<32><<<(unsigned)ceil_div(n_users, 8), 256, 0, stream>>>(
+        users, n_users, f_u, f_i, d, tr_indptr, tr_idx, cand, thr, unorm, scal, eps_rel, K, out_ids, out_scores,
+        redo_rows, reinterpret_cast<int32_t*>(scal + 1));
+    CGX_LAUNCH_CHECK();
+  } else {
+    CGX_CUDA(cudaFuncSetAttribute(k_eval_umma<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_eval_umma<64, 16><<<grid, TC_THREADS, smem, stream>>>(Au, Bi, users, n_users, I, Kp, tr_indptr, tr_idx, cand, thr);
+    CGX_LAUNCH_CHECK();
+    k_rescore<64><<<(unsigned)ceil_div(n_users, 8), 256, 0, stream>>>(
+        users, n_users, f_u, f_i, d, tr_indptr, tr_idx, cand, thr, unorm, scal, eps_rel, K, out_ids, out_scores,
+        redo_rows, reinterpret_cast<int32_t*>(scal + 1));
+    CGX_LAUNCH_CHECK();
+  }
+  if (redo_rows != nullptr) {   // rows whose completeness proof failed: exact kernel, count read on device
+    CGX_TRY(eval_fp32_rows(users, redo, reinterpret_cast<int32_t*>(scal + 1), n_users, f_u, f_i, I, d, tr_indptr,
+                           tr_idx, K, out_ids, out_scores, stream));
+    if (getenv("CGX_DEBUG_EVAL") != nullptr) {   // diagnostics only: synchronises
+      unsigned int h[2];
+      CGX_CUDA(cudaMemcpyAsync(h, scal, 8, cudaMemcpyDeviceToHost, stream));
+      CGX_CUDA(cudaStreamSynchronize(stream));
+      fprintf(stderr, "[cgx eval] rows=%lld redo=%u (%.3f %%)\n", (long long)n_users, h[1], 100.0 * h[1] / n_users);
+    }
+  }
+  return CGX_OK;
 }
 
 }  // namespace cgx

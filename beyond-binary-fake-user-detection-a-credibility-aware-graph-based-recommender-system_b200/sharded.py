@@ -61,7 +61,17 @@ def all_reduce_sum(t: torch.Tensor, group=None) -> torch.Tensor:
     return t
 
 
-class CudaBackend:
+class BackendBase:
+    """A shard backend provides item_rows(x_u, bwd) and user_rows(x_i, bwd); the fused form below has
+    a generic default so that test doubles only implement the two products."""
+
+    def user_rows_acc(self, x_i, bwd, acc_in, scale, need_y=True):
+        """y = user_rows(x_i); acc = scale * (acc_in + y).  Returns (y or None, acc)."""
+        y = self.user_rows(x_i, bwd)
+        return (y if need_y else None), (acc_in + y).mul_(scale)
+
+
+class CudaBackend(BackendBase):
     """The two products of one shard, on libcredgcn.so."""
 
     def __init__(self, graph: CredGraph):
@@ -90,6 +100,14 @@ class CudaBackend:
         """[U_local, d]: A x_i (bwd: C^T x_i) for this shard's users."""
         return self._spmm(self.graph.by_user, x_i, bwd)
 
+    def user_rows_acc(self, x_i, bwd, acc_in, scale, need_y=True):
+        """Same product with the running sum / gradient seed fused into the SpMM epilogue."""
+        csr = self.graph.by_user
+        y = torch.empty(csr.n_rows, x_i.shape[1], dtype=torch.float32, device=x_i.device) if need_y else None
+        acc = torch.empty(csr.n_rows, x_i.shape[1], dtype=torch.float32, device=x_i.device)
+        self._spmm(csr, x_i, bwd, y=y, acc_in=acc_in.contiguous(), acc_out=acc, scale=scale)
+        return y, acc
+
 
 class ShardedPropagation:
     """K-layer propagation and its adjoint over user shards (lightgcn_cu.py:420-448 /
@@ -103,15 +121,16 @@ class ShardedPropagation:
     def forward(self, e0_u: torch.Tensor, e0_i: torch.Tensor):
         """e0_u: this shard's user rows; e0_i: the replicated item table.  Returns (final_u shard, final_i)."""
         s = 1.0 / (self.K + 1)
-        acc_u, acc_i = e0_u.clone(), e0_i.clone()
+        acc_u, acc_i = e0_u, e0_i
         u, i = e0_u, e0_i
-        for _ in range(self.K):
+        for k in range(self.K):
+            last = k == self.K - 1
             i_new = all_reduce_sum(self.b.item_rows(u, False), self.group)
-            u_new = self.b.user_rows(i if self.order == "jacobi" else i_new, False)
-            acc_i += i_new
-            acc_u += u_new
+            u_new, acc_u = self.b.user_rows_acc(i if self.order == "jacobi" else i_new, False, acc_u,
+                                                s if last else 1.0, need_y=not last)
+            acc_i = acc_i + i_new if k == 0 else acc_i.add_(i_new)
             u, i = u_new, i_new
-        return acc_u.mul_(s), acc_i.mul_(s)
+        return acc_u, acc_i.mul_(s)
 
     def backward(self, g_u: torch.Tensor, g_i_total: torch.Tensor):
         """g_u: dL/d(final_u) rows of this shard; g_i_total: dL/d(final_i) already summed over ranks.
@@ -119,16 +138,17 @@ class ShardedPropagation:
         s = 1.0 / (self.K + 1)
         if self.order == "gs":
             bu = g_u
-            for _ in range(self.K):
+            for k in range(self.K):
                 bi = all_reduce_sum(self.b.item_rows(bu, True), self.group).add_(g_i_total)
-                bu = self.b.user_rows(bi, True).add_(g_u)
-            return bu.mul(s), g_i_total.mul(s)
+                _, bu = self.b.user_rows_acc(bi, True, g_u, s if k == self.K - 1 else 1.0, need_y=False)
+            return bu, g_i_total.mul(s)
         bu, bi = g_u, g_i_total
-        for _ in range(self.K):
-            nu = self.b.user_rows(bi, True).add_(g_u)
+        for k in range(self.K):
+            last = k == self.K - 1
+            _, nu = self.b.user_rows_acc(bi, True, g_u, s if last else 1.0, need_y=False)
             ni = all_reduce_sum(self.b.item_rows(bu, True), self.group).add_(g_i_total)
-            bu, bi = nu, ni
-        return bu.mul(s), bi.mul(s)
+            bu, bi = nu, (ni.mul_(s) if last else ni)
+        return bu, bi
 
 
 def build_local_graph(local_edges, num_local_users, num_items, cred_local, variant, device, group=None) -> CredGraph:
@@ -152,7 +172,10 @@ class ShardedTrainStep:
         self.reg = float(reg_weight)
         self.eu.grad, self.ei.grad = torch.zeros_like(self.eu), torch.zeros_like(self.ei)
         self.g_u = torch.empty_like(self.eu)
-        self.gi2 = torch.empty(2, *self.ei.shape, dtype=torch.float32, device=self.ei.device)   # [seed ; ego]
+        n = self.ei.numel()
+        self.red = torch.empty(2 * n + 4, dtype=torch.float32, device=self.ei.device)   # [seed ; ego ; loss]
+        self.gi2 = self.red[: 2 * n].view(2, *self.ei.shape)
+        self.loss = self.red[2 * n: 2 * n + 1]
         self.ego_u = torch.empty_like(self.eu)
         self._bufs = {}
 
@@ -163,23 +186,24 @@ class ShardedTrainStep:
         B = users_local.numel()
         B_total = int(batch_total) if batch_total is not None else B * _world(self.group)
         if B not in self._bufs:
-            self._bufs[B] = (torch.empty(3 * B, dtype=torch.int64, device=dev), bpr_buffers(g, B, dev))
+            b = bpr_buffers(g, B, dev)
+            self._bufs[B] = (torch.empty(3 * B, dtype=torch.int64, device=dev), (self.loss,) + b[1:])
         plan, bufs = self._bufs[B]
         pos, neg = self.sampler.sample(users_local)
         bpr_plan(g, users_local, pos, neg, plan)
         f_u, f_i = self.prop.forward(self.eu.data, self.ei.data)
         self.g_u.zero_()
-        self.gi2.zero_()
+        self.red.zero_()
         self.ego_u.zero_()
         loss, _, _, ego_rows, ego_coef = bpr_fused(g, f_u, f_i, self.eu.data, self.ei.data, users_local, pos, neg,
                                                    self.reg, 0.0, None, self.g_u, self.gi2[0], plan, bufs, B_total)
         apply_ego(g, ego_rows, ego_coef, self.eu.data, self.ei.data, self.ego_u, self.gi2[1])
-        all_reduce_sum(self.gi2, self.group)               # item seed and item L2 gradient in ONE collective
+        all_reduce_sum(self.red, self.group)      # item seed, item L2 gradient and the loss in ONE collective
         d_u, d_i = self.prop.backward(self.g_u, self.gi2[0])
         self.eu.grad.copy_(d_u.add_(self.ego_u))
         self.ei.grad.copy_(d_i.add_(self.gi2[1]))
         self.opt.step()
-        return all_reduce_sum(loss.clone(), self.group)
+        return self.loss.clone()
 
 
 # ------------------------------------------------------------------------------------------
@@ -251,7 +275,7 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
             "e2e": {"value": E / (e2e_ms / 1e3), "unit": "edges/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(host_batches[0].nbytes) * world, "d2h_bytes_per_step": 4 * world},
             "gpu_launches": int(launches), "loss": loss_host,
-            "collectives_per_step": 2 * K + 2,
+            "collectives_per_step": 2 * K + 1,
         }))
     dist.barrier()
     dist.destroy_process_group()

@@ -450,3 +450,56 @@ def test_errors_are_loud(cg):
     fi = torch.zeros(sg.num_items, 64, device=DEV)
     loss, *_ = cg["model"].bpr_fused(gr, f, fi, f, fi, [0], [sg.num_items + 3], [0], 1e-4)             # bad item id
     assert torch.isnan(loss).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core (tcgen05) score path
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(300, 420, 32), (943, 1682, 64), (700, 5000, 128), (130, 257, 16)])
+def test_tensor_core_topk_equals_fp32_path(cg, shape):
+    """BF16x3 tensor-core selection + exact re-scoring (+ proof / redo) must return exactly what the
+    fp32 kernel returns: same ids, same score bits."""
+    U, I, d = shape
+    sg = cg["synth"].make_graph("C1", num_users=U, num_items=I, num_edges=min(U * I // 8, 60_000))
+    rng = np.random.default_rng(U + d)
+    fu = torch.tensor((rng.standard_normal((U, d)) * 0.2).astype(np.float32), device=DEV)
+    fi = torch.tensor((rng.standard_normal((I, d)) * 0.2).astype(np.float32), device=DEV)
+    fi[::7] = fi[3]                                    # exact score ties across many items
+    tr = orc.edges_to_user_csr(sg.train_edges, U)
+    ev = cg["evaluate"]
+    users = torch.arange(0, U, 2)
+    csr = ev._device_csr(tr, DEV)
+    for K in (10, 20, 40):
+        ids0, sc0 = ev.topk_device(fu, fi, users, csr, K, "fp32")
+        ids1, sc1 = ev.topk_device(fu, fi, users, csr, K, "bf16x3")
+        assert torch.equal(ids0, ids1), (shape, K, int((ids0 != ids1).sum()))
+        assert torch.equal(sc0, sc1)
+
+
+def test_tensor_core_single_pass_bf16_is_close(cg):
+    """precision='bf16' (one bf16 pass, no proof): stated tolerance = at least 97 % of the exact top-20
+    ids recovered, scores of common ids exact (they are re-scored in fp32)."""
+    U, I, d = 1000, 6000, 64
+    rng = np.random.default_rng(9)
+    fu = torch.tensor((rng.standard_normal((U, d)) * 0.2).astype(np.float32), device=DEV)
+    fi = torch.tensor((rng.standard_normal((I, d)) * 0.2).astype(np.float32), device=DEV)
+    ev = cg["evaluate"]
+    csr = ev._device_csr((np.zeros(U + 1, np.int64), np.zeros(0, np.int64)), DEV)
+    ids0, _ = ev.topk_device(fu, fi, torch.arange(U), csr, 20, "fp32")
+    ids1, _ = ev.topk_device(fu, fi, torch.arange(U), csr, 20, "bf16")
+    a, b = ids0.cpu().numpy(), ids1.cpu().numpy()
+    overlap = np.mean([len(set(x) & set(y)) / 20 for x, y in zip(a, b)])
+    assert overlap > 0.97, overlap
+
+
+def test_evaluate_full_ranking_tensor_core_metrics(cg, golden):
+    g = golden
+    if "full_20" not in g:
+        pytest.skip("lightgcn_cu.py has no full-rank evaluator")
+    net = _model(cg, g, _build(cg, g))
+    res = cg["evaluate"].evaluate_full_ranking(
+        net, (g["csr_indptr"], g["csr_indices"]), (g["test_indptr"], g["test_indices"]), int(g["num_items"]), DEV,
+        precision="bf16x3")
+    for K in (10, 20):
+        np.testing.assert_allclose([res[K][k] for k in ("precision", "recall", "ndcg")], g[f"full_{K}"][:3],
+                                   rtol=TOL, atol=1e-6)

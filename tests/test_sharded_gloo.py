@@ -36,7 +36,10 @@ def test_partition_users_balances_nonzeros():
         assert p.shape[1] == 0 or (p[0].min() >= 0 and p[0].max() < b[r + 1] - b[r])
 
 
-class OracleShardBackend:
+from credgcn.sharded import BackendBase  # noqa: E402
+
+
+class OracleShardBackend(BackendBase):
     """Test double of sharded.CudaBackend: SciPy products of one user shard, weights from GLOBAL degrees."""
 
     def __init__(self, edges, lo, hi, num_items, cred, variant, deg_i_global):
