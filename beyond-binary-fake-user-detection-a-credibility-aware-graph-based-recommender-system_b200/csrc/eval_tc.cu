@@ -16,12 +16,13 @@
 // is therefore identical to CGX_SCORE_FP32.  precision = BF16 is the single-pass variant (K' = d,
 // error ~2^-8 relative, no proof, no redo) for callers that accept approximate ranking.
 //
-// Kernel anatomy (one CTA per 128 users, 288 threads):
+// Kernel anatomy (one CTA per 128 users, 9 or 13 warps):
 //   warp 0      TMEM allocation, then one elected lane issues tcgen05.mma (M=128, N=128, K=16 per
 //               instruction, K'/16 instructions per item tile), tcgen05.commit -> mbarriers
-//   warps 1-4   epilogue: tcgen05.ld 32x32b.x16 -> registers, predicated append of scores >= the row
+//   warps 1-4 (and 5-8 when two epilogue groups are used: group g owns accumulator stage g)
+//               epilogue: tcgen05.ld 32x32b.x16 -> registers, predicated append of scores >= the row
 //               threshold, warp-uniform drain into the row's K' kept candidates (one thread per user)
-//   warps 5-8   producers: cp.async (16 B, L2-only) the next 128-item tile of the bf16 item table into
+//   last 4      producers: cp.async (16 B, L2-only) the next 128-item tile of the bf16 item table into
 //               shared memory in the canonical K-major SWIZZLE_128B UMMA layout (64-column k-blocks,
 //               128-byte rows, 16-byte chunks XOR-ed with row%8 -- what TMA would write), so that a
 //               row's 8 chunks are one coalesced 128-byte global read AND one conflict-free shared
@@ -42,7 +43,6 @@ int eval_fp32_rows(const int64_t* users, const int32_t* row_list, const int32_t*
 
 constexpr int TC_M = 128;          // users per CTA
 constexpr int TC_N = 128;          // items per tile
-constexpr int TC_THREADS = 288;    // 9 warps
 constexpr int TC_STAGES = 2;
 constexpr float TC_MASKED = -1e9f;
 
@@ -155,26 +155,31 @@ __global__ void k_tc_convert(const float* __restrict__ src, const int64_t* __res
 }
 
 // ---- the UMMA kernel ---------------------------------------------------------------------------
-template <int KC, int BC>   // kept candidates per user, arrival-buffer slots per user
-__global__ void __launch_bounds__(TC_THREADS, 1) k_eval_umma(const __nv_bfloat16* __restrict__ Au,   // [n_users, Kp]
+// KC kept candidates and BC arrival-buffer slots per (user, epilogue group); NG epilogue groups of 4 warps.
+// With NG = 2 group g drains accumulator stage g (tiles of parity g) into its own list, which doubles the
+// warps that scan scores -- the epilogue, not the MMA, bounds this kernel (d is only 64..128).
+template <int KC, int BC, int NG>
+__global__ void __launch_bounds__(32 * (5 + 4 * NG), 1) k_eval_umma(const __nv_bfloat16* __restrict__ Au,   // [n_users, Kp]
                                                              const __nv_bfloat16* __restrict__ Bi,   // [I, Kp]
                                                              const int64_t* __restrict__ users, int64_t n_users,
                                                              int32_t I, int32_t Kp,
                                                              const int64_t* __restrict__ tr_indptr,
                                                              const int32_t* __restrict__ tr_idx,
-                                                             int32_t* __restrict__ cand_ids,       // [n_users, KC]
-                                                             float* __restrict__ cand_thr) {        // [n_users]
+                                                             int32_t* __restrict__ cand_ids,       // [n_users, cand_stride]
+                                                             int32_t cand_stride,
+                                                             float* __restrict__ cand_thr,          // [n_users, 2]
+                                                             int dbg) {
+  constexpr int TC_THREADS = 32 * (5 + 4 * NG);
   extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
   // SWIZZLE_128B atoms must start on 1024-byte boundaries of the shared window
   unsigned char* tc_smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
   const uint32_t tile_bytes = uint32_t(TC_M) * Kp * 2;           // one operand tile (128 rows x Kp bf16)
   unsigned char* smem_a = tc_smem;
   unsigned char* smem_b = tc_smem + tile_bytes;                   // TC_STAGES tiles
-  float* list_s = reinterpret_cast<float*>(smem_b + TC_STAGES * tile_bytes);   // [KC][128]  unsorted candidates
-  int32_t* list_i = reinterpret_cast<int32_t*>(list_s + KC * TC_M);           // [KC][128]
-  float* buf_s = reinterpret_cast<float*>(list_i + KC * TC_M);                // [BC][128]  arrivals not yet merged
-  int32_t* buf_i = reinterpret_cast<int32_t*>(buf_s + BC * TC_M);             // [BC][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(buf_i + BC * TC_M);
+  float* list_s_all = reinterpret_cast<float*>(smem_b + TC_STAGES * tile_bytes);   // [NG][KC][128] unsorted candidates
+  int32_t* list_i_all = reinterpret_cast<int32_t*>(list_s_all + NG * KC * TC_M);   // [NG][KC][128]
+  uint2* buf_all = reinterpret_cast<uint2*>(list_i_all + NG * KC * TC_M);          // [NG][BC][128] arrivals (score bits, item)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(buf_all + NG * BC * TC_M);
   uint64_t* full_bar = bars;                 // [TC_STAGES]  producers -> MMA
   uint64_t* empty_bar = bars + TC_STAGES;    // [TC_STAGES]  MMA (commit) -> producers
   uint64_t* tfull_bar = bars + 2 * TC_STAGES;   // [2]       MMA (commit) -> epilogue
@@ -222,7 +227,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_eval_umma(const __nv_bfloat16
       tc_fence_after();
       if (lane == 0) {
         const uint32_t b_addr = smem_u32(smem_b + s * tile_bytes);
-        for (int kb = 0; kb < n_kb; ++kb) {
+        for (int kb = 0; kb < ((dbg & 2) ? 0 : n_kb); ++kb) {
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
             umma_bf16(tmem_base + a * TC_N, umma_desc_sw128(a_addr + kb * (TC_M * 128) + k4 * 32),
@@ -234,20 +239,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_eval_umma(const __nv_bfloat16
       }
       __syncwarp();
     }
-  } else if (warp >= 5) {
+  } else if (warp >= 1 + 4 * NG) {
     // ===== producers: stage item tiles with cp.async, one group per tile, two tiles in flight =====
-    const int pt = threadIdx.x - 5 * 32;   // 0..127
+    const int pt = threadIdx.x - (1 + 4 * NG) * 32;   // 0..127
     for (int j = 0; j <= n_tiles; ++j) {
       if (j < n_tiles) {
         const int s = j % TC_STAGES;
         mbar_wait(empty_bar + s, ((j / TC_STAGES) & 1) ^ 1);
         const uint32_t dstb = smem_u32(smem_b + s * tile_bytes);
         const int64_t i0 = int64_t(j) * TC_N;
-        for (int q = pt; q < chunks; q += 128) {
-          const int c = q & 7, r = (q >> 3) & (TC_N - 1), kb = q >> 10;
-          const bool ok = i0 + r < I;
-          const __nv_bfloat16* src = Bi + (ok ? (i0 + r) : 0) * Kp + kb * 64 + c * 8;
-          cp_async16(dstb + kb * (TC_N * 128) + r * 128 + ((c ^ (r & 7)) << 4), src, ok ? 16u : 0u);   // 0 -> zero fill
+        // thread pt owns chunk column c = pt % 8 of rows r0, r0+16, ... (128 threads cover 16 rows x 8 chunks)
+        const int c = pt & 7, r0 = pt >> 3;
+        const __nv_bfloat16* src0 = Bi + (i0 + r0) * Kp + c * 8;
+        const uint32_t dst0 = dstb + r0 * 128 + ((c ^ (r0 & 7)) << 4);     // (r0 + 16 t) % 8 == r0 % 8
+        const int rows_left = int((I - i0 - r0 + 15) / 16);                // rows r0 + 16 t that exist
+        for (int kb = 0; kb < ((dbg & 4) ? 0 : n_kb); ++kb) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const bool ok = t < rows_left;
+            cp_async16(dst0 + kb * (TC_N * 128) + t * 2048, ok ? src0 + int64_t(t) * 16 * Kp + kb * 64 : Bi,
+                       ok ? 16u : 0u);   // 0 -> zero fill
+          }
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
@@ -267,6 +279,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_eval_umma(const __nv_bfloat16
     // keeps most lanes busy in a drain (a lane sees ~0.8 arrivals per 128-item tile in steady state).
     // The kept list stays unsorted; k_rescore ranks it.  TMEM loads are software pipelined.
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int grp = (warp - 1) >> 2;           // epilogue group: owns the tiles j with j % NG == grp
+    float* list_s = list_s_all + grp * KC * TC_M;
+    int32_t* list_i = list_i_all + grp * KC * TC_M;
+    uint2* buf = buf_all + grp * BC * TC_M;
     const int row = quad * 32 + lane;
     const int64_t ug = u0 + row;
     const bool live = ug < n_users;
@@ -278,15 +294,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_eval_umma(const __nv_bfloat16
     }
     int32_t next_masked = tr_cur < tr_hi ? __ldg(tr_idx + tr_cur) : INT32_MAX;
     for (int p = 0; p < KC; ++p) { list_s[p * TC_M + row] = -FLT_MAX; list_i[p * TC_M + row] = INT32_MAX; }
-    float thr = -FLT_MAX;      // score of the weakest kept candidate
+    float thr = live ? -FLT_MAX : FLT_MAX;      // score of the weakest kept candidate (dead rows accept nothing)
     int32_t thr_id = INT32_MAX;
     int weakest = 0;           // its slot
-    int cnt = 0;               // arrivals waiting in the buffer
+    uint2* const wr0 = buf + row;   // arrival slot e of this row = wr0[e * 128]
+    uint2* wr = wr0;                // next free slot: the append is one compare, one 8-byte store, one pointer bump
 
     auto drain = [&]() {
+      const int cnt = int(wr - wr0) / TC_M;
       for (int e = 0; e < cnt; ++e) {
-        float sc = buf_s[e * TC_M + row];
-        const int32_t item = buf_i[e * TC_M + row];
+        const uint2 ent = wr0[e * TC_M];
+        float sc = __uint_as_float(ent.x);
+        const int32_t item = int32_t(ent.y);
         while (next_masked < item) {
           ++tr_cur;
           next_masked = tr_cur < tr_hi ? __ldg(tr_idx + tr_cur) : INT32_MAX;
@@ -305,14 +324,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_eval_umma(const __nv_bfloat16
           }
         }
       }
-      cnt = 0;
+      wr = wr0;
     };
 
-    for (int j = 0; j < n_tiles; ++j) {
+    for (int j = grp; j < n_tiles; j += NG) {
       const int a = j & 1;
       mbar_wait(tfull_bar + a, (j >> 1) & 1);
       tc_fence_after();
       const int32_t i0 = j * TC_N;
+      const int valid = I - i0 < TC_N ? I - i0 : TC_N;   // columns of this tile that are real items
       const uint32_t tbase = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(a * TC_N);
       float v[2][16];
       tmem_ld16(tbase, v[0]);
@@ -320,16 +340,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_eval_umma(const __nv_bfloat16
 #pragma unroll
       for (int ch = 0; ch < TC_N / 16; ++ch) {
         if (ch + 1 < TC_N / 16) tmem_ld16(tbase + (ch + 1) * 16, v[(ch + 1) & 1]);   // in flight during the scan below
+        if (dbg & 1) {
+        } else if (ch * 16 + 16 <= valid) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const int32_t item = i0 + ch * 16 + q;
-          if (live && v[ch & 1][q] >= thr && item < I) {
-            buf_s[cnt * TC_M + row] = v[ch & 1][q];
-            buf_i[cnt * TC_M + row] = item;
-            ++cnt;
+          for (int q = 0; q < 16; ++q) {
+            if (v[ch & 1][q] >= thr) {
+              *wr = make_uint2(__float_as_uint(v[ch & 1][q]), uint32_t(i0 + ch * 16 + q));
+              wr += TC_M;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            if (v[ch & 1][q] >= thr && ch * 16 + q < valid) {
+              *wr = make_uint2(__float_as_uint(v[ch & 1][q]), uint32_t(i0 + ch * 16 + q));
+              wr += TC_M;
+            }
           }
         }
-        if (__any_sync(0xffffffffu, cnt > BC - 16)) drain();
+        if (__any_sync(0xffffffffu, wr - wr0 > (BC - 16) * TC_M)) {
+          if (dbg & 8) wr = wr0; else drain();
+        }
         if (ch + 1 < TC_N / 16) tmem_wait_ld();
       }
       tc_fence_before();
@@ -337,8 +368,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_eval_umma(const __nv_bfloat16
     }
     drain();
     if (live) {
-      for (int p = 0; p < KC; ++p) cand_ids[ug * KC + p] = list_i[p * TC_M + row];
-      cand_thr[ug] = thr;
+      for (int p = 0; p < KC; ++p) cand_ids[ug * cand_stride + grp * KC + p] = list_i[p * TC_M + row];
+      if (grp == 0) for (int p = NG * KC; p < cand_stride; ++p) cand_ids[ug * cand_stride + p] = INT32_MAX;
+      cand_thr[ug * 2 + grp] = thr;
+      if (NG == 1) cand_thr[ug * 2 + 1] = thr;
     }
   }
   tc_fence_before();
@@ -404,26 +437,58 @@ __global__ void __launch_bounds__(256) k_rescore(const int64_t* __restrict__ use
   for (int o = 16; o > 0; o >>= 1) kth = fmaxf(kth, __shfl_xor_sync(0xffffffffu, kth, o));
   if (lane == 0 && redo_rows != nullptr) {
     // proof of completeness: nothing outside the list can have an exact score >= kth
-    const float thr = cand_thr[r];            // approx score of the weakest candidate (-FLT_MAX: list not full)
+    // approx score of the weakest kept candidate of either group: nothing outside the lists scores above it
+    const float thr = fmaxf(cand_thr[2 * r], cand_thr[2 * r + 1]);
     const float eps = eps_rel * u_norm[r] * __uint_as_float(*max_norm_bits);
     if (thr > -FLT_MAX && !(kth > thr + eps)) redo_rows[atomicAdd(n_redo, 1)] = int32_t(r);
   }
 }
 
+struct TcConfig {
+  int KC, BC, NG, stride;   // stride = candidates per user handed to k_rescore (32 or 64)
+};
+static TcConfig tc_config(int32_t K) {
+  // Two epilogue groups (24, 16, 2, 64) were measured SLOWER on C2 (3.69 ms vs 3.19 ms): each group keeps
+  // its own, weaker threshold, so more scores reach the merge code.  Set CGX_EVAL_GROUPS=2 to try it.
+  static const bool two = getenv("CGX_EVAL_GROUPS") != nullptr && atoi(getenv("CGX_EVAL_GROUPS")) == 2;
+  if (two && K + 4 <= 24) return {24, 16, 2, 64};
+  if (K + 12 <= 32) return {32, 32, 1, 32};
+  return {64, 16, 1, 64};
+}
+static size_t tc_smem(const TcConfig& c, int Kp) {
+  return size_t(1 + TC_STAGES) * TC_M * Kp * 2 + size_t(c.NG) * (c.KC + c.BC) * TC_M * 8 + 128 + 1024;
+}
+
 size_t eval_topk_tc_workspace(int64_t n_users, int32_t I, int32_t d, int32_t K, int precision) {
   const int parts = precision == CGX_SCORE_BF16X3 ? 3 : 1;
   const size_t Kp = size_t((parts * d + 63) / 64) * 64;
-  const int KC = K + 12 <= 32 ? 32 : 64;
-  return align_up(size_t(n_users) * Kp * 2) + align_up(size_t(I) * Kp * 2) + align_up(size_t(n_users) * KC * 4) +
-         3 * align_up(size_t(n_users) * 4) + 1024;
+  return align_up(size_t(n_users) * Kp * 2) + align_up(size_t(I) * Kp * 2) + align_up(size_t(n_users) * 64 * 4) +
+         4 * align_up(size_t(n_users) * 4) + 1024;
 }
 
 static bool tc_supported(int32_t d, int32_t K, int parts) {
   const int Kp = (parts * d + 63) / 64 * 64;
-  const int KC = K + 12 <= 32 ? 32 : 64;
   if (K + 12 > 64) return false;
-  const size_t smem = size_t(1 + TC_STAGES) * TC_M * Kp * 2 + size_t(KC + (KC == 32 ? 32 : 16)) * TC_M * 8 + 128;
-  return smem + 1024 <= 227 * 1024;
+  return tc_smem(tc_config(K), Kp) <= 227 * 1024;
+}
+
+template <int KC, int BC, int NG, int STRIDE>
+static int tc_launch(const __nv_bfloat16* Au, const __nv_bfloat16* Bi, const int64_t* users, int64_t n_users,
+                     const float* f_u, const float* f_i, int32_t I, int32_t d, int Kp, const int64_t* tr_indptr,
+                     const int32_t* tr_idx, int32_t K, int32_t* cand, float* thr, const float* unorm,
+                     const unsigned int* scal, float eps_rel, int32_t* out_ids, float* out_scores, int32_t* redo_rows,
+                     int32_t* n_redo, cudaStream_t stream) {
+  const size_t smem = tc_smem(TcConfig{KC, BC, NG, STRIDE}, Kp);
+  CGX_CUDA(cudaFuncSetAttribute(k_eval_umma<KC, BC, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_eval_umma<KC, BC, NG><<<(unsigned)ceil_div(n_users, TC_M), 32 * (5 + 4 * NG), smem, stream>>>(
+      Au, Bi, users, n_users, I, Kp, tr_indptr, tr_idx, cand, STRIDE, thr,
+      getenv("CGX_EVAL_DBG") ? atoi(getenv("CGX_EVAL_DBG")) : 0);
+  CGX_LAUNCH_CHECK();
+  k_rescore<STRIDE><<<(unsigned)ceil_div(n_users, 8), 256, 0, stream>>>(users, n_users, f_u, f_i, d, tr_indptr, tr_idx,
+                                                                       cand, thr, unorm, scal, eps_rel, K, out_ids,
+                                                                       out_scores, redo_rows, n_redo);
+  CGX_LAUNCH_CHECK();
+  return CGX_OK;
 }
 
 int eval_topk_tc(const int64_t* users, int64_t n_users, const float* f_u, const float* f_i, int32_t I, int32_t d,
@@ -439,12 +504,12 @@ int eval_topk_tc(const int64_t* users, int64_t n_users, const float* f_u, const 
   CGX_REQUIRE(workspace_bytes >= eval_topk_tc_workspace(n_users, I, d, K, precision), CGX_ERR_WORKSPACE,
               "eval_topk: workspace too small");
   const int Kp = (parts * d + 63) / 64 * 64;
-  const int KC = K + 12 <= 32 ? 32 : 64;
+  const TcConfig cfg = tc_config(K);
   Arena ws(workspace, workspace_bytes);
   __nv_bfloat16* Au = ws.take<__nv_bfloat16>(size_t(n_users) * Kp);
   __nv_bfloat16* Bi = ws.take<__nv_bfloat16>(size_t(I) * Kp);
-  int32_t* cand = ws.take<int32_t>(size_t(n_users) * KC);
-  float* thr = ws.take<float>(n_users);
+  int32_t* cand = ws.take<int32_t>(size_t(n_users) * 64);
+  float* thr = ws.take<float>(size_t(n_users) * 2);
   float* unorm = ws.take<float>(n_users);
   int32_t* redo = ws.take<int32_t>(n_users);
   unsigned int* scal = ws.take<unsigned int>(4);   // [0] max item norm bits, [1] redo count
@@ -454,31 +519,23 @@ int eval_topk_tc(const int64_t* users, int64_t n_users, const float* f_u, const 
   CGX_LAUNCH_CHECK();
   k_tc_convert<<<(unsigned)ceil_div(I, 8), 256, 0, stream>>>(f_i, nullptr, I, d, parts, Kp, 1, Bi, nullptr, scal);
   CGX_LAUNCH_CHECK();
-  const size_t smem = size_t(1 + TC_STAGES) * TC_M * Kp * 2 + size_t(KC + (KC == 32 ? 32 : 16)) * TC_M * 8 + 128 + 1024;
-  const unsigned grid = (unsigned)ceil_div(n_users, TC_M);
   // bf16x3: dropped lo*lo term, bf16 rounding of lo, fp32 accumulation inside the MMA: 2^-13 |a||b| is a safe cap
   const float eps_rel = 1.0f / 8192.0f;
   int32_t* redo_rows = precision == CGX_SCORE_BF16X3 ? redo : nullptr;
-  if (KC == 32) {
-    CGX_CUDA(cudaFuncSetAttribute(k_eval_umma<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_eval_umma<32, 32><<<grid, TC_THREADS, smem, stream>>>(Au, Bi, users, n_users, I, Kp, tr_indptr, tr_idx, cand, thr);
-    CGX_LAUNCH_CHECK();
-    k_rescore<32><<<(unsigned)ceil_div(n_users, 8), 256, 0, stream>>>(
-        users, n_users, f_u, f_i, d, tr_indptr, tr_idx, cand, thr, unorm, scal, eps_rel, K, out_ids, out_scores,
-        redo_rows, reinterpret_cast<int32_t*>(scal + 1));
-    CGX_LAUNCH_CHECK();
+  int32_t* n_redo = reinterpret_cast<int32_t*>(scal + 1);
+#define CGX_TC_ARGS Au, Bi, users, n_users, f_u, f_i, I, d, Kp, tr_indptr, tr_idx, K, cand, thr, unorm, scal, eps_rel, \
+                    out_ids, out_scores, redo_rows, n_redo, stream
+  if (cfg.NG == 2) {
+    CGX_TRY((tc_launch<24, 16, 2, 64>(CGX_TC_ARGS)));
+  } else if (cfg.KC == 32) {
+    CGX_TRY((tc_launch<32, 32, 1, 32>(CGX_TC_ARGS)));
   } else {
-    CGX_CUDA(cudaFuncSetAttribute(k_eval_umma<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_eval_umma<64, 16><<<grid, TC_THREADS, smem, stream>>>(Au, Bi, users, n_users, I, Kp, tr_indptr, tr_idx, cand, thr);
-    CGX_LAUNCH_CHECK();
-    k_rescore<64><<<(unsigned)ceil_div(n_users, 8), 256, 0, stream>>>(
-        users, n_users, f_u, f_i, d, tr_indptr, tr_idx, cand, thr, unorm, scal, eps_rel, K, out_ids, out_scores,
-        redo_rows, reinterpret_cast<int32_t*>(scal + 1));
-    CGX_LAUNCH_CHECK();
+    CGX_TRY((tc_launch<64, 16, 1, 64>(CGX_TC_ARGS)));
   }
+#undef CGX_TC_ARGS
   if (redo_rows != nullptr) {   // rows whose completeness proof failed: exact kernel, count read on device
-    CGX_TRY(eval_fp32_rows(users, redo, reinterpret_cast<int32_t*>(scal + 1), n_users, f_u, f_i, I, d, tr_indptr,
-                           tr_idx, K, out_ids, out_scores, stream));
+    CGX_TRY(eval_fp32_rows(users, redo, n_redo, n_users, f_u, f_i, I, d, tr_indptr, tr_idx, K, out_ids, out_scores,
+                           stream));
     if (getenv("CGX_DEBUG_EVAL") != nullptr) {   // diagnostics only: synchronises
       unsigned int h[2];
       CGX_CUDA(cudaMemcpyAsync(h, scal, 8, cudaMemcpyDeviceToHost, stream));
