@@ -66,7 +66,10 @@ _SIGNATURES = {
     "cgx_sampler_build_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "cgx_sampler_build": (C.c_int, [_P, C.c_int32, C.c_double, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "cgx_sample_triples": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int32, _P, _P, _P, _P, _P, C.c_float,
-                                     C.c_int32, C.c_uint64, C.c_uint64, _P, _P, _P]),
+                                     C.c_int32, C.c_uint64, C.c_uint64, _P, _P, _P, _P]),
+    "cgx_tick": (C.c_int, [_P, _P]),
+    "cgx_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, _P, _P, _P, C.c_int64, C.c_float, C.c_float,
+                                C.c_float, C.c_float, _P, C.c_int64, _P]),
     "cgx_eval_topk_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int]),
     "cgx_eval_topk": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.c_int, _P,
                                 _P, _P, C.c_size_t, _P]),

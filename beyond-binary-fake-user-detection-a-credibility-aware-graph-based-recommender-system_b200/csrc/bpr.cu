@@ -357,7 +357,11 @@ extern "C" int cgx_bpr_plan(const int64_t* users, const int64_t* pos, const int6
   const int entry_bits = bits_for(n), row_bits = bits_for(int64_t(U) + I);
   if (n <= PS_MAX) {
     const size_t smem = plan_small_smem();
-    CGX_CUDA(cudaFuncSetAttribute(k_plan_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool attr_set = false;   // once per process: keeps the call out of CUDA-graph captures after warm-up
+    if (!attr_set) {
+      CGX_CUDA(cudaFuncSetAttribute(k_plan_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
     k_plan_small<<<1, PS_THREADS, smem, stream>>>(users, pos, neg, batch, U, I, entry_bits, row_bits, plan);
     CGX_LAUNCH_CHECK();
     return CGX_OK;

@@ -60,9 +60,11 @@ __global__ void __launch_bounds__(SM_THREADS) k_sample(const int64_t* __restrict
                                                        const int32_t* __restrict__ idx, int32_t I,
                                                        SamplerTables tb, float mix_pop, int32_t max_tries,
                                                        uint64_t seed, uint64_t offset,
+                                                       const unsigned long long* __restrict__ offset_dev,
                                                        int64_t* __restrict__ pos_out, int64_t* __restrict__ neg_out) {
   const int64_t t = int64_t(blockIdx.x) * SM_THREADS + threadIdx.x;
   if (t >= B) return;
+  if (offset_dev != nullptr) offset += *offset_dev;   // device-side step counter (CUDA-graph replay)
   const Philox rng{uint32_t(seed), uint32_t(seed >> 32)};
   const uint32_t o_lo = uint32_t(offset), o_hi = uint32_t(offset >> 32);
   // counter = (slot, draw index, offset.lo, offset.hi); draw 0 is the positive
@@ -203,7 +205,8 @@ extern "C" int cgx_sample_triples(const int64_t* users, int64_t batch, const int
                                   const int32_t* samp_idx, int32_t num_items, const int32_t* items_by_deg,
                                   const int32_t* class_start, const float* class_prob, const int32_t* class_alias,
                                   const int32_t* n_classes, float mix_pop, int32_t max_tries, uint64_t seed,
-                                  uint64_t offset, int64_t* pos_out, int64_t* neg_out, void* stream_) {
+                                  uint64_t offset, const uint64_t* offset_dev, int64_t* pos_out, int64_t* neg_out,
+                                  void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CGX_REQUIRE(users && samp_indptr && samp_idx && pos_out && neg_out && batch > 0 && num_items > 0, CGX_ERR_ARG,
               "sample_triples: bad argument");
@@ -212,7 +215,8 @@ extern "C" int cgx_sample_triples(const int64_t* users, int64_t batch, const int
                 "sample_triples: popularity tables missing");
   SamplerTables tb{items_by_deg, class_start, class_prob, class_alias, n_classes};
   k_sample<<<(unsigned)ceil_div(batch, SM_THREADS), SM_THREADS, 0, stream>>>(
-      users, batch, samp_indptr, samp_idx, num_items, tb, mix_pop, max_tries, seed, offset, pos_out, neg_out);
+      users, batch, samp_indptr, samp_idx, num_items, tb, mix_pop, max_tries, seed, offset,
+      reinterpret_cast<const unsigned long long*>(offset_dev), pos_out, neg_out);
   CGX_LAUNCH_CHECK();
   return CGX_OK;
 }

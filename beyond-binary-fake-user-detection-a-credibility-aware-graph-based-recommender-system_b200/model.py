@@ -249,27 +249,68 @@ class LightGCN(_Base):
 
 
 # ------------------------------------------------------------------------------------------
-# fused training step (sampler -> forward -> loss -> backward -> Adam), no autograd graph
+# optimiser + fused training step (sampler -> forward -> loss -> backward -> Adam), no autograd graph
 # ------------------------------------------------------------------------------------------
+class FusedAdam:
+    """torch.optim.Adam(params, lr) semantics (defaults: betas (0.9, 0.999), eps 1e-8; lightgcn_cu.py:587)
+    for the two embedding tables, one kernel launch per step.  The step count lives on the device so
+    that a captured CUDA graph keeps advancing it."""
+
+    def __init__(self, user_weight: torch.Tensor, item_weight: torch.Tensor, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        self.params = (user_weight, item_weight)
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.m = [torch.zeros_like(p) for p in self.params]
+        self.v = [torch.zeros_like(p) for p in self.params]
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=user_weight.device)   # steps taken so far
+
+    def zero_grad(self, set_to_none: bool = False):
+        for p in self.params:
+            if p.grad is not None:
+                p.grad.zero_()
+
+    @torch.no_grad()
+    def step(self):
+        pu, pi = self.params
+        dev = pu.device
+        with torch.cuda.device(dev):
+            st = stream_ptr(dev)
+            check(lib().cgx_tick(ptr(self.step_dev), st))
+            check(lib().cgx_adam_step(ptr(pu.data), ptr(_f32c(pu.grad)), ptr(self.m[0]), ptr(self.v[0]), pu.numel(),
+                                      ptr(pi.data), ptr(_f32c(pi.grad)), ptr(self.m[1]), ptr(self.v[1]), pi.numel(),
+                                      self.lr, self.betas[0], self.betas[1], self.eps, ptr(self.step_dev), 0, st))
+
+    def state_dict(self):
+        return {"step": int(self.step_dev.item()), "exp_avg": self.m, "exp_avg_sq": self.v, "lr": self.lr,
+                "betas": self.betas, "eps": self.eps}
+
+
 class TrainStep:
-    """One full training step on pre-allocated buffers.  Equivalent to lightgcn_cu.py:632-652 /
-    lighgcn_cu_pop.py:858-863: final embeddings, BPR (+fair) + L2 loss, backward, dense Adam.
+    """One full training step on pre-allocated buffers.  Equivalent to lightgcn_cu.py:608-652 /
+    lighgcn_cu_pop.py:826-863: one (user, pos, neg) triple per batch user, final embeddings, BPR (+fair) + L2
+    loss, backward, dense Adam.
 
-    Adam stays torch (`torch.optim.Adam(lr)`, dense over both tables)."""
+    `step(users)` samples on device and updates the parameters; `forward_backward(users, pos, neg)` runs
+    on an injected triple list and leaves the gradients in `.grad` (parity tests).  `capture(batch)` records
+    the whole step as ONE CUDA graph (sampler offsets and the Adam step count are device-side counters), which
+    removes the ~25 per-step launch calls from the host's critical path."""
 
-    def __init__(self, model: _Base, lr=1e-3, reg_weight=1e-4, fair_weight=0.0, pop=None, optimizer=None):
+    def __init__(self, model: _Base, lr=1e-3, reg_weight=1e-4, fair_weight=0.0, pop=None, optimizer=None,
+                 sampler=None):
         self.model, self.graph = model, model.graph
         self.reg, self.fair = float(reg_weight), float(fair_weight)
         dev = model.user_emb.weight.device
         self.pop = None if pop is None else torch.as_tensor(pop, dtype=torch.float32, device=dev).contiguous()
-        self.opt = optimizer or torch.optim.Adam(model.parameters(), lr=lr, fused=True)
         eu, ei = model.user_emb.weight, model.item_emb.weight
         self.f_u, self.f_i = torch.empty_like(eu), torch.empty_like(ei)
         self.g_u, self.g_i = torch.empty_like(eu), torch.empty_like(ei)
         eu.grad, ei.grad = torch.empty_like(eu), torch.empty_like(ei)
+        self.opt = optimizer or FusedAdam(eu, ei, lr=lr)
+        self.sampler = sampler
         self.phase_events = None      # set to a list to collect (start, fwd_end, loss_end, bwd_end) CUDA events
         self.side = torch.cuda.Stream(device=dev)     # plan + gradient-buffer clearing overlap the forward
+        self.tick = torch.zeros(1, dtype=torch.int64, device=dev)   # sampler offset counter (device side)
         self._bufs = {}
+        self._graph = None
 
     def _mark(self, marks):
         if self.phase_events is not None:
@@ -317,6 +358,60 @@ class TrainStep:
         return loss
 
     def __call__(self, users, pos, neg):
+        """Injected triples: forward, loss, backward, optimiser step."""
         loss = self.forward_backward(users, pos, neg)
         self.opt.step()
         return loss
+
+    # ---- sampling step, optionally as one CUDA graph --------------------------------------------
+    @torch.no_grad()
+    def _sampled_step(self, users):
+        dev = self.graph.device
+        with torch.cuda.device(dev):
+            check(lib().cgx_tick(ptr(self.tick), stream_ptr(dev)))
+        pos, neg = self.sampler.sample(users, offset=0, offset_dev=self.tick)
+        return self.__call__(users, pos, neg)
+
+    def capture(self, batch: int):
+        """Record sample + forward + loss + backward + Adam for `batch` users as one CUDA graph."""
+        if self.sampler is None:
+            raise _lib.CgxError("TrainStep.capture needs a TripleSampler (pass sampler=...)")
+        dev = self.graph.device
+        self._g_users = torch.zeros(batch, dtype=torch.int64, device=dev)
+        keep = self.phase_events
+        self.phase_events = None
+        warm = torch.cuda.Stream(device=dev)
+        warm.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(warm):                       # warm-up outside capture (allocations, attributes)
+            state = [p.detach().clone() for p in (self.model.user_emb.weight, self.model.item_emb.weight)]
+            opt_state = ([t.clone() for t in self.opt.m], [t.clone() for t in self.opt.v], self.opt.step_dev.clone(),
+                         self.tick.clone()) if isinstance(self.opt, FusedAdam) else None
+            for _ in range(2):
+                self._sampled_step(self._g_users)
+            # the warm-up steps must not count: restore parameters, optimiser state and counters
+            self.model.user_emb.weight.data.copy_(state[0])
+            self.model.item_emb.weight.data.copy_(state[1])
+            if opt_state is not None:
+                for dst, src in zip(self.opt.m, opt_state[0]):
+                    dst.copy_(src)
+                for dst, src in zip(self.opt.v, opt_state[1]):
+                    dst.copy_(src)
+                self.opt.step_dev.copy_(opt_state[2])
+                self.tick.copy_(opt_state[3])
+        torch.cuda.current_stream(dev).wait_stream(warm)
+        torch.cuda.synchronize(dev)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._g_loss = self._sampled_step(self._g_users)
+        self.phase_events = keep
+        return self
+
+    def step(self, users):
+        """users: int64 batch of users with >= 1 train item (CUDA or pinned host tensor)."""
+        if self.sampler is None:
+            raise _lib.CgxError("TrainStep.step needs a TripleSampler (pass sampler=...)")
+        if self._graph is not None and users.numel() == self._g_users.numel() and self.phase_events is None:
+            self._g_users.copy_(users, non_blocking=True)
+            self._graph.replay()
+            return self._g_loss
+        return self._sampled_step(_i64c(users, self.graph.device))

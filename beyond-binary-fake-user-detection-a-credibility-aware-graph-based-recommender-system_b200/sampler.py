@@ -79,8 +79,9 @@ class TripleSampler:
                                               ptr(self.n_classes), ptr(ws), ws.numel(), stream_ptr(dev)))
             self.tables = (self.items_by_deg, self.class_start, self.class_prob, self.class_alias, self.n_classes)
 
-    def sample(self, users: torch.Tensor, offset: int | None = None):
-        """users: int64 CUDA tensor of batch users, each with >= 1 train item.  Returns (pos, neg)."""
+    def sample(self, users: torch.Tensor, offset: int | None = None, offset_dev: torch.Tensor | None = None):
+        """users: int64 CUDA tensor of batch users, each with >= 1 train item.  Returns (pos, neg).
+        offset_dev: int64[1] device counter added to the offset (CUDA-graph replay)."""
         g, dev = self.graph, self.graph.device
         users = torch.as_tensor(users, device=dev).to(torch.int64).contiguous()
         B = users.numel()
@@ -94,6 +95,6 @@ class TripleSampler:
             check(lib().cgx_sample_triples(ptr(users), B, ptr(g.samp_indptr), ptr(g.samp_idx), g.num_items,
                                            ptr(t[0]), ptr(t[1]), ptr(t[2]), ptr(t[3]), ptr(t[4]),
                                            -1.0 if self.mix_pop is None else float(self.mix_pop), self.max_tries,
-                                           int(self.seed) & 0xFFFFFFFFFFFFFFFF, int(offset), ptr(pos), ptr(neg),
-                                           stream_ptr(dev)))
+                                           int(self.seed) & 0xFFFFFFFFFFFFFFFF, int(offset), ptr(offset_dev),
+                                           ptr(pos), ptr(neg), stream_ptr(dev)))
         return pos, neg

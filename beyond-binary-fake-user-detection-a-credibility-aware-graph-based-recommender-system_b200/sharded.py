@@ -27,7 +27,7 @@ import torch.distributed as dist
 from . import _lib
 from ._lib import check, lib, ptr, stream_ptr, workspace
 from .graph import CredGraph, build_graph
-from .model import apply_ego, bpr_buffers, bpr_fused, bpr_plan
+from .model import FusedAdam, apply_ego, bpr_buffers, bpr_fused, bpr_plan
 from .sampler import TripleSampler
 
 
@@ -168,9 +168,9 @@ class ShardedTrainStep:
         self.ei = torch.nn.Parameter(item_emb.contiguous())
         self.prop = ShardedPropagation(CudaBackend(graph), num_layers, order, group)
         self.sampler = TripleSampler(graph, mix_pop, gamma, max_tries, seed)
-        self.opt = torch.optim.Adam([self.eu, self.ei], lr=lr, fused=True)
         self.reg = float(reg_weight)
         self.eu.grad, self.ei.grad = torch.zeros_like(self.eu), torch.zeros_like(self.ei)
+        self.opt = FusedAdam(self.eu, self.ei, lr=lr)
         self.g_u = torch.empty_like(self.eu)
         n = self.ei.numel()
         self.red = torch.empty(2 * n + 4, dtype=torch.float32, device=self.ei.device)   # [seed ; ego ; loss]

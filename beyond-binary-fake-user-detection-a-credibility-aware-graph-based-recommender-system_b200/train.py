@@ -124,8 +124,7 @@ def train_on_arrays(train_edges, val_edges, test_edges, num_users, num_items, cr
         model = LightGCN(num_users, num_items, cfg.emb_dim, cfg.num_layers, graph.operator("A"),
                          graph.operator("C")).to(device)
         reg = cfg.reg
-    step = TrainStep(model, lr=cfg.lr, reg_weight=reg, fair_weight=cfg.lambda_fair if variant == "cu" else 0.0,
-                     pop=pop_fair if (variant == "cu" and cfg.lambda_fair) else None)
+    step = None
 
     rng = np.random.default_rng(cfg.seed)
     indptr_tr = train_csr[0]
@@ -142,6 +141,10 @@ def train_on_arrays(train_edges, val_edges, test_edges, num_users, num_items, cr
         sampler = TripleSampler(graph, cfg.neg_mix_pop, cfg.neg_pop_gamma, cfg.neg_max_tries, cfg.seed)
     else:
         sampler = TripleSampler(graph, None, seed=cfg.seed)
+    step = TrainStep(model, lr=cfg.lr, reg_weight=reg, fair_weight=cfg.lambda_fair if variant == "cu" else 0.0,
+                     pop=pop_fair if (variant == "cu" and cfg.lambda_fair) else None, sampler=sampler)
+    if len(train_users) >= cfg.batch_size:
+        step.capture(cfg.batch_size)          # full batches replay one CUDA graph; the tail batch runs eagerly
 
     def run_eval(csr):
         if cfg.eval_mode == "full" and variant != "cu":
@@ -162,9 +165,7 @@ def train_on_arrays(train_edges, val_edges, test_edges, num_users, num_items, cr
         users_dev = torch.from_numpy(train_users).to(device)
         losses = []
         for start in range(0, len(train_users), cfg.batch_size):
-            batch = users_dev[start:start + cfg.batch_size]
-            pos, neg = sampler.sample(batch)
-            losses.append(step(batch, pos, neg))
+            losses.append(step.step(users_dev[start:start + cfg.batch_size]).clone())
         avg_loss = float(torch.stack(losses).mean().item()) if losses else 0.0
         print(f"Epoch {epoch:03d} | loss={avg_loss:.6f}" if variant == "cu" else f"Epoch {epoch:02d} | loss={avg_loss:.6f}")
 

@@ -216,13 +216,26 @@ int cgx_sampler_build(const int32_t* deg_i, int32_t num_items, double gamma,
 
 /* users int64[B]: batch users (each must own >= 1 train item, as CU:592 guarantees).
  * mix_pop < 0 selects the uniform sampler of CU:295-299 (tables may then be NULL).
- * After max_tries rejected proposals the kernel falls back to uniform proposals (V2:373-376). */
+ * After max_tries rejected proposals the kernel falls back to uniform proposals (V2:373-376).
+ * offset_dev (nullable): device counter added to `offset`, so that a captured CUDA graph draws new
+ * triples on every replay (advance it with cgx_tick). */
 int cgx_sample_triples(const int64_t* users, int64_t batch, const int64_t* samp_indptr,
                        const int32_t* samp_idx, int32_t num_items,
                        const int32_t* items_by_deg, const int32_t* class_start,
                        const float* class_prob, const int32_t* class_alias, const int32_t* n_classes,
                        float mix_pop, int32_t max_tries, uint64_t seed, uint64_t offset,
-                       int64_t* pos_out, int64_t* neg_out, void* stream);
+                       const uint64_t* offset_dev, int64_t* pos_out, int64_t* neg_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimiser.  Replaces torch.optim.Adam(lr).step() (CU:587,652; V2:793,863; torch defaults) on the two
+ * embedding tables in one launch.  step = step_host + *step_dev (step_dev nullable), 1-based.
+ * cgx_tick increments a device counter by one (graph-replayable step / sampler offsets).
+ * ------------------------------------------------------------------------------------------ */
+int cgx_tick(uint64_t* counter, void* stream);
+int cgx_adam_step(float* p0, const float* g0, float* m0, float* v0, int64_t n0,
+                  float* p1, const float* g1, float* m1, float* v1, int64_t n1,
+                  float lr, float beta1, float beta2, float eps,
+                  const uint64_t* step_dev, int64_t step_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Full-rank evaluation.  Replaces the per-user loop of evaluate_full_ranking (V2:691-704):

@@ -503,3 +503,45 @@ def test_evaluate_full_ranking_tensor_core_metrics(cg, golden):
     for K in (10, 20):
         np.testing.assert_allclose([res[K][k] for k in ("precision", "recall", "ndcg")], g[f"full_{K}"][:3],
                                    rtol=TOL, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# optimiser and CUDA-graph step
+# ------------------------------------------------------------------------------------------------
+def test_fused_adam_matches_torch_adam(cg):
+    torch.manual_seed(3)
+    pu, pi = torch.randn(500, 64, device=DEV), torch.randn(300, 64, device=DEV)
+    qu, qi = torch.nn.Parameter(pu.clone()), torch.nn.Parameter(pi.clone())
+    ref = torch.optim.Adam([qu, qi], lr=1e-3)
+    ru, ri = torch.nn.Parameter(pu.clone()), torch.nn.Parameter(pi.clone())
+    mine = cg["model"].FusedAdam(ru, ri, lr=1e-3)
+    for t in range(5):
+        gu, gi = torch.randn_like(pu) * (10.0 ** -t), torch.randn_like(pi)
+        gi[::3] = 0.0
+        qu.grad, qi.grad, ru.grad, ri.grad = gu.clone(), gi.clone(), gu.clone(), gi.clone()
+        ref.step()
+        mine.step()
+        assert rel_err(ru.detach().cpu().numpy(), qu.detach().cpu().numpy()) < 1e-6
+        assert rel_err(ri.detach().cpu().numpy(), qi.detach().cpu().numpy()) < 1e-6
+    assert mine.state_dict()["step"] == 5
+
+
+def test_graph_captured_step_equals_eager_steps(cg):
+    """TrainStep.capture: N graph replays == N eager steps (same device-side sampler offsets and Adam
+    step counts), bit for bit."""
+    sg = cg["synth"].make_graph("C1")
+    gr = cg["graph"].build_graph(sg.train_edges, sg.num_users, sg.num_items, sg.cred, "v2", DEV)
+    users = torch.nonzero(gr.deg_u > 0).reshape(-1)[:512]
+    outs = []
+    for use_graph in (False, True):
+        torch.manual_seed(11)
+        net = cg["model"].LightGCN(sg.num_users, sg.num_items, 64, 3, gr.operator("A"), gr.operator("C")).to(DEV)
+        samp = cg["sampler"].TripleSampler(gr, 0.7, 0.75, 50, seed=5)
+        st = cg["model"].TrainStep(net, lr=1e-2, reg_weight=1e-4, sampler=samp)
+        if use_graph:
+            st.capture(512)
+        losses = [float(st.step(users).item()) for _ in range(4)]
+        outs.append((losses, net.user_emb.weight.detach().clone(), net.item_emb.weight.detach().clone()))
+    assert outs[0][0] == outs[1][0]
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    assert outs[0][0][-1] < outs[0][0][0]
