@@ -351,6 +351,11 @@ def main():
     bwd_ms = float(np.mean([m[2].elapsed_time(m[3]) for m in phases]))
     prop_ms = fwd_ms + bwd_ms
     hbm_peak, peak_src = peaks()
+    traffic = None
+    tpath = ROOT / "profiles" / "r1_traffic.json"
+    if tpath.exists():
+        traffic = json.loads(tpath.read_text()).get(args.workload, {}).get("bytes_per_launch")
+    table_mb = (U + I) * d * 4 / 1e6
     alg = algorithmic_bytes(U, I, gr.nnz, d, K)
     n_spmm = 4 * K
     achieved = alg / (prop_ms / 1e3) / 1e9
@@ -366,12 +371,16 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {
-            "bound": "hbm", "kernel": "k_spmm_rows (+ long-row partial/finish), 4K launches per step",
+            "bound": "hbm", "kernel": "k_spmm (+ k_spmm_finish for rows > 16384 nnz), 4K launches per step",
             "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-            "peak_source": peak_src, "traffic": None,
+            "peak_source": peak_src, "traffic": traffic,
+            "traffic_source": "ncu --set full capture of k_spmm, profiles/r1_traffic.json" if traffic else None,
             "algorithmic_bytes_per_step": alg, "algorithmic_bytes_per_launch": alg / n_spmm,
             "avg_launch_ms": prop_ms / n_spmm,
-            "note": "tables of this workload fit the 126 MB L2, so the gather-model figure can exceed the HBM peak",
+            "note": (f"embedding tables are {table_mb:.0f} MB: they fit the 126 MB L2, so the gather-model figure "
+                     "can exceed the HBM peak" if table_mb < 100 else
+                     f"embedding tables are {table_mb:.0f} MB (>> L2): HBM bound; the gather model counts every "
+                     "neighbour row as a fresh read, L2 hits on popular rows put DRAM traffic below it"),
         },
         "phases_ms": {"propagate_fwd": fwd_ms, "bpr_loss+grad_scatter": loss_ms, "propagate_bwd": bwd_ms,
                       "sampler+adam+rest": ms - prop_ms - loss_ms},
