@@ -30,7 +30,7 @@ class CsrStruct(C.Structure):
         ("indptr", C.c_void_p), ("idx", C.c_void_p), ("val_fwd", C.c_void_p), ("val_bwd", C.c_void_p),
         ("perm", C.c_void_p), ("n_long", C.c_int32), ("n_chunks", C.c_int32),
         ("chunk_ptr", C.c_void_p), ("chunk_row", C.c_void_p),
-        ("n_huge", C.c_int32), ("reserved_", C.c_int32), ("arrive", C.c_void_p),
+        ("n_huge", C.c_int32), ("reserved_", C.c_int32), ("arrive", C.c_void_p), ("work", C.c_void_p),
     ]
 
 
@@ -49,6 +49,7 @@ _SIGNATURES = {
     "cgx_row_schedule": (C.c_int, [_P, C.c_int32, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                    C.POINTER(C.c_int32), _P, C.c_size_t, _P]),
     "cgx_row_schedule_chunks": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
+    "cgx_row_schedule_work": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "cgx_spmm_workspace_bytes": (C.c_size_t, [_CSR, C.c_int32]),
     "cgx_spmm": (C.c_int, [_CSR, C.c_int, C.c_int32, _P, _P, _P, _P, C.c_float, _P, C.c_size_t, _P]),
     "cgx_propagate_workspace_bytes": (C.c_size_t, [_CSR, _CSR, C.c_int32]),

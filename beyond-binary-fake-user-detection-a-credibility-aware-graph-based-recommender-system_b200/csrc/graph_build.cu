@@ -397,3 +397,43 @@ extern "C" int cgx_row_schedule_chunks(int32_t n_rows, int32_t n_long, int32_t n
   CGX_LAUNCH_CHECK();
   return CGX_OK;
 }
+
+namespace cgx {
+__global__ void k_sched_work(const int64_t* __restrict__ indptr, const int32_t* __restrict__ perm, int32_t n_rows,
+                             int32_t n_long, int32_t n_chunks, const int32_t* __restrict__ chunk_ptr,
+                             const int32_t* __restrict__ chunk_row, int4* __restrict__ work) {
+  const int64_t item = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t n_items = int64_t(n_chunks) + (n_rows - n_long);
+  if (item >= n_items) return;
+  int64_t begin;
+  int32_t len, tag;
+  if (item < n_chunks) {
+    const int32_t k = chunk_row[item];
+    const int32_t row = perm[k];
+    begin = indptr[row] + int64_t(int32_t(item) - chunk_ptr[k]) * CGX_CHUNK;
+    const int64_t left = indptr[row + 1] - begin;
+    len = int32_t(left < CGX_CHUNK ? left : CGX_CHUNK);
+    tag = k;
+  } else {
+    const int32_t row = perm[item - n_chunks + n_long];
+    begin = indptr[row];
+    len = int32_t(indptr[row + 1] - begin);
+    tag = row;
+  }
+  work[item] = make_int4(int32_t(uint32_t(begin)), int32_t(begin >> 32), len, tag);
+}
+}  // namespace cgx
+
+extern "C" int cgx_row_schedule_work(const int64_t* indptr, const int32_t* perm, int32_t n_rows, int32_t n_long,
+                                     int32_t n_chunks, const int32_t* chunk_ptr, const int32_t* chunk_row,
+                                     void* work, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CGX_REQUIRE(indptr && perm && work && n_rows > 0 && n_long >= 0 && n_chunks >= 0, CGX_ERR_ARG,
+              "row_schedule_work: bad argument");
+  CGX_REQUIRE(n_long == 0 || (chunk_ptr && chunk_row), CGX_ERR_ARG, "row_schedule_work: chunk tables missing");
+  const int64_t n_items = int64_t(n_chunks) + (n_rows - n_long);
+  k_sched_work<<<grid_for(n_items), GB_THREADS, 0, stream>>>(indptr, perm, n_rows, n_long, n_chunks, chunk_ptr,
+                                                            chunk_row, static_cast<int4*>(work));
+  CGX_LAUNCH_CHECK();
+  return CGX_OK;
+}

@@ -68,16 +68,11 @@ __device__ __forceinline__ unsigned group_mask() {
 
 // acc[v] (v < V) += sum over nnz in [begin, end) of val * X[idx, :]; one group, lane = 0..G-1.
 template <int G, int V, int UNR, int HINT>
-__device__ __forceinline__ void gather_range(const int32_t* __restrict__ idx, const float* __restrict__ val,
-                                             int64_t begin, int64_t end, const float4* __restrict__ X, int lane,
-                                             unsigned mask, float4 (&acc)[V]) {
+__device__ __forceinline__ void gather_batches(const int32_t* __restrict__ idx, const float* __restrict__ val,
+                                               int64_t begin, int64_t end, const float4* __restrict__ X, int lane,
+                                               unsigned mask, int32_t c_nxt, float w_nxt, float4 (&acc)[V]) {
+  // (c_nxt, w_nxt) = this lane's column id / value of the first batch, already loaded by the caller
   constexpr int ROW4 = G * V;  // float4 per embedding row
-  int32_t c_nxt = 0;
-  float w_nxt = 0.f;
-  if (begin + lane < end) {
-    c_nxt = __ldg(idx + begin + lane);
-    w_nxt = __ldg(val + begin + lane);
-  }
   for (int64_t base = begin; base < end; base += G) {
     const int32_t c = c_nxt;
     const float w = w_nxt;
@@ -112,6 +107,19 @@ __device__ __forceinline__ void gather_range(const int32_t* __restrict__ idx, co
       }
     }
   }
+}
+
+template <int G, int V, int UNR, int HINT>
+__device__ __forceinline__ void gather_range(const int32_t* __restrict__ idx, const float* __restrict__ val,
+                                             int64_t begin, int64_t end, const float4* __restrict__ X, int lane,
+                                             unsigned mask, float4 (&acc)[V]) {
+  int32_t c = 0;
+  float w = 0.f;
+  if (begin + lane < end) {
+    c = __ldg(idx + begin + lane);
+    w = __ldg(val + begin + lane);
+  }
+  gather_batches<G, V, UNR, HINT>(idx, val, begin, end, X, lane, mask, c, w, acc);
 }
 
 template <int G, int V>
@@ -192,6 +200,82 @@ __global__ void __launch_bounds__(SP_THREADS, MINB) k_spmm(const int64_t* __rest
   epilogue<G, V>(row, lane, acc, Y, ACC_IN, ACC_OUT, acc_scale);
 }
 
+// Persistent, software-pipelined form of k_spmm: a fixed grid of groups walks the flattened work list
+// (cgx_row_schedule_work) round-robin -- group g takes items g, g + n_groups, ... so every round hands
+// neighbouring groups items of equal weight, heaviest rounds first -- and while an item's rows are
+// being gathered the NEXT item's 16-byte descriptor and its first batch of column ids / values are
+// already in flight.  That removes the per-row pointer chase (perm -> indptr -> idx -> rows) from the
+// critical path, which is what bounds rows of 10-40 non-zeros.
+template <int G, int V, int UNR, int HINT, int MINB>
+__global__ void __launch_bounds__(SP_THREADS, MINB) k_spmm_p(const int4* __restrict__ work, int64_t n_items,
+                                                             const int32_t* __restrict__ idx,
+                                                             const float* __restrict__ val, SpmmSched sc,
+                                                             const float4* __restrict__ X, float4* __restrict__ Y,
+                                                             const float4* ACC_IN, float4* ACC_OUT, float acc_scale,
+                                                             float4* partial) {
+  constexpr int ROW4 = G * V;
+  const int lane = threadIdx.x & (G - 1);
+  const unsigned mask = group_mask<G>();
+  const int64_t n_groups = int64_t(gridDim.x) * (SP_THREADS / G);
+  int64_t item = (int64_t(blockIdx.x) * SP_THREADS + threadIdx.x) / G;
+  if (item >= n_items) return;
+  int4 cur = __ldg(work + item);
+  int64_t begin = (int64_t(cur.y) << 32) | uint32_t(cur.x);
+  int32_t c0v = 0;
+  float w0v = 0.f;
+  if (lane < cur.z) {
+    c0v = __ldg(idx + begin + lane);
+    w0v = __ldg(val + begin + lane);
+  }
+  while (true) {
+    const int64_t nitem = item + n_groups;
+    const bool more = nitem < n_items;
+    int4 nxt = make_int4(0, 0, 0, 0);
+    if (more) nxt = __ldg(work + nitem);                 // descriptor of the next item: in flight during the gather
+    float4 acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    gather_batches<G, V, UNR, HINT>(idx, val, begin, begin + cur.z, X, lane, mask, c0v, w0v, acc);
+    const int64_t nbegin = (int64_t(nxt.y) << 32) | uint32_t(nxt.x);
+    c0v = 0;
+    w0v = 0.f;
+    if (more && lane < nxt.z) {                          // first batch of the next item: in flight during the epilogue
+      c0v = __ldg(idx + nbegin + lane);
+      w0v = __ldg(val + nbegin + lane);
+    }
+    if (item < sc.n_chunks) {
+      const int32_t k = cur.w;
+#pragma unroll
+      for (int v = 0; v < V; ++v) __stcg(partial + item * ROW4 + v * G + lane, acc[v]);
+      if (k >= sc.n_huge) {                              // rows above CGX_HUGE_ROW are combined by k_spmm_finish
+        const int32_t ch0 = __ldg(sc.chunk_ptr + k), ch1 = __ldg(sc.chunk_ptr + k + 1);
+        __threadfence();                                 // release: this group's partial is visible device-wide
+        __syncwarp(mask);
+        int prev = 0;
+        if (lane == 0) prev = atomicAdd(sc.arrive + k, 1);
+        prev = __shfl_sync(mask, prev, 0, G);
+        if (prev == ch1 - ch0 - 1) {                     // last chunk of the row: add the partials in chunk order
+          __threadfence();
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int c = ch0; c < ch1; ++c) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[v] = add4(acc[v], __ldcg(partial + int64_t(c) * ROW4 + v * G + lane));
+          }
+          epilogue<G, V>(int64_t(__ldg(sc.perm + k)), lane, acc, Y, ACC_IN, ACC_OUT, acc_scale);
+          if (lane == 0) sc.arrive[k] = 0;               // self-resetting for the next launch
+        }
+      }
+    } else {
+      epilogue<G, V>(int64_t(cur.w), lane, acc, Y, ACC_IN, ACC_OUT, acc_scale);
+    }
+    if (!more) break;
+    item = nitem;
+    cur = nxt;
+    begin = nbegin;
+  }
+}
+
 // one CTA per huge row: groups sum interleaved chunk partials, fixed-order reduction, epilogue
 template <int G, int V>
 __global__ void __launch_bounds__(SP_THREADS) k_spmm_finish(SpmmSched sc, const float4* __restrict__ partial,
@@ -229,6 +313,22 @@ __global__ void k_scale(const float4* __restrict__ in, float4* __restrict__ out,
   if (p < n4) out[p] = scale4(in[p], s);
 }
 
+static int spmm_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+// The persistent, software-pipelined kernel is kept as an experiment: measured SLOWER than one group per
+// item with hardware CTA scheduling (C2 d=64: 0.62 vs 0.43 ms fwd+bwd; 64M-edge d=128: 65.4 vs 61.2 ms;
+// profiles/r1_spmm_variants.txt), so it is off unless CGX_SPMM_PERSISTENT=1.
+static bool spmm_persistent() {
+  static const bool v = spmm_env("CGX_SPMM_PERSISTENT", 0) != 0;
+  return v;
+}
+static int spmm_waves() {
+  static const int v = spmm_env("CGX_SPMM_WAVES", 1);
+  return v < 1 ? 1 : v;
+}
+
 template <int G, int V, int UNR, int HINT, int MINB>
 static int launch_spmm(const cgx_csr* m, const float* val, const float* X, float* Y, const float* ACC_IN,
                        float* ACC_OUT, float acc_scale, void* workspace, size_t workspace_bytes,
@@ -243,9 +343,19 @@ static int launch_spmm(const cgx_csr* m, const float* val, const float* X, float
   }
   SpmmSched sc{m->perm, m->chunk_ptr, m->chunk_row, m->arrive, m->n_long, m->n_chunks, m->n_huge};
   const int64_t items = int64_t(m->n_chunks) + (m->n_rows - m->n_long);
-  k_spmm<G, V, UNR, HINT, MINB><<<(unsigned)ceil_div(items, GROUPS), SP_THREADS, 0, stream>>>(
-      m->indptr, m->idx, val, m->n_rows, sc, reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(Y),
-      reinterpret_cast<const float4*>(ACC_IN), reinterpret_cast<float4*>(ACC_OUT), acc_scale, partial);
+  if (m->work != nullptr && spmm_persistent()) {
+    int64_t blocks = ceil_div(items, GROUPS);
+    const int64_t resident = int64_t(148) * MINB * spmm_waves();     // CTAs that fit the chip at once (x waves)
+    if (blocks > resident) blocks = resident;
+    k_spmm_p<G, V, UNR, HINT, MINB><<<(unsigned)blocks, SP_THREADS, 0, stream>>>(
+        static_cast<const int4*>(m->work), items, m->idx, val, sc, reinterpret_cast<const float4*>(X),
+        reinterpret_cast<float4*>(Y), reinterpret_cast<const float4*>(ACC_IN), reinterpret_cast<float4*>(ACC_OUT),
+        acc_scale, partial);
+  } else {
+    k_spmm<G, V, UNR, HINT, MINB><<<(unsigned)ceil_div(items, GROUPS), SP_THREADS, 0, stream>>>(
+        m->indptr, m->idx, val, m->n_rows, sc, reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(Y),
+        reinterpret_cast<const float4*>(ACC_IN), reinterpret_cast<float4*>(ACC_OUT), acc_scale, partial);
+  }
   CGX_LAUNCH_CHECK();
   if (m->n_huge > 0) {
     k_spmm_finish<G, V><<<(unsigned)m->n_huge, SP_THREADS, 0, stream>>>(

@@ -68,6 +68,7 @@ class Csr:
     n_chunks: int = 0
     n_huge: int = 0
     arrive: torch.Tensor | None = None
+    work: torch.Tensor | None = None
     _struct: CsrStruct | None = field(default=None, repr=False)
 
     def struct(self) -> CsrStruct:
@@ -82,6 +83,7 @@ class Csr:
             s.chunk_row = self.chunk_row.data_ptr() if self.n_long else None
             s.n_huge = self.n_huge
             s.arrive = self.arrive.data_ptr() if self.n_long else None
+            s.work = self.work.data_ptr() if self.work is not None else None
             self._struct = s
         return self._struct
 
@@ -104,6 +106,11 @@ class Csr:
                 self.chunk_row = torch.empty(self.n_chunks, dtype=torch.int32, device=dev)
                 check(lib().cgx_row_schedule_chunks(self.n_rows, self.n_long, self.n_chunks, ptr(self.chunk_ptr),
                                                     ptr(self.chunk_row), ptr(ws), ws.numel(), stream_ptr(dev)))
+            n_items = self.n_chunks + self.n_rows - self.n_long
+            self.work = torch.empty(max(n_items, 1), 4, dtype=torch.int32, device=dev)
+            check(lib().cgx_row_schedule_work(ptr(self.indptr), ptr(self.perm), self.n_rows, self.n_long,
+                                              self.n_chunks, ptr(self.chunk_ptr), ptr(self.chunk_row),
+                                              ptr(self.work), stream_ptr(dev)))
         self._struct = None
 
     def row_ids(self) -> torch.Tensor:

@@ -85,6 +85,8 @@ typedef struct {
   int32_t reserved_;
   int32_t* arrive;           /* device, [n_long] arrival counters, zero between launches (self-resetting);
                                 mutable: at most one SpMM per cgx_csr may be in flight at a time */
+  const void* work;          /* device, [n_chunks + n_rows - n_long] 16-byte work items in launch order
+                                {int64 begin; int32 len; int32 row (or perm position of a chunk's row)} */
 } cgx_csr;
 
 #define CGX_LONG_ROW 256     /* rows above this many non-zeros are split */
@@ -132,6 +134,12 @@ int cgx_row_schedule(const int64_t* indptr, int32_t n_rows, int32_t* perm, int32
                      void* stream);
 int cgx_row_schedule_chunks(int32_t n_rows, int32_t n_long, int32_t n_chunks, int32_t* chunk_ptr,
                             int32_t* chunk_row, void* workspace, size_t workspace_bytes, void* stream);
+/* Flattens the schedule into the 16-byte work items the SpMM kernel streams (one load per item instead
+ * of the perm -> indptr -> chunk table pointer chase): work = device buffer of
+ * 16 * (n_chunks + n_rows - n_long) bytes.  chunk_ptr / chunk_row may be NULL when n_long == 0. */
+int cgx_row_schedule_work(const int64_t* indptr, const int32_t* perm, int32_t n_rows, int32_t n_long,
+                          int32_t n_chunks, const int32_t* chunk_ptr, const int32_t* chunk_row, void* work,
+                          void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Propagation.  Replaces torch.sparse.mm + stack().mean() (CU:420-448, V2:472-490) and their
