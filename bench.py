@@ -29,8 +29,8 @@ METRIC = "edges/sec (3-layer cred-weighted LightGCN fwd+bwd)"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4"])
     ap.add_argument("--batch", type=int, default=4096)
@@ -61,47 +61,54 @@ def algorithmic_bytes(U, I, E, d, K):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md recipe): one background `nvidia-smi -lms 20`
+    for the life of the bench; `window()` marks the timed region and `summary()` reports the samples whose
+    timestamps fall inside it (or, for regions shorter than the sampling period, the nearest ones)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.rows, self.stop_flag, self.index = [], threading.Event(), index
-        self.t = threading.Thread(target=self.run, daemon=True)
-
-    def run(self):
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(",")])
-            except Exception:
-                pass
-            self.stop_flag.wait(0.1)
+        self.t0 = self.t1 = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
+        except Exception:
+            self.proc = None
 
     def __enter__(self):
-        self.t.start()
+        self.t0 = time.time()
         return self
 
     def __exit__(self, *a):
-        self.stop_flag.set()
-        self.t.join(timeout=6)
+        self.t1 = time.time()
 
     def summary(self):
-        sm, mx, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = []
+        if self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
             try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-                for n, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+                out, _ = self.proc.communicate(timeout=5)
             except Exception:
-                continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                out = ""
+            import datetime
+            for line in out.splitlines():
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(f[1]), float(f[2]), [v.lower().startswith("active") for v in f[4:8]]))
+                except Exception:
+                    continue
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        inside = [r for r in rows if self.t0 - 0.02 <= r[0] <= self.t1 + 0.02]
+        if not inside and rows:                      # region shorter than the sampling period: nearest samples
+            mid = 0.5 * (self.t0 + self.t1)
+            inside = sorted(rows, key=lambda r: abs(r[0] - mid))[:3]
+        reasons = sorted({n for r in inside for n, v in zip(names, r[3]) if v})
+        return {"sm_mhz": float(np.median([r[1] for r in inside])) if inside else None,
+                "sm_max_mhz": max([r[2] for r in inside]) if inside else None,
+                "reasons": reasons, "samples": len(inside), "samples_total": len(rows)}
 
 
 def make_workload(name, device=None):
@@ -303,6 +310,7 @@ def main():
     def one_step(users):
         return step.step(users)
 
+    clocks = ClockSampler(local)      # polls from here on; the timed region is marked below
     # ---- warm-up ----
     for s in range(max(args.warmup, 3)):
         one_step(dev_batches[s % len(dev_batches)])
@@ -313,7 +321,7 @@ def main():
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     launches0 = _lib.lib().cgx_launch_count()
-    with ClockSampler(local) as clocks:
+    with clocks:
         torch.cuda.synchronize()
         for s in range(args.steps):
             if not args.no_flush:
