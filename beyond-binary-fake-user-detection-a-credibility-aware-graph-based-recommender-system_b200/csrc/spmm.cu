@@ -157,6 +157,11 @@ __global__ void __launch_bounds__(SP_THREADS, MINB) k_spmm(const int64_t* __rest
                                                            float4* __restrict__ Y, const float4* ACC_IN,
                                                            float4* ACC_OUT, float acc_scale, float4* partial) {
   constexpr int ROW4 = G * V;
+  // Programmatic dependent launch: let the next kernel of the stream start its own prologue now, and run
+  // THIS kernel's prologue (schedule lookups, first batch of column ids / values -- graph constants) while the
+  // previous kernel is still draining.  Nothing the previous kernel wrote is read, and nothing is written,
+  // before griddepcontrol.wait returns.
+  asm volatile("griddepcontrol.launch_dependents;");
   const int lane = threadIdx.x & (G - 1);
   const int64_t item = (int64_t(blockIdx.x) * SP_THREADS + threadIdx.x) / G;
   const unsigned mask = group_mask<G>();
@@ -170,7 +175,14 @@ __global__ void __launch_bounds__(SP_THREADS, MINB) k_spmm(const int64_t* __rest
     const int64_t rbeg = __ldg(indptr + row), rend = __ldg(indptr + row + 1);
     const int64_t begin = rbeg + int64_t(int32_t(item) - c0) * CGX_CHUNK;
     const int64_t end = begin + CGX_CHUNK < rend ? begin + CGX_CHUNK : rend;
-    gather_range<G, V, UNR, HINT>(idx, val, begin, end, X, lane, mask, acc);
+    int32_t cf = 0;
+    float wf = 0.f;
+    if (begin + lane < end) {
+      cf = __ldg(idx + begin + lane);
+      wf = __ldg(val + begin + lane);
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    gather_batches<G, V, UNR, HINT>(idx, val, begin, end, X, lane, mask, cf, wf, acc);
 #pragma unroll
     for (int v = 0; v < V; ++v) __stcg(partial + item * ROW4 + v * G + lane, acc[v]);
     if (k < sc.n_huge) return;            // combined by k_spmm_finish
@@ -196,7 +208,14 @@ __global__ void __launch_bounds__(SP_THREADS, MINB) k_spmm(const int64_t* __rest
   if (r >= n_rows) return;
   const int32_t row = __ldg(sc.perm + r);
   const int64_t begin = __ldg(indptr + row), end = __ldg(indptr + row + 1);
-  gather_range<G, V, UNR, HINT>(idx, val, begin, end, X, lane, mask, acc);
+  int32_t cf = 0;
+  float wf = 0.f;
+  if (begin + lane < end) {
+    cf = __ldg(idx + begin + lane);
+    wf = __ldg(val + begin + lane);
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  gather_batches<G, V, UNR, HINT>(idx, val, begin, end, X, lane, mask, cf, wf, acc);
   epilogue<G, V>(row, lane, acc, Y, ACC_IN, ACC_OUT, acc_scale);
 }
 
@@ -324,6 +343,10 @@ static bool spmm_persistent() {
   static const bool v = spmm_env("CGX_SPMM_PERSISTENT", 0) != 0;
   return v;
 }
+static bool spmm_pdl() {   // programmatic dependent launch of k_spmm (CGX_SPMM_PDL=0 disables)
+  static const bool v = spmm_env("CGX_SPMM_PDL", 1) != 0;
+  return v;
+}
 static int spmm_waves() {
   static const int v = spmm_env("CGX_SPMM_WAVES", 1);
   return v < 1 ? 1 : v;
@@ -352,9 +375,20 @@ static int launch_spmm(const cgx_csr* m, const float* val, const float* X, float
         reinterpret_cast<float4*>(Y), reinterpret_cast<const float4*>(ACC_IN), reinterpret_cast<float4*>(ACC_OUT),
         acc_scale, partial);
   } else {
-    k_spmm<G, V, UNR, HINT, MINB><<<(unsigned)ceil_div(items, GROUPS), SP_THREADS, 0, stream>>>(
-        m->indptr, m->idx, val, m->n_rows, sc, reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(Y),
-        reinterpret_cast<const float4*>(ACC_IN), reinterpret_cast<float4*>(ACC_OUT), acc_scale, partial);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ceil_div(items, GROUPS));
+    cfg.blockDim = dim3(SP_THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = spmm_pdl() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CGX_CUDA(cudaLaunchKernelEx(&cfg, k_spmm<G, V, UNR, HINT, MINB>, m->indptr, m->idx, val, m->n_rows, sc,
+                                reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(Y),
+                                reinterpret_cast<const float4*>(ACC_IN), reinterpret_cast<float4*>(ACC_OUT), acc_scale,
+                                partial));
   }
   CGX_LAUNCH_CHECK();
   if (m->n_huge > 0) {
