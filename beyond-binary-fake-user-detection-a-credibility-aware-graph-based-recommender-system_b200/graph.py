@@ -321,6 +321,38 @@ def build_message_passing_mats_degree_aware(train_edges_2xE, num_users, num_item
     return build_message_passing_mats(train_edges_2xE, num_users, num_items, cred_u, device, degree_aware=True)
 
 
+class NormAdj:
+    """Handle returned by build_norm_adj: the (U+I) x (U+I) symmetric operator of plain LightGCN
+    (lightgcn.py:352-372) held as the two bipartite blocks of a CredGraph with credibility == 1."""
+
+    def __init__(self, graph: CredGraph):
+        self.graph = graph
+        n = graph.num_users + graph.num_items
+        self.shape = (n, n)
+
+    def size(self, dim=None):
+        return self.shape if dim is None else self.shape[dim]
+
+    def coalesce(self):
+        return self
+
+    def to_sparse_coo(self) -> torch.Tensor:
+        g = self.graph
+        a = g.operator("A")
+        r, c = a.indices()
+        v = a.values()
+        idx = torch.cat([torch.stack([r, c + g.num_users]), torch.stack([c + g.num_users, r])], dim=1)
+        return torch.sparse_coo_tensor(idx, torch.cat([v, v]), size=self.shape).coalesce()
+
+
+def build_norm_adj(train_edges, num_users, num_items, device="cuda") -> NormAdj:
+    """Drop-in for lightgcn.py:352: D^-1/2 A D^-1/2 of the bipartite graph (duplicate edges add up).
+    The reference evaluates deg^-0.5 with torch.pow, which is not reproducible bit for bit across
+    devices; values here are m / sqrt(deg_u * deg_i) in correctly rounded fp32 (within a few ulp)."""
+    g = build_graph(train_edges, num_users, num_items, np.ones(num_users, dtype=np.float32), "cu", device)
+    return NormAdj(g)
+
+
 def graph_of(M_a, M_b) -> CredGraph:
     """The CredGraph behind a pair of operator views (order-insensitive; both must share it)."""
     if not (isinstance(M_a, Operator) and isinstance(M_b, Operator)):

@@ -248,6 +248,39 @@ class LightGCN(_Base):
                               pos_items, neg_items, reg_weight)
 
 
+class RawLightGCN(torch.nn.Module):
+    """Plain LightGCN of lightgcn.py:306-349 (the thesis' ablation baseline): ONE embedding table over
+    users + items and the symmetric normalised adjacency; x <- A x on a bipartite graph is the Jacobi
+    schedule on the two blocks of the table.  state_dict key: `emb.weight`."""
+
+    def __init__(self, num_users, num_items, emb_dim, num_layers, norm_adj):
+        super().__init__()
+        from .graph import NormAdj
+        if not isinstance(norm_adj, NormAdj):
+            raise TypeError("expected the handle returned by credgcn.graph.build_norm_adj")
+        self.num_users, self.num_items, self.num_layers = num_users, num_items, num_layers
+        self.num_nodes = num_users + num_items
+        self.norm_adj, self.graph = norm_adj, norm_adj.graph
+        if not lib().cgx_emb_dim_supported(emb_dim):
+            raise _lib.CgxError(f"emb_dim={emb_dim} unsupported: use 16, 32, 64, 128 or 256")
+        self.emb = torch.nn.Embedding(self.num_nodes, emb_dim)
+        torch.nn.init.xavier_uniform_(self.emb.weight)
+
+    def propagate(self):
+        w = self.emb.weight
+        fu, fi = _Propagate.apply(w[: self.num_users], w[self.num_users:], self.graph, self.num_layers, "jacobi")
+        return torch.cat([fu, fi], dim=0)
+
+    def get_user_item_emb(self):
+        x = self.propagate()
+        return x[: self.num_users], x[self.num_users:]
+
+    def bpr_loss(self, users, pos_items, neg_items, user_emb, item_emb, reg_weight: float):
+        w = self.emb.weight
+        return fused_bpr_loss(self.graph, user_emb, item_emb, w[: self.num_users], w[self.num_users:], users,
+                              pos_items, neg_items, reg_weight)
+
+
 # ------------------------------------------------------------------------------------------
 # optimiser + fused training step (sampler -> forward -> loss -> backward -> Adam), no autograd graph
 # ------------------------------------------------------------------------------------------

@@ -545,3 +545,27 @@ def test_graph_captured_step_equals_eager_steps(cg):
     assert outs[0][0] == outs[1][0]
     assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
     assert outs[0][0][-1] < outs[0][0][0]
+
+
+# ------------------------------------------------------------------------------------------------
+# plain LightGCN baseline (lightgcn.py): SURVEY.md section 8f-4
+# ------------------------------------------------------------------------------------------------
+def test_raw_lightgcn_matches_reference(cg):
+    g = load_golden("small", "raw")
+    U, I, d, K = int(g["num_users"]), int(g["num_items"]), int(g["emb_dim"]), int(g["num_layers"])
+    adj = cg["graph"].build_norm_adj(g["train_edges"], U, I, DEV)
+    coo = adj.to_sparse_coo()
+    np.testing.assert_array_equal(coo.indices().cpu().numpy(), g["adj_idx"])
+    np.testing.assert_allclose(coo.values().cpu().numpy(), g["adj_val"], rtol=1e-6)     # torch.pow vs exact sqrt/div
+    net = cg["model"].RawLightGCN(U, I, d, K, adj)
+    assert set(net.state_dict().keys()) == {"emb.weight"}
+    net.load_state_dict({"emb.weight": torch.tensor(g["emb0"])})
+    net = net.to(DEV)
+    ue, ie = net.get_user_item_emb()
+    assert rel_err(ue.detach().cpu().numpy(), g["final_u"]) < TOL
+    assert rel_err(ie.detach().cpu().numpy(), g["final_i"]) < TOL
+    ut, pt, nt = (torch.tensor(g[k], device=DEV) for k in ("users", "pos", "neg"))
+    loss = net.bpr_loss(ut, pt, nt, ue, ie, 1e-4)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) / abs(float(g["loss"])) < TOL
+    assert rel_err(net.emb.weight.grad.cpu().numpy(), g["grad"]) < TOL

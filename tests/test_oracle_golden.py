@@ -140,3 +140,18 @@ def test_full_ranking(golden):
             got = [res[K][k] for k in ("item_coverage", "avg_log_popularity", "avg_self_information",
                                        "cred_utility", "high_cred_recall", "low_cred_recall")]
             np.testing.assert_allclose(got, want[3:], rtol=TOL, atol=1e-6)
+
+
+def test_plain_lightgcn_is_the_unit_credibility_jacobi_case():
+    """lightgcn.py (no credibility, one N x N operator) == Jacobi propagation with c_u = 1 on both
+    blocks: pins the reduction the product uses for SURVEY.md section 8f-4 against the reference's outputs."""
+    from conftest import load_golden
+    g = load_golden("small", "raw")
+    U, I, K = int(g["num_users"]), int(g["num_items"]), int(g["num_layers"])
+    ops = orc.Operators(g["train_edges"], U, I, np.ones(U, np.float32), "cu")
+    e0 = g["emb0"]
+    fu, fi = orc.propagate(ops, e0[:U], e0[U:], K, "jacobi")
+    assert rel_err(fu, g["final_u"]) < TOL and rel_err(fi, g["final_i"]) < TOL
+    loss, gu, gi, _, _ = orc.train_step_grads(ops, e0[:U], e0[U:], g["users"], g["pos"], g["neg"], K, "jacobi", 1e-4)
+    assert abs(loss - float(g["loss"])) / abs(float(g["loss"])) < TOL
+    assert rel_err(np.concatenate([gu, gi]), g["grad"]) < TOL
