@@ -215,5 +215,13 @@ def train_lightgcn():
 
 
 def main():
+    """The reference's main() (lightgcn_cu.py:690-703): build the graph files if they are missing, then train.
+    Unlike the reference, the raw JSONL is only required when the graph files do not exist yet."""
+    from . import ingest
     set_seed(config.cfg.seed)
+    if not (Path(config.cfg.out_dir) / "npy" / "train_edges.npy").exists():
+        print("Graph files not found. Building graph first...")
+        ingest.build_graph_from_jsonl()
+    else:
+        print("Graph files exist. Skipping construction.")
     train_lightgcn()
