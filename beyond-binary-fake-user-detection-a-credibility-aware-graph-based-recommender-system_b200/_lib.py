@@ -71,6 +71,13 @@ _SIGNATURES = {
     "cgx_tick": (C.c_int, [_P, _P]),
     "cgx_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, _P, _P, _P, C.c_int64, C.c_float, C.c_float,
                                 C.c_float, C.c_float, _P, C.c_int64, _P]),
+    "cgx_comm_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "cgx_comm_free": (C.c_int, [_P]),
+    "cgx_comm_ipc_handle": (C.c_int, [_P, _P]),
+    "cgx_comm_ipc_open": (C.c_int, [_P, C.POINTER(C.c_void_p)]),
+    "cgx_comm_ipc_close": (C.c_int, [_P]),
+    "cgx_comm_allreduce": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_size_t, C.c_size_t, C.c_size_t,
+                                     C.c_int64, C.c_uint32, _P]),
     "cgx_eval_topk_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int]),
     "cgx_eval_topk": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.c_int, _P,
                                 _P, _P, C.c_size_t, _P]),

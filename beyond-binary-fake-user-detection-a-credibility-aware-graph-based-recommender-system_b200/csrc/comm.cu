@@ -1,0 +1,153 @@
+// Item-table exchange of the user-sharded propagation over NVLink peer memory.
+//
+// The reference is single-device (no collective to replace); SURVEY.md section 8e defines the exchange: every
+// rank holds a PARTIAL item table (the product over its own users) that must be summed over ranks once
+// per layer.  NCCL's all-reduce is latency-bound at these sizes (10-20 MB: ~56 us at 2 GPUs, measured),
+// so the sum is done by one kernel over peer-mapped buffers instead:
+//
+//   * every rank owns one cudaMalloc'ed communication buffer, exported with cudaIpcGetMemHandle and
+//     mapped by all peers (cudaIpcOpenMemHandle): two `in` regions, two `out` regions (parity of the
+//     collective's epoch), and a flag page;
+//   * the SpMM writes its partial straight into in[parity] (no staging copy);
+//   * k_p2p_allreduce, two-shot and pull-based:
+//       A. signal "my partial is complete" into every peer's flag page (st.release.sys), wait for all
+//          peers' signals (ld.acquire.sys);
+//       1. rank r sums slice r of all partials IN RANK ORDER (peer loads over NVLink; deterministic,
+//          identical bits on every rank) and stores the reduced slice into every peer's out[parity];
+//       B. the last CTA to finish signals "my slice is delivered" to every peer and waits for theirs, so
+//          the kernel completes only when out[parity] is whole.
+//     Double buffering by parity makes the entry barrier sufficient against write-after-read hazards: a
+//     rank re-uses in/out[parity] two collectives later, and it cannot pass barrier A of the collective in
+//     between before every peer has finished reading/writing the previous use.
+//   * epochs are 1, 2, 3, ... and must advance identically on all ranks (the propagation schedule is
+//     deterministic).
+#include <string.h>
+
+#include "common.cuh"
+
+namespace cgx {
+
+constexpr int P2P_MAX_RANKS = 16;
+constexpr int P2P_THREADS = 256;
+
+struct P2PPeers {
+  char* base[P2P_MAX_RANKS];   // peer-mapped communication buffers, index = rank
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_peer(const float4* p) {   // written by another GPU: never from a stale L1 line
+  float4 r;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// flag page layout (uint32): [0 .. R) barrier A slots, [R .. 2R) barrier B slots, [2R] CTA arrival counter
+__global__ void __launch_bounds__(P2P_THREADS) k_p2p_allreduce(P2PPeers peers, int rank, int world, size_t in_off,
+                                                               size_t out_off, size_t flag_off, int64_t n4,
+                                                               uint32_t epoch) {
+  uint32_t* my_flags = reinterpret_cast<uint32_t*>(peers.base[rank] + flag_off);
+  // ---- barrier A: all partials complete ----
+  if (blockIdx.x == 0 && threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<uint32_t*>(peers.base[threadIdx.x] + flag_off) + rank, epoch);
+  }
+  if (threadIdx.x < world) {
+    while (ld_acquire_sys(my_flags + threadIdx.x) < epoch) __nanosleep(64);
+  }
+  __syncthreads();
+  // ---- reduce-scatter + all-gather of my slice ----
+  const int64_t per = (n4 + world - 1) / world;
+  const int64_t lo = int64_t(rank) * per;
+  const int64_t hi = lo + per < n4 ? lo + per : n4;
+  for (int64_t i = lo + int64_t(blockIdx.x) * P2P_THREADS + threadIdx.x; i < hi; i += int64_t(gridDim.x) * P2P_THREADS) {
+    float4 s = ld_peer(reinterpret_cast<const float4*>(peers.base[0] + in_off) + i);
+    for (int p = 1; p < world; ++p) {
+      const float4 v = ld_peer(reinterpret_cast<const float4*>(peers.base[p] + in_off) + i);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    for (int p = 0; p < world; ++p) reinterpret_cast<float4*>(peers.base[p] + out_off)[i] = s;
+  }
+  // ---- barrier B: every slice delivered ----
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(my_flags + 2 * world, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x == 0) my_flags[2 * world] = 0;   // self-resetting
+  if (threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<uint32_t*>(peers.base[threadIdx.x] + flag_off) + world + rank, epoch);
+    while (ld_acquire_sys(my_flags + world + threadIdx.x) < epoch) __nanosleep(64);
+  }
+}
+
+}  // namespace cgx
+
+using namespace cgx;
+
+extern "C" int cgx_comm_alloc(size_t bytes, void** base_out) {
+  CGX_REQUIRE(base_out != nullptr && bytes > 0, CGX_ERR_ARG, "comm_alloc: bad argument");
+  CGX_CUDA(cudaMalloc(base_out, bytes));
+  CGX_CUDA(cudaMemset(*base_out, 0, bytes));
+  CGX_CUDA(cudaDeviceSynchronize());
+  return CGX_OK;
+}
+
+extern "C" int cgx_comm_free(void* base) {
+  if (base) CGX_CUDA(cudaFree(base));
+  return CGX_OK;
+}
+
+extern "C" int cgx_comm_ipc_handle(void* base, void* handle_out_64) {
+  CGX_REQUIRE(base && handle_out_64, CGX_ERR_ARG, "comm_ipc_handle: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  CGX_CUDA(cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(handle_out_64), base));
+  return CGX_OK;
+}
+
+extern "C" int cgx_comm_ipc_open(const void* handle_64, void** peer_base_out) {
+  CGX_REQUIRE(handle_64 && peer_base_out, CGX_ERR_ARG, "comm_ipc_open: bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle_64, sizeof(h));
+  CGX_CUDA(cudaIpcOpenMemHandle(peer_base_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return CGX_OK;
+}
+
+extern "C" int cgx_comm_ipc_close(void* peer_base) {
+  if (peer_base) CGX_CUDA(cudaIpcCloseMemHandle(peer_base));
+  return CGX_OK;
+}
+
+extern "C" int cgx_comm_allreduce(int rank, int world, void* const* peer_bases, size_t in_off, size_t out_off,
+                                  size_t flag_off, int64_t n_floats, uint32_t epoch, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CGX_REQUIRE(world >= 1 && world <= P2P_MAX_RANKS && rank >= 0 && rank < world && peer_bases, CGX_ERR_ARG,
+              "comm_allreduce: bad rank/world");
+  CGX_REQUIRE(n_floats > 0 && n_floats % 4 == 0 && in_off % 16 == 0 && out_off % 16 == 0 && flag_off % 16 == 0 &&
+                  epoch > 0,
+              CGX_ERR_ARG, "comm_allreduce: bad sizes/offsets");
+  P2PPeers peers;
+  for (int p = 0; p < world; ++p) {
+    CGX_REQUIRE(peer_bases[p] != nullptr, CGX_ERR_ARG, "comm_allreduce: NULL peer buffer");
+    peers.base[p] = static_cast<char*>(peer_bases[p]);
+  }
+  const int64_t n4 = n_floats / 4;
+  const int64_t per = ceil_div(n4, world);
+  int64_t blocks = ceil_div(per, P2P_THREADS * 4);
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  if (blocks < 1) blocks = 1;
+  k_p2p_allreduce<<<(unsigned)blocks, P2P_THREADS, 0, stream>>>(peers, rank, world, in_off, out_off, flag_off, n4,
+                                                             epoch);
+  CGX_LAUNCH_CHECK();
+  return CGX_OK;
+}

@@ -61,6 +61,84 @@ def all_reduce_sum(t: torch.Tensor, group=None) -> torch.Tensor:
     return t
 
 
+class CollectiveExchange:
+    """Partial item table -> whole item table through torch.distributed (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, group=None):
+        self.group = group
+
+    def partial_buffer(self, shape, device):
+        return torch.empty(shape, dtype=torch.float32, device=device)
+
+    def reduce(self, buf):
+        return all_reduce_sum(buf, self.group)
+
+
+class _RawCuda:
+    def __init__(self, address, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (address, False),
+                                         "version": 3, "strides": None}
+
+
+class P2PExchange:
+    """Same contract over NVLink peer memory (csrc/comm.cu): partials are written straight into a
+    peer-mapped buffer and summed in rank order by one two-shot pull kernel.  Needs all ranks on one node
+    with peer access (NVSwitch); the process group is only used once, to hand out the IPC handles."""
+
+    REGION_ALIGN = 1 << 16
+
+    def __init__(self, max_floats: int, device, group=None):
+        import ctypes as C
+        self.group, self.device = group, torch.device(device)
+        self.world = _world(group)
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.region = (4 * int(max_floats) + self.REGION_ALIGN - 1) // self.REGION_ALIGN * self.REGION_ALIGN
+        self.flag_off = 4 * self.region
+        total = self.flag_off + 4096
+        base = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().cgx_comm_alloc(total, C.byref(base)))
+            handle = (C.c_char * 64)()
+            check(lib().cgx_comm_ipc_handle(base, handle))
+            handles = [None] * self.world
+            if self.world > 1:
+                dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            self.bases = (C.c_void_p * self.world)()
+            for p in range(self.world):
+                if p == self.rank:
+                    self.bases[p] = base.value
+                else:
+                    peer = C.c_void_p()
+                    check(lib().cgx_comm_ipc_open(C.c_char_p(handles[p]), C.byref(peer)))
+                    self.bases[p] = peer.value
+        self.base = base
+        self.bytes = torch.as_tensor(_RawCuda(base.value, total), device=self.device)
+        self.epoch = 0
+        if self.world > 1:
+            dist.barrier(group=group)          # every rank has mapped every buffer before the first collective
+
+    def _view(self, offset, shape):
+        n = int(np.prod(shape))
+        return self.bytes[offset: offset + 4 * n].view(torch.float32).view(shape)
+
+    def partial_buffer(self, shape, device=None):
+        """The `in` region of the NEXT collective: fill it, then call reduce() on it."""
+        if 4 * int(np.prod(shape)) > self.region:
+            raise _lib.CgxError("P2PExchange: payload larger than the communication regions")
+        return self._view(((self.epoch + 1) & 1) * self.region, shape)
+
+    def reduce(self, buf):
+        self.epoch += 1
+        par = self.epoch & 1
+        n = buf.numel()
+        n_pad = (n + 3) // 4 * 4
+        with torch.cuda.device(self.device):
+            check(lib().cgx_comm_allreduce(self.rank, self.world, self.bases, par * self.region,
+                                           (2 + par) * self.region, self.flag_off, n_pad, self.epoch,
+                                           stream_ptr(self.device)))
+        return self._view((2 + par) * self.region, tuple(buf.shape))
+
+
 class BackendBase:
     """A shard backend provides item_rows(x_u, bwd) and user_rows(x_i, bwd); the fused form below has
     a generic default so that test doubles only implement the two products."""
@@ -92,9 +170,9 @@ class CudaBackend(BackendBase):
                                  ptr(ws), ws.numel(), stream_ptr(x.device)))
         return y if y is not None else acc_out
 
-    def item_rows(self, x_u, bwd=False):
-        """Partial [I, d]: C x_u (bwd: A^T x_u) summed over THIS shard's users."""
-        return self._spmm(self.graph.by_item, x_u, bwd)
+    def item_rows(self, x_u, bwd=False, out=None):
+        """Partial [I, d]: C x_u (bwd: A^T x_u) summed over THIS shard's users (written into `out` if given)."""
+        return self._spmm(self.graph.by_item, x_u, bwd, y=out)
 
     def user_rows(self, x_i, bwd=False):
         """[U_local, d]: A x_i (bwd: C^T x_i) for this shard's users."""
@@ -113,10 +191,19 @@ class ShardedPropagation:
     """K-layer propagation and its adjoint over user shards (lightgcn_cu.py:420-448 /
     Version-2/lighgcn_cu_pop.py:472-490 and their autograd)."""
 
-    def __init__(self, backend, num_layers: int, order: str, group=None):
+    def __init__(self, backend, num_layers: int, order: str, group=None, exchange=None):
         if order not in ("jacobi", "gs"):
             raise ValueError(order)
         self.b, self.K, self.order, self.group = backend, int(num_layers), order, group
+        self.ex = exchange or CollectiveExchange(group)
+
+    def _item_exchange(self, x_u, bwd, shape):
+        """Partial item table of this shard -> whole item table (one exchange)."""
+        buf = self.ex.partial_buffer(shape, x_u.device)
+        res = self.b.item_rows(x_u, bwd, out=buf)
+        if res is not buf:                      # backends without an `out` argument return a fresh tensor
+            buf.copy_(res)
+        return self.ex.reduce(buf)
 
     def forward(self, e0_u: torch.Tensor, e0_i: torch.Tensor):
         """e0_u: this shard's user rows; e0_i: the replicated item table.  Returns (final_u shard, final_i)."""
@@ -125,7 +212,7 @@ class ShardedPropagation:
         u, i = e0_u, e0_i
         for k in range(self.K):
             last = k == self.K - 1
-            i_new = all_reduce_sum(self.b.item_rows(u, False), self.group)
+            i_new = self._item_exchange(u, False, tuple(e0_i.shape))
             u_new, acc_u = self.b.user_rows_acc(i if self.order == "jacobi" else i_new, False, acc_u,
                                                 s if last else 1.0, need_y=not last)
             acc_i = acc_i + i_new if k == 0 else acc_i.add_(i_new)
@@ -139,14 +226,14 @@ class ShardedPropagation:
         if self.order == "gs":
             bu = g_u
             for k in range(self.K):
-                bi = all_reduce_sum(self.b.item_rows(bu, True), self.group).add_(g_i_total)
+                bi = self._item_exchange(bu, True, tuple(g_i_total.shape)).add_(g_i_total)
                 _, bu = self.b.user_rows_acc(bi, True, g_u, s if k == self.K - 1 else 1.0, need_y=False)
             return bu, g_i_total.mul(s)
         bu, bi = g_u, g_i_total
         for k in range(self.K):
             last = k == self.K - 1
             _, nu = self.b.user_rows_acc(bi, True, g_u, s if last else 1.0, need_y=False)
-            ni = all_reduce_sum(self.b.item_rows(bu, True), self.group).add_(g_i_total)
+            ni = self._item_exchange(bu, True, tuple(g_i_total.shape)).add_(g_i_total)
             bu, bi = nu, (ni.mul_(s) if last else ni)
         return bu, bi
 
@@ -162,20 +249,22 @@ class ShardedTrainStep:
     triples (means over the GLOBAL batch), sharded backward, Adam on (local users, replicated items)."""
 
     def __init__(self, graph: CredGraph, user_emb: torch.Tensor, item_emb: torch.Tensor, num_layers, order,
-                 lr=1e-3, reg_weight=1e-4, mix_pop=0.7, gamma=0.75, max_tries=50, seed=42, group=None):
+                 lr=1e-3, reg_weight=1e-4, mix_pop=0.7, gamma=0.75, max_tries=50, seed=42, group=None,
+                 exchange: str = "p2p"):
         self.graph, self.group = graph, group
         self.eu = torch.nn.Parameter(user_emb.contiguous())
         self.ei = torch.nn.Parameter(item_emb.contiguous())
-        self.prop = ShardedPropagation(CudaBackend(graph), num_layers, order, group)
+        n_red = 2 * self.ei.numel() + 4
+        if exchange == "p2p" and _world(group) > 1:
+            self.ex = P2PExchange(n_red, self.ei.device, group)
+        else:
+            self.ex = CollectiveExchange(group)
+        self.prop = ShardedPropagation(CudaBackend(graph), num_layers, order, group, self.ex)
         self.sampler = TripleSampler(graph, mix_pop, gamma, max_tries, seed)
         self.reg = float(reg_weight)
         self.eu.grad, self.ei.grad = torch.zeros_like(self.eu), torch.zeros_like(self.ei)
         self.opt = FusedAdam(self.eu, self.ei, lr=lr)
         self.g_u = torch.empty_like(self.eu)
-        n = self.ei.numel()
-        self.red = torch.empty(2 * n + 4, dtype=torch.float32, device=self.ei.device)   # [seed ; ego ; loss]
-        self.gi2 = self.red[: 2 * n].view(2, *self.ei.shape)
-        self.loss = self.red[2 * n: 2 * n + 1]
         self.ego_u = torch.empty_like(self.eu)
         self.tick = torch.zeros(1, dtype=torch.int64, device=self.ei.device)
         self._bufs = {}
@@ -187,26 +276,32 @@ class ShardedTrainStep:
         B = users_local.numel()
         B_total = int(batch_total) if batch_total is not None else B * _world(self.group)
         if B not in self._bufs:
-            b = bpr_buffers(g, B, dev)
-            self._bufs[B] = (torch.empty(3 * B, dtype=torch.int64, device=dev), (self.loss,) + b[1:])
+            self._bufs[B] = (torch.empty(3 * B, dtype=torch.int64, device=dev), bpr_buffers(g, B, dev))
         plan, bufs = self._bufs[B]
         with torch.cuda.device(dev):
             check(lib().cgx_tick(ptr(self.tick), stream_ptr(dev)))
         pos, neg = self.sampler.sample(users_local, offset=0, offset_dev=self.tick)
         bpr_plan(g, users_local, pos, neg, plan)
         f_u, f_i = self.prop.forward(self.eu.data, self.ei.data)
+        n = self.ei.numel()
+        red = self.ex.partial_buffer((2 * n + 4,), dev)        # [item seed ; item L2 gradient ; loss]
+        gi2 = red[: 2 * n].view(2, *self.ei.shape)
         self.g_u.zero_()
-        self.red.zero_()
+        red.zero_()
         self.ego_u.zero_()
+        bufs = (red[2 * n: 2 * n + 1],) + tuple(bufs[1:])
         loss, _, _, ego_rows, ego_coef = bpr_fused(g, f_u, f_i, self.eu.data, self.ei.data, users_local, pos, neg,
-                                                   self.reg, 0.0, None, self.g_u, self.gi2[0], plan, bufs, B_total)
-        apply_ego(g, ego_rows, ego_coef, self.eu.data, self.ei.data, self.ego_u, self.gi2[1])
-        all_reduce_sum(self.red, self.group)      # item seed, item L2 gradient and the loss in ONE collective
-        d_u, d_i = self.prop.backward(self.g_u, self.gi2[0])
+                                                   self.reg, 0.0, None, self.g_u, gi2[0], plan, bufs, B_total)
+        apply_ego(g, ego_rows, ego_coef, self.eu.data, self.ei.data, self.ego_u, gi2[1])
+        # item seed, item L2 gradient and the loss in ONE exchange; cloned because the exchange's output region is
+        # recycled two exchanges later while the seed is needed by every backward layer
+        red = self.ex.reduce(red).clone()
+        gi2 = red[: 2 * n].view(2, *self.ei.shape)
+        d_u, d_i = self.prop.backward(self.g_u, gi2[0])
         self.eu.grad.copy_(d_u.add_(self.ego_u))
-        self.ei.grad.copy_(d_i.add_(self.gi2[1]))
+        self.ei.grad.copy_(d_i.add_(gi2[1]))
         self.opt.step()
-        return self.loss
+        return red[2 * n: 2 * n + 1]
 
     # NOTE: capturing this step (kernels + NCCL all-reduces) as one CUDA graph was tried and HUNG on the
     # 2-GPU box (torch 2.11 / NCCL 2.28.9, capture_error_mode="thread_local"); the sharded step therefore
@@ -230,7 +325,8 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
     item_emb = torch.nn.init.xavier_uniform_(torch.empty(I, d)).to(dev)          # identical on every rank
     torch.manual_seed(1000 + rank)
     user_emb = torch.nn.init.xavier_uniform_(torch.empty(U, d)).to(dev)
-    step = ShardedTrainStep(gr, user_emb, item_emb, K, shp["order"], mix_pop=None if shp["variant"] == "cu" else 0.7)
+    step = ShardedTrainStep(gr, user_emb, item_emb, K, shp["order"], mix_pop=None if shp["variant"] == "cu" else 0.7,
+                            exchange=__import__("os").environ.get("CGX_EXCHANGE", "p2p"))
     train_users = torch.nonzero(gr.deg_u > 0).reshape(-1).cpu().numpy()
     np.random.default_rng(42 + rank).shuffle(train_users)
     nb = len(train_users) // args.batch
@@ -286,6 +382,7 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
                     "h2d_bytes_per_step": int(host_batches[0].nbytes) * world, "d2h_bytes_per_step": 4 * world},
             "gpu_launches": int(launches), "loss": loss_host,
             "collectives_per_step": 2 * K + 1, "cuda_graph": graphed,
+            "exchange": type(step.ex).__name__,
         }))
     dist.barrier()
     dist.destroy_process_group()

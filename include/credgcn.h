@@ -246,6 +246,24 @@ int cgx_adam_step(float* p0, const float* g0, float* m0, float* v0, int64_t n0,
                   const uint64_t* step_dev, int64_t step_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Multi-GPU item-table exchange over NVLink peer memory (user-sharded propagation; the
+ * reference is single-device).  One communication buffer per rank: cgx_comm_alloc (cudaMalloc, zeroed),
+ * cgx_comm_ipc_handle -> 64-byte cudaIpcMemHandle_t to hand to the peers, cgx_comm_ipc_open on their
+ * side.  cgx_comm_allreduce sums n_floats float32 at byte offset in_off of every rank's buffer, in rank
+ * order (deterministic), into byte offset out_off of every rank's buffer: a two-shot pull kernel with
+ * system-scope flag barriers at flag_off (>= 4 * (2 * world + 1) bytes, zero before first use).
+ * peer_bases: host array of `world` device pointers (own buffer at index rank).  epoch: 1, 2, 3, ... the
+ * same on all ranks; consecutive epochs must alternate between two in/out regions.
+ * ------------------------------------------------------------------------------------------ */
+int cgx_comm_alloc(size_t bytes, void** base_out);
+int cgx_comm_free(void* base);
+int cgx_comm_ipc_handle(void* base, void* handle_out_64);
+int cgx_comm_ipc_open(const void* handle_64, void** peer_base_out);
+int cgx_comm_ipc_close(void* peer_base);
+int cgx_comm_allreduce(int rank, int world, void* const* peer_bases, size_t in_off, size_t out_off,
+                       size_t flag_off, int64_t n_floats, uint32_t epoch, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Full-rank evaluation.  Replaces the per-user loop of evaluate_full_ranking (V2:691-704):
  * scores of `users` against every item, train items forced to -1e9, best K by
  * (score desc, item id asc).  out_ids int32[n, K], out_scores float[n, K].

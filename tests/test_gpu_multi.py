@@ -23,8 +23,8 @@ def _worker(rank, world, port, out):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         from credgcn import graph, model, synth
-        from credgcn.sharded import (CudaBackend, ShardedPropagation, all_reduce_sum, build_local_graph,
-                                     partition_users, shard_edges)
+        from credgcn.sharded import (CollectiveExchange, CudaBackend, P2PExchange, ShardedPropagation,
+                                     all_reduce_sum, build_local_graph, partition_users, shard_edges)
         sg = synth.make_graph("C1", duplicate_edges=100)
         U, I, d, K = sg.num_users, sg.num_items, 64, 3
         deg_u = np.bincount(sg.train_edges[0], minlength=U)
@@ -36,22 +36,28 @@ def _worker(rank, world, port, out):
         eu = torch.nn.init.xavier_uniform_(torch.empty(U, d))
         ei = torch.nn.init.xavier_uniform_(torch.empty(I, d))
         res = {}
+        p2p = P2PExchange(2 * I * d + 4, dev)         # NVLink peer-memory exchange (csrc/comm.cu)
         for variant, order in (("v2", "gs"), ("cu", "jacobi"), ("da", "gs")):
-            gl = build_local_graph(shard_edges(sg.train_edges, bounds, rank), hi - lo, I, sg.cred[lo:hi], variant, dev)
-            prop = ShardedPropagation(CudaBackend(gl), K, order)
+          gl = build_local_graph(shard_edges(sg.train_edges, bounds, rank), hi - lo, I, sg.cred[lo:hi], variant, dev)
+          outs = {}
+          for ex_name, ex in (("nccl", CollectiveExchange()), ("p2p", p2p)):
+            prop = ShardedPropagation(CudaBackend(gl), K, order, exchange=ex)
             eu_l, ei_d = eu[lo:hi].to(dev).contiguous(), ei.to(dev)
             f_u, f_i = prop.forward(eu_l, ei_d)
             g_u = torch.zeros_like(eu_l)
-            gi2 = torch.zeros(2, I, d, device=dev)
+            gi2 = ex.partial_buffer((2, I, d), dev).zero_()
             ego_u = torch.zeros_like(eu_l)
             loss, _, _, ego_rows, ego_coef = model.bpr_fused(gl, f_u, f_i, eu_l, ei_d, users[mine] - lo, pos[mine],
                                                              neg[mine], 1e-4, 0.0, None, g_u, gi2[0],
                                                              batch_total=len(users))
             model.apply_ego(gl, ego_rows, ego_coef, eu_l, ei_d, ego_u, gi2[1])
-            all_reduce_sum(gi2)
+            gi2 = ex.reduce(gi2).clone()
             all_reduce_sum(loss)
             d_u, d_i = prop.backward(g_u, gi2[0])
             d_u, d_i = d_u + ego_u, d_i + gi2[1]
+            outs[ex_name] = (f_u.clone(), f_i.clone(), d_u.clone(), d_i.clone())
+          same = all(torch.equal(a, b) for a, b in zip(outs["nccl"], outs["p2p"]))
+          if True:
             if rank == 0:      # single-GPU truth on the whole graph
                 gr = graph.build_graph(sg.train_edges, U, I, sg.cred, variant, dev)
                 Net = model.CredLightGCN if variant == "cu" else model.LightGCN
@@ -66,7 +72,7 @@ def _worker(rank, world, port, out):
                     loss=abs(loss.item() - want.item()) / abs(want.item()),
                     f_u=rel(f_u, st.f_u[lo:hi]), f_i=rel(f_i, st.f_i),
                     d_u=rel(d_u, net.user_emb.weight.grad[lo:hi]), d_i=rel(d_i, net.item_emb.weight.grad),
-                    deg=int((gl.deg_i != gr.deg_i).sum().item()))
+                    deg=int((gl.deg_i != gr.deg_i).sum().item()), p2p_equals_nccl=bool(same))
         if rank == 0:
             out[0] = res
     finally:
@@ -84,4 +90,5 @@ def test_two_gpu_sharded_equals_single_gpu():
         res = dict(out)[0]
     for variant, e in res.items():
         assert e.pop("deg") == 0, variant
+        assert e.pop("p2p_equals_nccl"), variant          # two ranks: a + b in rank order == NCCL's sum, bit for bit
         assert max(e.values()) < 1e-4, (variant, e)

@@ -55,9 +55,10 @@ class OracleShardBackend(BackendBase):
         self.A = sp.csr_matrix((av, (ar, ac)), shape=(hi - lo, num_items), dtype=np.float32)
         self.C = sp.csr_matrix((cv, (cr, cc)), shape=(num_items, hi - lo), dtype=np.float32)
 
-    def item_rows(self, x_u, bwd=False):
+    def item_rows(self, x_u, bwd=False, out=None):
         m = self.A.T if bwd else self.C
-        return torch.from_numpy(np.asarray(m @ x_u.numpy(), dtype=np.float32))
+        res = torch.from_numpy(np.asarray(m @ x_u.numpy(), dtype=np.float32))
+        return res if out is None else out.copy_(res)
 
     def user_rows(self, x_i, bwd=False):
         m = self.C.T if bwd else self.A
