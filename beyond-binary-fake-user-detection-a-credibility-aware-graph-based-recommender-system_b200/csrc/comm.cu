@@ -16,11 +16,12 @@
 //          identical bits on every rank) and stores the reduced slice into every peer's out[parity];
 //       B. the last CTA to finish signals "my slice is delivered" to every peer and waits for theirs, so
 //          the kernel completes only when out[parity] is whole.
-//     Double buffering by parity makes the entry barrier sufficient against write-after-read hazards: a
-//     rank re-uses in/out[parity] two collectives later, and it cannot pass barrier A of the collective in
-//     between before every peer has finished reading/writing the previous use.
-//   * epochs are 1, 2, 3, ... and must advance identically on all ranks (the propagation schedule is
-//     deterministic).
+//     Barrier B also means nobody still reads a rank's `in` region when its kernel completes, and barrier A
+//     means nobody writes a rank's `out` region before that rank's earlier kernels (the consumers of the
+//     previous result) have finished: regions can be re-used immediately.  Two regions are kept only so that
+//     the result of the previous exchange stays readable (the Jacobi order needs it).
+//   * the epoch is a device-side counter (cgx_tick before every exchange) that advances identically on all
+//     ranks (the propagation schedule is deterministic), so a whole step can be replayed as a CUDA graph.
 #include <string.h>
 
 #include "common.cuh"
@@ -53,7 +54,8 @@ __device__ __forceinline__ float4 ld_peer(const float4* p) {   // written by ano
 // flag page layout (uint32): [0 .. R) barrier A slots, [R .. 2R) barrier B slots, [2R] CTA arrival counter
 __global__ void __launch_bounds__(P2P_THREADS) k_p2p_allreduce(P2PPeers peers, int rank, int world, size_t in_off,
                                                                size_t out_off, size_t flag_off, int64_t n4,
-                                                               uint32_t epoch) {
+                                                               const unsigned long long* __restrict__ epoch_dev) {
+  const uint32_t epoch = uint32_t(*epoch_dev);   // device-side counter: the launch is replayable in a CUDA graph
   uint32_t* my_flags = reinterpret_cast<uint32_t*>(peers.base[rank] + flag_off);
   // ---- barrier A: all partials complete ----
   if (blockIdx.x == 0 && threadIdx.x < world) {
@@ -68,13 +70,36 @@ __global__ void __launch_bounds__(P2P_THREADS) k_p2p_allreduce(P2PPeers peers, i
   const int64_t per = (n4 + world - 1) / world;
   const int64_t lo = int64_t(rank) * per;
   const int64_t hi = lo + per < n4 ? lo + per : n4;
-  for (int64_t i = lo + int64_t(blockIdx.x) * P2P_THREADS + threadIdx.x; i < hi; i += int64_t(gridDim.x) * P2P_THREADS) {
-    float4 s = ld_peer(reinterpret_cast<const float4*>(peers.base[0] + in_off) + i);
-    for (int p = 1; p < world; ++p) {
-      const float4 v = ld_peer(reinterpret_cast<const float4*>(peers.base[p] + in_off) + i);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  // P2P_UNROLL x world peer loads are issued before the first add: NVLink round trips (~2 us) overlap
+  constexpr int P2P_UNROLL = 4;
+  const int64_t stride = int64_t(gridDim.x) * P2P_THREADS;
+  for (int64_t i0 = lo + int64_t(blockIdx.x) * P2P_THREADS + threadIdx.x; i0 < hi; i0 += stride * P2P_UNROLL) {
+    float4 acc[P2P_UNROLL];
+#pragma unroll
+    for (int t = 0; t < P2P_UNROLL; ++t) {
+      const int64_t i = i0 + t * stride;
+      acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < hi) acc[t] = ld_peer(reinterpret_cast<const float4*>(peers.base[0] + in_off) + i);
     }
-    for (int p = 0; p < world; ++p) reinterpret_cast<float4*>(peers.base[p] + out_off)[i] = s;
+    for (int p = 1; p < world; ++p) {
+      float4 v[P2P_UNROLL];
+#pragma unroll
+      for (int t = 0; t < P2P_UNROLL; ++t) {
+        const int64_t i = i0 + t * stride;
+        v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < hi) v[t] = ld_peer(reinterpret_cast<const float4*>(peers.base[p] + in_off) + i);
+      }
+#pragma unroll
+      for (int t = 0; t < P2P_UNROLL; ++t) {
+        acc[t].x += v[t].x; acc[t].y += v[t].y; acc[t].z += v[t].z; acc[t].w += v[t].w;
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < P2P_UNROLL; ++t) {
+      const int64_t i = i0 + t * stride;
+      if (i < hi)
+        for (int p = 0; p < world; ++p) reinterpret_cast<float4*>(peers.base[p] + out_off)[i] = acc[t];
+    }
   }
   // ---- barrier B: every slice delivered ----
   __threadfence_system();
@@ -129,12 +154,12 @@ extern "C" int cgx_comm_ipc_close(void* peer_base) {
 }
 
 extern "C" int cgx_comm_allreduce(int rank, int world, void* const* peer_bases, size_t in_off, size_t out_off,
-                                  size_t flag_off, int64_t n_floats, uint32_t epoch, void* stream_) {
+                                  size_t flag_off, int64_t n_floats, const uint64_t* epoch_dev, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CGX_REQUIRE(world >= 1 && world <= P2P_MAX_RANKS && rank >= 0 && rank < world && peer_bases, CGX_ERR_ARG,
               "comm_allreduce: bad rank/world");
   CGX_REQUIRE(n_floats > 0 && n_floats % 4 == 0 && in_off % 16 == 0 && out_off % 16 == 0 && flag_off % 16 == 0 &&
-                  epoch > 0,
+                  epoch_dev != nullptr,
               CGX_ERR_ARG, "comm_allreduce: bad sizes/offsets");
   P2PPeers peers;
   for (int p = 0; p < world; ++p) {
@@ -144,10 +169,10 @@ extern "C" int cgx_comm_allreduce(int rank, int world, void* const* peer_bases, 
   const int64_t n4 = n_floats / 4;
   const int64_t per = ceil_div(n4, world);
   int64_t blocks = ceil_div(per, P2P_THREADS * 4);
-  if (blocks > 148 * 2) blocks = 148 * 2;
+  if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
   k_p2p_allreduce<<<(unsigned)blocks, P2P_THREADS, 0, stream>>>(peers, rank, world, in_off, out_off, flag_off, n4,
-                                                             epoch);
+                                                             reinterpret_cast<const unsigned long long*>(epoch_dev));
   CGX_LAUNCH_CHECK();
   return CGX_OK;
 }

@@ -113,7 +113,8 @@ class P2PExchange:
                     self.bases[p] = peer.value
         self.base = base
         self.bytes = torch.as_tensor(_RawCuda(base.value, total), device=self.device)
-        self.epoch = 0
+        self.epoch_dev = torch.zeros(1, dtype=torch.int64, device=self.device)   # exchanges done so far
+        self.slot = 0                                                          # region of the next exchange
         if self.world > 1:
             dist.barrier(group=group)          # every rank has mapped every buffer before the first collective
 
@@ -121,21 +122,25 @@ class P2PExchange:
         n = int(np.prod(shape))
         return self.bytes[offset: offset + 4 * n].view(torch.float32).view(shape)
 
+    def begin_step(self):
+        """Restart the region alternation: every step then uses the same addresses (CUDA-graph replay)."""
+        self.slot = 0
+
     def partial_buffer(self, shape, device=None):
-        """The `in` region of the NEXT collective: fill it, then call reduce() on it."""
+        """The `in` region of the NEXT exchange: fill it, then call reduce() on it."""
         if 4 * int(np.prod(shape)) > self.region:
             raise _lib.CgxError("P2PExchange: payload larger than the communication regions")
-        return self._view(((self.epoch + 1) & 1) * self.region, shape)
+        return self._view(self.slot * self.region, shape)
 
     def reduce(self, buf):
-        self.epoch += 1
-        par = self.epoch & 1
-        n = buf.numel()
-        n_pad = (n + 3) // 4 * 4
+        par = self.slot
+        self.slot ^= 1
+        n_pad = (buf.numel() + 3) // 4 * 4
         with torch.cuda.device(self.device):
+            st = stream_ptr(self.device)
+            check(lib().cgx_tick(ptr(self.epoch_dev), st))
             check(lib().cgx_comm_allreduce(self.rank, self.world, self.bases, par * self.region,
-                                           (2 + par) * self.region, self.flag_off, n_pad, self.epoch,
-                                           stream_ptr(self.device)))
+                                           (2 + par) * self.region, self.flag_off, n_pad, ptr(self.epoch_dev), st))
         return self._view((2 + par) * self.region, tuple(buf.shape))
 
 
@@ -268,6 +273,7 @@ class ShardedTrainStep:
         self.ego_u = torch.empty_like(self.eu)
         self.tick = torch.zeros(1, dtype=torch.int64, device=self.ei.device)
         self._bufs = {}
+        self._graph = None
 
     @torch.no_grad()
     def __call__(self, users_local: torch.Tensor, batch_total: int | None = None):
@@ -278,6 +284,8 @@ class ShardedTrainStep:
         if B not in self._bufs:
             self._bufs[B] = (torch.empty(3 * B, dtype=torch.int64, device=dev), bpr_buffers(g, B, dev))
         plan, bufs = self._bufs[B]
+        if hasattr(self.ex, "begin_step"):
+            self.ex.begin_step()
         with torch.cuda.device(dev):
             check(lib().cgx_tick(ptr(self.tick), stream_ptr(dev)))
         pos, neg = self.sampler.sample(users_local, offset=0, offset_dev=self.tick)
@@ -303,11 +311,36 @@ class ShardedTrainStep:
         self.opt.step()
         return red[2 * n: 2 * n + 1]
 
-    # NOTE: capturing this step (kernels + NCCL all-reduces) as one CUDA graph was tried and HUNG on the
-    # 2-GPU box (torch 2.11 / NCCL 2.28.9, capture_error_mode="thread_local"); the sharded step therefore
-    # launches eagerly.  Left for a later round together with a fused SpMM + reduce over NVLink peer memory.
+    def capture(self, batch: int):
+        """Record the whole sharded step as one CUDA graph.  Only with the peer-memory exchange: every launch
+        of the step is then a kernel of this library or a torch elementwise op, and the exchange epochs are
+        device-side counters.  (Capturing the NCCL variant hung on this stack: torch 2.11 / NCCL 2.28.9.)"""
+        if not isinstance(self.ex, P2PExchange):
+            raise _lib.CgxError("ShardedTrainStep.capture needs exchange='p2p'")
+        dev = self.eu.device
+        self._g_users = torch.zeros(batch, dtype=torch.int64, device=dev)
+        state = (self.eu.data, self.ei.data, self.opt.m[0], self.opt.m[1], self.opt.v[0], self.opt.v[1],
+                 self.opt.step_dev, self.tick)
+        warm = torch.cuda.Stream(device=dev)
+        warm.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(warm):
+            keep = [t.clone() for t in state]
+            for _ in range(2):                     # every rank runs the same two steps: exchanges stay matched
+                self(self._g_users)
+            for dst, src in zip(state, keep):
+                dst.copy_(src)
+        torch.cuda.current_stream(dev).wait_stream(warm)
+        torch.cuda.synchronize(dev)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._g_loss = self(self._g_users)
+        return self
 
     def step(self, users):
+        if self._graph is not None and users.numel() == self._g_users.numel():
+            self._g_users.copy_(users, non_blocking=True)
+            self._graph.replay()
+            return self._g_loss
         return self(torch.as_tensor(users).to(self.eu.device, non_blocking=True))
 
 
@@ -335,7 +368,9 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
     pinned = [torch.from_numpy(b).pin_memory() for b in host_batches]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    graphed = False
+    graphed = isinstance(step.ex, P2PExchange) and __import__("os").environ.get("CGX_SHARDED_GRAPH", "1") == "1"
+    if graphed:
+        step.capture(args.batch)
     for s in range(max(args.warmup, 3)):
         step.step(dev_batches[s % len(dev_batches)])
     torch.cuda.synchronize()

@@ -252,8 +252,8 @@ int cgx_adam_step(float* p0, const float* g0, float* m0, float* v0, int64_t n0,
  * side.  cgx_comm_allreduce sums n_floats float32 at byte offset in_off of every rank's buffer, in rank
  * order (deterministic), into byte offset out_off of every rank's buffer: a two-shot pull kernel with
  * system-scope flag barriers at flag_off (>= 4 * (2 * world + 1) bytes, zero before first use).
- * peer_bases: host array of `world` device pointers (own buffer at index rank).  epoch: 1, 2, 3, ... the
- * same on all ranks; consecutive epochs must alternate between two in/out regions.
+ * peer_bases: host array of `world` device pointers (own buffer at index rank).  epoch_dev: device counter
+ * holding 1, 2, 3, ... for successive exchanges (cgx_tick it before each call), the same on all ranks.
  * ------------------------------------------------------------------------------------------ */
 int cgx_comm_alloc(size_t bytes, void** base_out);
 int cgx_comm_free(void* base);
@@ -261,7 +261,7 @@ int cgx_comm_ipc_handle(void* base, void* handle_out_64);
 int cgx_comm_ipc_open(const void* handle_64, void** peer_base_out);
 int cgx_comm_ipc_close(void* peer_base);
 int cgx_comm_allreduce(int rank, int world, void* const* peer_bases, size_t in_off, size_t out_off,
-                       size_t flag_off, int64_t n_floats, uint32_t epoch, void* stream);
+                       size_t flag_off, int64_t n_floats, const uint64_t* epoch_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Full-rank evaluation.  Replaces the per-user loop of evaluate_full_ranking (V2:691-704):

@@ -1,0 +1,24 @@
+"""Item-table exchange alone: P2P kernel vs NCCL all-reduce, 2+ GPUs (torchrun)."""
+import os, sys, pathlib, json
+sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[1]))
+import torch, torch.distributed as dist
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local); dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+from credgcn.sharded import P2PExchange, CollectiveExchange
+out = {}
+for n in (38048 * 64, 2 * 38048 * 64 + 4, 2_000_000 * 128):
+    p2p = P2PExchange(n, dev)
+    for name, ex in (("p2p", p2p), ("nccl", CollectiveExchange())):
+        for _ in range(5):
+            b = ex.partial_buffer((n,), dev); b.fill_(1.0); r = ex.reduce(b)
+        torch.cuda.synchronize(); dist.barrier()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20):
+            b = ex.partial_buffer((n,), dev); r = ex.reduce(b)
+        e.record(); torch.cuda.synchronize()
+        out[f"{name}_{n*4/1e6:.1f}MB_us"] = round(a.elapsed_time(e) * 50, 1)
+    del p2p
+if rank == 0: print(json.dumps({"world": world, **out}))
+dist.barrier(); dist.destroy_process_group()
