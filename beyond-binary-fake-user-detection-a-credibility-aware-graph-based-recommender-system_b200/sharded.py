@@ -260,9 +260,20 @@ class ShardedTrainStep:
         self.eu = torch.nn.Parameter(user_emb.contiguous())
         self.ei = torch.nn.Parameter(item_emb.contiguous())
         n_red = 2 * self.ei.numel() + 4
+        self.ex = None
         if exchange == "p2p" and _world(group) > 1:
-            self.ex = P2PExchange(n_red, self.ei.device, group)
-        else:
+            # peer mapping can be unavailable (no NVLink/IPC between the ranks): all ranks must then agree to
+            # use the collective exchange, so the outcome itself is reduced
+            ok = torch.ones(1, device=self.ei.device)
+            try:
+                self.ex = P2PExchange(n_red, self.ei.device, group)
+            except Exception as e:      # noqa: BLE001 -- any failure means "no peer path"
+                ok.zero_()
+                self._p2p_error = f"{type(e).__name__}: {e}"
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if ok.item() == 0:
+                self.ex = None
+        if self.ex is None:
             self.ex = CollectiveExchange(group)
         self.prop = ShardedPropagation(CudaBackend(graph), num_layers, order, group, self.ex)
         self.sampler = TripleSampler(graph, mix_pop, gamma, max_tries, seed)
@@ -344,6 +355,76 @@ class ShardedTrainStep:
         return self(torch.as_tensor(users).to(self.eu.device, non_blocking=True))
 
 
+@torch.no_grad()
+def evaluate_full_ranking_sharded(f_u_local, f_i, graph: CredGraph, test_edges_local, num_items, Ks=(10, 20),
+                                  item_pop=None, total_train=0, cred_local=None, group_pct=0.20, group=None,
+                                  precision="fp32"):
+    """User-sharded full-rank evaluation (Version-2/lighgcn_cu_pop.py:653-752): every rank ranks ITS users
+    against the replicated item table -- no embedding traffic -- and only per-user metric vectors of the evaluated
+    users (a few floats each) are gathered to form the global means, coverage set and credibility groups.
+    `graph` is the rank's local CredGraph (train mask = its duplicate-keeping user rows); `test_edges_local`
+    holds the rank's users with shard-local ids."""
+    from . import evaluate as ev
+    from .graph import user_csr_device
+    dev = f_u_local.device
+    U_loc = graph.num_users
+    ip, ix = user_csr_device(test_edges_local, U_loc, num_items, dev)
+    te = (ip.cpu().numpy(), ix.cpu().numpy().astype(np.int64))
+    users = np.flatnonzero(np.diff(te[0]) > 0).astype(np.int64)
+    K = max(Ks)
+    if users.size:
+        ids, _ = ev.topk_device(f_u_local, f_i, torch.from_numpy(users), (graph.samp_indptr, graph.samp_idx), K, precision)
+        ranked = ids.cpu().numpy()
+    else:
+        ranked = np.zeros((0, K), np.int32)
+    hits = ev._hits_matrix(ranked, users, te, num_items) if users.size else np.zeros((0, K), bool)
+    n_gt = np.diff(te[0])[users]
+    world = _world(group)
+    rank = dist.get_rank(group) if world > 1 else 0
+    payload = dict(hits=hits, n_gt=n_gt, ranked=ranked, cred=None if cred_local is None else np.asarray(cred_local)[users],
+                   rank=np.full(users.size, rank))
+    parts = [payload]
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, payload, group=group)
+    hits = np.concatenate([p["hits"] for p in parts])
+    n_gt = np.concatenate([p["n_gt"] for p in parts])
+    ranked = np.concatenate([p["ranked"] for p in parts])
+    n = hits.shape[0]
+    if n == 0:
+        raise RuntimeError("No users with test interactions. Check your split or threshold.")
+    disc = 1.0 / np.log2(np.arange(K) + 2.0)
+    idcg_tab = np.concatenate([[0.0], np.cumsum(disc)])
+    extra = item_pop is not None and cred_local is not None
+    if extra:
+        cred_all = np.concatenate([p["cred"] for p in parts])
+        hi, lo = ev.make_cred_groups(np.arange(n), cred_all, group_pct)
+        in_hi, in_lo = np.isin(np.arange(n), hi), np.isin(np.arange(n), lo)
+    out = {}
+    for k in Ks:
+        h = hits[:, :k]
+        nh = h.sum(1)
+        recall = nh / np.maximum(n_gt, 1)
+        idcg = idcg_tab[np.minimum(n_gt, k)]
+        ndcg = np.where(idcg > 0, (h * disc[:k]).sum(1) / np.where(idcg > 0, idcg, 1.0), 0.0)
+        res = {"precision": float((nh / k).mean()), "recall": float(recall.mean()), "ndcg": float(ndcg.mean())}
+        if extra:
+            top = ranked[:, :k].astype(np.int64)
+            pcount = item_pop[top].astype(np.float64)
+            res.update({
+                "item_coverage": np.unique(top).size / max(num_items, 1),
+                "avg_log_popularity": float(np.log(pcount + 1.0).mean(1).mean()),
+                "avg_self_information": float((-np.log2((pcount + 1.0) / (total_train + num_items))).mean(1).mean()),
+                "cred_utility": float(cred_all.astype(np.float64).mean()),
+                "high_cred_recall": float(recall[in_hi].sum() / max(int(in_hi.sum()), 1)),
+                "low_cred_recall": float(recall[in_lo].sum() / max(int(in_lo.sum()), 1)),
+                "high_users": int(in_hi.sum()), "low_users": int(in_lo.sum()),
+            })
+        res.update({"users_eval": n, "mode": "full"})
+        out[k] = res
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 # bench.py --gpus N (N > 1): weak scaling, one C2-shaped user shard per rank
 # ------------------------------------------------------------------------------------------
@@ -370,7 +451,16 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
 
     graphed = isinstance(step.ex, P2PExchange) and __import__("os").environ.get("CGX_SHARDED_GRAPH", "1") == "1"
     if graphed:
-        step.capture(args.batch)
+        try:
+            step.capture(args.batch)
+        except Exception as e:          # noqa: BLE001
+            graphed, step._graph = False, None
+            print(f"[bench] rank {rank}: CUDA-graph capture failed ({type(e).__name__}: {e}); eager launches",
+                  file=__import__("sys").stderr)
+        flag = torch.tensor([1.0 if graphed else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if flag.item() == 0:            # every rank must take the same path
+            graphed, step._graph = False, None
     for s in range(max(args.warmup, 3)):
         step.step(dev_batches[s % len(dev_batches)])
     torch.cuda.synchronize()

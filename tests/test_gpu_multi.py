@@ -12,7 +12,9 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 ROOT = pathlib.Path(__file__).resolve().parents[1]
-sys.path.insert(0, str(ROOT))
+for _p in (ROOT, ROOT / "oracle"):
+    if str(_p) not in sys.path:
+        sys.path.insert(0, str(_p))
 pytestmark = pytest.mark.gpu
 
 
@@ -73,7 +75,30 @@ def _worker(rank, world, port, out):
                     f_u=rel(f_u, st.f_u[lo:hi]), f_i=rel(f_i, st.f_i),
                     d_u=rel(d_u, net.user_emb.weight.grad[lo:hi]), d_i=rel(d_i, net.item_emb.weight.grad),
                     deg=int((gl.deg_i != gr.deg_i).sum().item()), p2p_equals_nccl=bool(same))
+        # user-sharded full-rank evaluation == single-GPU evaluation of the whole graph
+        from credgcn import evaluate, config
+        from credgcn.sharded import evaluate_full_ranking_sharded
+        gl = build_local_graph(shard_edges(sg.train_edges, bounds, rank), hi - lo, I, sg.cred[lo:hi], "v2", dev)
+        torch.manual_seed(3)
+        fu = torch.randn(U, d, device=dev) * 0.2
+        fi = torch.randn(I, d, device=dev) * 0.2
+        item_pop, total = evaluate.compute_item_popularity(sg.train_edges, I)
+        got = evaluate_full_ranking_sharded(fu[lo:hi].contiguous(), fi, gl, shard_edges(sg.test_edges, bounds, rank), I,
+                                            (10, 20), item_pop, total, sg.cred[lo:hi])
         if rank == 0:
+            class _M:                      # minimal stand-in with the reference's accessor
+                def get_user_item_emb(self):
+                    return fu, fi
+            import credgcn_oracle as orc
+            want = evaluate.evaluate_full_ranking(_M(), orc.edges_to_user_csr(sg.train_edges, U),
+                                                  orc.edges_to_user_csr(sg.test_edges, U), I, dev, item_pop, total, sg.cred)
+            ev_err = 0.0
+            for kk in (10, 20):
+                for key in ("precision", "recall", "ndcg", "item_coverage", "avg_log_popularity",
+                            "avg_self_information", "cred_utility"):
+                    ev_err = max(ev_err, abs(got[kk][key] - want[kk][key]) / max(abs(want[kk][key]), 1e-12))
+                assert got[kk]["users_eval"] == want[kk]["users_eval"]
+            res["eval"] = dict(err=ev_err, deg=0, p2p_equals_nccl=True)
             out[0] = res
     finally:
         dist.destroy_process_group()
