@@ -57,6 +57,9 @@ class CFG:
     # which script's behaviour train_lightgcn() follows: "cu" | "v2" | "da" | "msg" | "me"
     variant: str = "v2"
     score_precision: str = "fp32"  # full-rank eval: "fp32" | "bf16x3" | "bf16"
+    # sampled eval: False = candidates from the reference's own PCG64 stream on the host (identical lists);
+    # True = candidates drawn on device (same protocol, Philox streams; no per-user Python loop)
+    sampled_eval_on_device: bool = False
 
 
 cfg = CFG()

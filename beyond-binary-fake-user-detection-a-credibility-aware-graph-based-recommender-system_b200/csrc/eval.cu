@@ -219,6 +219,24 @@ __global__ void __launch_bounds__(256) k_score_cands(const int64_t* __restrict__
   if (lane == 0) scores[p] = s;
 }
 
+// one warp per user: stable descending sort of C candidate scores by rank counting (np.argsort(-scores, stable))
+__global__ void __launch_bounds__(256) k_rank_cands(const float* __restrict__ scores, const int64_t* __restrict__ cand,
+                                                    int64_t n_users, int32_t C, int64_t* __restrict__ ranked) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= n_users) return;
+  const float* s = scores + r * C;
+  for (int i = lane; i < C; i += 32) {
+    const float si = s[i];
+    int rank = 0;
+    for (int j = 0; j < C; ++j) {
+      const float sj = __ldg(s + j);
+      rank += (sj > si || (sj == si && j < i)) ? 1 : 0;
+    }
+    ranked[r * C + rank] = cand[r * C + i];
+  }
+}
+
 int eval_topk_tc(const int64_t* users, int64_t n_users, const float* f_u, const float* f_i, int32_t I, int32_t d,
                  const int64_t* tr_indptr, const int32_t* tr_idx, int32_t K, int precision, int32_t* out_ids,
                  float* out_scores, void* workspace, size_t workspace_bytes, cudaStream_t stream);
@@ -283,6 +301,15 @@ extern "C" int cgx_score_candidates(const int64_t* users, const int64_t* cand, i
       return CGX_ERR_UNSUPPORTED;
   }
 #undef CGX_SC
+  CGX_LAUNCH_CHECK();
+  return CGX_OK;
+}
+
+extern "C" int cgx_rank_candidates(const float* scores, const int64_t* cand, int64_t n_users, int32_t n_cand,
+                                   int64_t* ranked, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CGX_REQUIRE(scores && cand && ranked && n_users > 0 && n_cand > 0, CGX_ERR_ARG, "rank_candidates: bad argument");
+  k_rank_cands<<<(unsigned)ceil_div(n_users, 8), 256, 0, stream>>>(scores, cand, n_users, n_cand, ranked);
   CGX_LAUNCH_CHECK();
   return CGX_OK;
 }

@@ -96,6 +96,37 @@ __global__ void __launch_bounds__(SM_THREADS) k_sample(const int64_t* __restrict
   neg_out[t] = int64_t(item);
 }
 
+// ---- sampled-evaluation candidates: 1 test positive + n_neg negatives outside test U train ----------
+// (lightgcn_cu.py:505-521; one thread per (user, slot), independent Philox streams)
+__global__ void __launch_bounds__(SM_THREADS) k_eval_candidates(const int64_t* __restrict__ users, int64_t n_users,
+                                                                const int64_t* __restrict__ tr_indptr,
+                                                                const int32_t* __restrict__ tr_idx,
+                                                                const int64_t* __restrict__ te_indptr,
+                                                                const int32_t* __restrict__ te_idx, int32_t I,
+                                                                int32_t n_cand, uint64_t seed,
+                                                                int64_t* __restrict__ cand) {
+  const int64_t t = int64_t(blockIdx.x) * SM_THREADS + threadIdx.x;
+  if (t >= n_users * n_cand) return;
+  const int64_t r = t / n_cand;
+  const int slot = int(t - r * n_cand);
+  const int64_t u = users[r];
+  const Philox rng{uint32_t(seed), uint32_t(seed >> 32)};
+  const int64_t te_lo = __ldg(te_indptr + u), te_hi = __ldg(te_indptr + u + 1);
+  if (slot == 0) {   // the positive: uniform over the user's test items (callers pass users with >= 1 test item)
+    const uint4 a = rng(uint32_t(r), 0u, uint32_t(r >> 32), 0x5eedu);
+    cand[t] = te_hi > te_lo ? int64_t(__ldg(te_idx + te_lo + int64_t(bounded(u64_of(a.x, a.y), uint64_t(te_hi - te_lo))))) : -1;
+    return;
+  }
+  const int64_t tr_lo = __ldg(tr_indptr + u), tr_hi = __ldg(tr_indptr + u + 1);
+  int32_t item = 0;
+  for (uint32_t tries = 0; tries < (1u << 20); ++tries) {
+    const uint4 a = rng(uint32_t(r), uint32_t(slot), uint32_t(r >> 32) ^ (tries << 8), 0x5eedu);
+    item = int32_t(bounded(u64_of(a.x, a.y), uint64_t(I)));
+    if (!row_has(te_idx, te_lo, te_hi, item) && !row_has(tr_idx, tr_lo, tr_hi, item)) break;
+  }
+  cand[t] = int64_t(item);
+}
+
 // ---- table build -------------------------------------------------------------------------------
 __global__ void k_deg_keys(const int32_t* __restrict__ deg, int32_t I, int bits_i, uint64_t* __restrict__ keys) {
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -217,6 +248,20 @@ extern "C" int cgx_sample_triples(const int64_t* users, int64_t batch, const int
   k_sample<<<(unsigned)ceil_div(batch, SM_THREADS), SM_THREADS, 0, stream>>>(
       users, batch, samp_indptr, samp_idx, num_items, tb, mix_pop, max_tries, seed, offset,
       reinterpret_cast<const unsigned long long*>(offset_dev), pos_out, neg_out);
+  CGX_LAUNCH_CHECK();
+  return CGX_OK;
+}
+
+extern "C" int cgx_eval_candidates(const int64_t* users, int64_t n_users, const int64_t* train_indptr,
+                                   const int32_t* train_idx, const int64_t* test_indptr, const int32_t* test_idx,
+                                   int32_t num_items, int32_t n_neg, uint64_t seed, int64_t* cand, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CGX_REQUIRE(users && train_indptr && train_idx && test_indptr && test_idx && cand && n_users > 0 && num_items > 0 &&
+                  n_neg >= 0,
+              CGX_ERR_ARG, "eval_candidates: bad argument");
+  const int64_t n = n_users * (1 + n_neg);
+  k_eval_candidates<<<(unsigned)ceil_div(n, SM_THREADS), SM_THREADS, 0, stream>>>(
+      users, n_users, train_indptr, train_idx, test_indptr, test_idx, num_items, 1 + n_neg, seed, cand);
   CGX_LAUNCH_CHECK();
   return CGX_OK;
 }

@@ -188,24 +188,55 @@ def sampled_candidates(train_csr, test_csr, num_items: int, n_neg: int, seed: in
     return users, cands
 
 
+def sampled_candidates_device(train_csr_dev, test_csr_dev, users, num_items: int, n_neg: int, seed: int):
+    """Candidate lists of the sampled protocol drawn by one kernel (cgx_eval_candidates)."""
+    dev = train_csr_dev[0].device
+    users = torch.as_tensor(users, device=dev).to(torch.int64).contiguous()
+    cand = torch.empty(users.numel(), 1 + n_neg, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().cgx_eval_candidates(ptr(users), users.numel(), ptr(train_csr_dev[0]), ptr(train_csr_dev[1]),
+                                        ptr(test_csr_dev[0]), ptr(test_csr_dev[1]), num_items, n_neg,
+                                        (int(seed) + 999) & 0xFFFFFFFFFFFFFFFF, ptr(cand), stream_ptr(dev)))
+    return cand
+
+
+def rank_candidates_device(scores: torch.Tensor, cands: torch.Tensor) -> torch.Tensor:
+    ranked = torch.empty_like(cands)
+    with torch.cuda.device(scores.device):
+        check(lib().cgx_rank_candidates(ptr(scores.contiguous()), ptr(cands.contiguous()), cands.shape[0],
+                                        cands.shape[1], ptr(ranked), stream_ptr(scores.device)))
+    return ranked
+
+
 @torch.no_grad()
 def evaluate_sampled(model, train_csr, test_csr, num_items: int, device=None, item_pop=None,
-                     total_train_interactions: int = 0, cred_np=None, candidates=None):
+                     total_train_interactions: int = 0, cred_np=None, candidates=None, on_device=None):
     """1 positive + cfg.sampled_negatives negatives per test user, ranked by score.
-    `candidates=(users, cands)` injects a candidate list (parity tests)."""
+    `candidates=(users, cands)` injects a candidate list (parity tests); `on_device` (default
+    cfg.sampled_eval_on_device) draws the candidates with the device kernel instead of the host PCG64 loop."""
     cfg = config.cfg
     f_u, f_i = _final_tables(model)
     tr = (np.asarray(train_csr[0]), np.asarray(train_csr[1]))
     te = (np.asarray(test_csr[0]), np.asarray(test_csr[1]))
-    if candidates is None:
-        users, cands = sampled_candidates(tr, te, num_items, cfg.sampled_negatives, cfg.seed)
-    else:
+    on_device = cfg.sampled_eval_on_device if on_device is None else on_device
+    if candidates is not None:
         users, cands = candidates
+        cands_dev = torch.from_numpy(np.ascontiguousarray(cands)).to(f_u.device)
+    elif on_device:
+        users = np.flatnonzero(np.diff(te[0]) > 0).astype(np.int64)
+        if len(users) == 0:
+            raise RuntimeError("No users with test interactions.")
+        cands_dev = sampled_candidates_device(_device_csr(tr, f_u.device), _device_csr(te, f_u.device), users,
+                                              num_items, cfg.sampled_negatives, cfg.seed)
+    else:
+        users, cands = sampled_candidates(tr, te, num_items, cfg.sampled_negatives, cfg.seed)
+        cands_dev = torch.from_numpy(cands).to(f_u.device) if len(users) else None
     if len(users) == 0:
         raise RuntimeError("No users with test interactions.")
-    scores = score_candidates_device(f_u, f_i, torch.from_numpy(users), torch.from_numpy(cands)).cpu().numpy()
-    order = np.argsort(-scores, axis=1, kind="stable")
-    ranked = np.take_along_axis(cands, order, axis=1)
+    scores = score_candidates_device(f_u, f_i, torch.from_numpy(np.asarray(users)), cands_dev)
+    ranked_dev = rank_candidates_device(scores, cands_dev)
+    ranked = ranked_dev.cpu().numpy()
+    cands = cands_dev.cpu().numpy()
     return metrics_from_ranked(ranked, users, te, num_items, cfg.Ks, "sampled(1pos+neg)", item_pop,
                                total_train_interactions, cred_np, cfg.cred_group_pct, gt_single=cands[:, 0],
                                extra_keys={"negatives": cfg.sampled_negatives})

@@ -280,6 +280,18 @@ int cgx_eval_topk(const int64_t* users, int64_t n_users, const float* f_u, const
 int cgx_score_candidates(const int64_t* users, const int64_t* cand, int64_t n_users, int32_t n_cand,
                          int32_t d, const float* f_u, const float* f_i, float* scores, void* stream);
 
+/* Candidate lists of the sampled protocol drawn on device (CU:505-521): cand int64[n, 1 + n_neg]; column 0
+ * is one of the user's test items (uniform), the others are uniform items outside test U train (rejection by
+ * binary search in both sorted rows).  users must each own >= 1 test item.  Philox streams per (user, slot). */
+int cgx_eval_candidates(const int64_t* users, int64_t n_users, const int64_t* train_indptr,
+                        const int32_t* train_idx, const int64_t* test_indptr, const int32_t* test_idx,
+                        int32_t num_items, int32_t n_neg, uint64_t seed, int64_t* cand, void* stream);
+
+/* ranked[r] = cand[r] reordered by descending score, ties keeping candidate order (np.argsort(-scores),
+ * CU:527, made stable). */
+int cgx_rank_candidates(const float* scores, const int64_t* cand, int64_t n_users, int32_t n_cand,
+                        int64_t* ranked, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

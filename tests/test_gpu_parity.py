@@ -569,3 +569,55 @@ def test_raw_lightgcn_matches_reference(cg):
     loss.backward()
     assert abs(loss.item() - float(g["loss"])) / abs(float(g["loss"])) < TOL
     assert rel_err(net.emb.weight.grad.cpu().numpy(), g["grad"]) < TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# sampled protocol on device: SURVEY.md section 8f-1
+# ------------------------------------------------------------------------------------------------
+def test_device_sampled_candidates_follow_the_protocol(cg):
+    sg = cg["synth"].make_graph("C1")
+    ev = cg["evaluate"]
+    tr = orc.edges_to_user_csr(sg.train_edges, sg.num_users)
+    te = orc.edges_to_user_csr(sg.test_edges, sg.num_users)
+    users = np.flatnonzero(np.diff(te[0]) > 0)
+    cand = ev.sampled_candidates_device(ev._device_csr(tr, DEV), ev._device_csr(te, DEV), users, sg.num_items, 99, 42)
+    cand2 = ev.sampled_candidates_device(ev._device_csr(tr, DEV), ev._device_csr(te, DEV), users, sg.num_items, 99, 42)
+    assert torch.equal(cand, cand2)                                   # counter-based: reproducible
+    c = cand.cpu().numpy()
+    assert c.shape == (len(users), 100)
+    for r, u in enumerate(users[:200]):
+        test_row, train_row = set(te[1][te[0][u]:te[0][u + 1]]), set(tr[1][tr[0][u]:tr[0][u + 1]])
+        assert c[r, 0] in test_row
+        assert not (set(c[r, 1:]) & (test_row | train_row)) and c[r, 1:].min() >= 0 and c[r, 1:].max() < sg.num_items
+    # negatives are uniform over the allowed items: chi-square on item-id deciles over all users
+    hist = np.bincount((c[:, 1:].ravel() * 10) // sg.num_items, minlength=10).astype(np.float64)
+    allowed = np.ones((len(users), sg.num_items), bool)
+    for r, u in enumerate(users):
+        allowed[r, te[1][te[0][u]:te[0][u + 1]]] = False
+        allowed[r, tr[1][tr[0][u]:tr[0][u + 1]]] = False
+    dec = (np.arange(sg.num_items) * 10) // sg.num_items
+    exp = np.array([(allowed[:, dec == k].sum(1) / allowed.sum(1)).sum() for k in range(10)]) * 99
+    assert ((hist - exp) ** 2 / exp).sum() < 40.0                     # 9 dof
+
+
+def test_device_ranking_equals_stable_argsort(cg):
+    rng = np.random.default_rng(0)
+    scores = rng.standard_normal((257, 100)).astype(np.float32)
+    scores[:, 10:20] = scores[:, :10]                                 # ties
+    cands = rng.integers(0, 5000, (257, 100))
+    got = cg["evaluate"].rank_candidates_device(torch.tensor(scores, device=DEV), torch.tensor(cands, device=DEV))
+    want = np.take_along_axis(cands, np.argsort(-scores, axis=1, kind="stable"), axis=1)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+
+
+def test_evaluate_sampled_on_device_is_statistically_equivalent(cg, golden):
+    """Device-drawn candidates: same protocol, different random stream -> metrics agree with the reference's
+    within sampling noise (binomial std of Recall@20 over the evaluated users, 5 sigma)."""
+    g = golden
+    net = _model(cg, g, _build(cg, g))
+    res = cg["evaluate"].evaluate_sampled(net, (g["csr_indptr"], g["csr_indices"]), (g["test_indptr"], g["test_indices"]),
+                                          int(g["num_items"]), DEV, on_device=True)
+    n = res[20]["users_eval"]
+    want = float(g["sampled_20"][1])
+    assert abs(res[20]["recall"] - want) < 5.0 * np.sqrt(max(want * (1 - want), 0.05) / n) + 0.02
+    assert res[20]["mode"] == "sampled(1pos+neg)" and res[20]["negatives"] == 99
