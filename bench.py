@@ -323,6 +323,7 @@ def main():
     launches0 = _lib.lib().cgx_launch_count()
     with clocks:
         torch.cuda.synchronize()
+        torch.cuda.profiler.start()          # `ncu --profile-from-start off` then sees exactly the timed steps
         for s in range(args.steps):
             if not args.no_flush:
                 flush_buf.fill_(s & 0xff)
@@ -330,6 +331,7 @@ def main():
             one_step(dev_batches[s % len(dev_batches)])
             ends[s].record()
         torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
         launches = _lib.lib().cgx_launch_count() - launches0
         step_ms = [a.elapsed_time(b) for a, b in zip(starts, ends)]
         phases = step.phase_events
