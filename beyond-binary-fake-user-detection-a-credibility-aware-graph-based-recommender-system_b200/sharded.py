@@ -431,19 +431,23 @@ def evaluate_full_ranking_sharded(f_u_local, f_i, graph: CredGraph, test_edges_l
 def bench_main(args, rank: int, world: int, dev: torch.device):
     from . import synth
     shp = synth.SHAPES[args.workload]
-    sg = synth.make_graph(args.workload, seed=20240 + 1000 * (rank + 1), item_seed=20242)
+    if args.workload in ("C4", "C5"):
+        sg = synth.make_graph_device(args.workload, dev, seed=20240 + 1000 * (rank + 1), item_seed=20242)
+    else:
+        sg = synth.make_graph(args.workload, seed=20240 + 1000 * (rank + 1), item_seed=20242)
     U, I, d, K = sg.num_users, sg.num_items, shp["emb_dim"], shp["num_layers"]
-    E_local = sg.train_edges.shape[1]
+    E_local = int(sg.train_edges.shape[1])
     gr = build_local_graph(sg.train_edges, U, I, sg.cred, shp["variant"], dev)
     torch.manual_seed(42)
-    item_emb = torch.nn.init.xavier_uniform_(torch.empty(I, d)).to(dev)          # identical on every rank
+    item_emb = torch.nn.init.xavier_uniform_(torch.empty(I, d, device=dev))      # identical on every rank
     torch.manual_seed(1000 + rank)
-    user_emb = torch.nn.init.xavier_uniform_(torch.empty(U, d)).to(dev)
+    user_emb = torch.nn.init.xavier_uniform_(torch.empty(U, d, device=dev))
+    del sg
     step = ShardedTrainStep(gr, user_emb, item_emb, K, shp["order"], mix_pop=None if shp["variant"] == "cu" else 0.7,
                             exchange=__import__("os").environ.get("CGX_EXCHANGE", "p2p"))
     train_users = torch.nonzero(gr.deg_u > 0).reshape(-1).cpu().numpy()
     np.random.default_rng(42 + rank).shuffle(train_users)
-    nb = len(train_users) // args.batch
+    nb = min(len(train_users) // args.batch, 64)
     host_batches = [train_users[s * args.batch:(s + 1) * args.batch] for s in range(max(nb, 1))]
     dev_batches = [torch.from_numpy(b).to(dev) for b in host_batches]
     pinned = [torch.from_numpy(b).pin_memory() for b in host_batches]
@@ -461,6 +465,9 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if flag.item() == 0:            # every rank must take the same path
             graphed, step._graph = False, None
+    c0 = lib().cgx_launch_count()
+    step(dev_batches[0])                         # one eager step: how many kernels of the library a step launches
+    launches_per_step = lib().cgx_launch_count() - c0
     for s in range(max(args.warmup, 3)):
         step.step(dev_batches[s % len(dev_batches)])
     torch.cuda.synchronize()
@@ -476,6 +483,8 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
     torch.cuda.synchronize()
     dist.barrier()
     launches = lib().cgx_launch_count() - launches0
+    if graphed:                                  # replays do not pass through the host-side counter
+        launches = launches_per_step * args.steps
     total_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in zip(starts, ends))], device=dev)
     dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
 

@@ -177,7 +177,8 @@ def make_graph(
 
 
 def make_graph_device(name: str = "C4", device="cuda", *, num_users=None, num_items=None, num_edges=None,
-                      seed: int | None = None, fake_frac: float = 0.05, split=(0.8, 0.1, 0.1)) -> SynthGraph:
+                      seed: int | None = None, fake_frac: float = 0.05, split=(0.8, 0.1, 0.1),
+                      item_seed: int | None = None) -> SynthGraph:
     """Same law as make_graph, generated with torch on `device` for the shapes NumPy is too slow for
     (C4: 200M edges, C5: 1B edges).  Edge count is approximate (+-1 %): de-duplication is done by one
     sort instead of top-up rounds.  Edge arrays stay on the device (SynthGraph fields hold tensors)."""
@@ -206,7 +207,10 @@ def make_graph_device(name: str = "C4", device="cuda", *, num_users=None, num_it
     ranks = torch.arange(1, I + 1, device=dev, dtype=torch.float64)
     cdf = torch.cumsum(ranks.pow(-0.8), 0)
     cdf = (cdf / cdf[-1]).to(torch.float32)
-    perm = torch.randperm(I, device=dev, generator=gen)
+    if item_seed is None:
+        perm = torch.randperm(I, device=dev, generator=gen)
+    else:       # popularity ranking fixed independently of `seed`: user shards of one catalogue
+        perm = torch.randperm(I, device=dev, generator=torch.Generator(device=dev).manual_seed(item_seed))
     act = torch.exp(torch.randn(U, device=dev, generator=gen))
     act[is_fake] = 0.0
     cnt = torch.floor(act * (E_gen * 1.12 / act.sum())).to(torch.int64)
