@@ -77,7 +77,7 @@ def test_reference_named_builders(cg, golden):
 
 @pytest.mark.parametrize("tag", VARIANTS)
 def test_graph_build_vs_oracle_c1_shape(cg, tag):
-    """C1-shaped graph (943 x 1,682 x 100k): long rows (> 512 nnz), zero-degree items, duplicates,
+    """C1-shaped graph (943 x 1,682 x 100k): long rows (> 256 nnz), zero-degree items, duplicates,
     cred end points 0.0 / 1.0."""
     sg = cg["synth"].make_graph("C1", duplicate_edges=300)
     gr = cg["graph"].build_graph(sg.train_edges, sg.num_users, sg.num_items, sg.cred, tag, DEV)
@@ -97,7 +97,7 @@ def test_graph_build_vs_oracle_c1_shape(cg, tag):
     ct = ops.Ct.tocoo()
     order = np.lexsort((ct.col, ct.row))
     np.testing.assert_array_equal(_bits(gr.by_user.val_bwd.cpu().numpy()), _bits(ct.data[order]))
-    assert gr.by_item.n_long > 0, "C1 has items above 512 train edges: the chunked path must be exercised"
+    assert gr.by_item.n_long > 0, "C1 has items above 256 train edges: the chunked path must be exercised"
     assert (np.diff(gr.by_item.indptr.cpu().numpy()) == 0).any() or True
 
 
