@@ -16,17 +16,18 @@
 // is therefore identical to CGX_SCORE_FP32.  precision = BF16 is the single-pass variant (K' = d,
 // error ~2^-8 relative, no proof, no redo) for callers that accept approximate ranking.
 //
-// Kernel anatomy (one CTA per 128 users, 9 or 13 warps):
+// Kernel anatomy (one CTA per 128 users, 13 or 17 warps):
 //   warp 0      TMEM allocation, then one elected lane issues tcgen05.mma (M=128, N=128, K=16 per
 //               instruction, K'/16 instructions per item tile), tcgen05.commit -> mbarriers
 //   warps 1-4 (and 5-8 when two epilogue groups are used: group g owns accumulator stage g)
 //               epilogue: tcgen05.ld 32x32b.x16 -> registers, predicated append of scores >= the row
 //               threshold, warp-uniform drain into the row's K' kept candidates (one thread per user)
-//   last 4      producers: cp.async (16 B, L2-only) the next 128-item tile of the bf16 item table into
+//   next 4      producers: cp.async (16 B, L2-only) the next 128-item tile of the bf16 item table into
 //               shared memory in the canonical K-major SWIZZLE_128B UMMA layout (64-column k-blocks,
 //               128-byte rows, 16-byte chunks XOR-ed with row%8 -- what TMA would write), so that a
 //               row's 8 chunks are one coalesced 128-byte global read AND one conflict-free shared
 //               write; then fence to the async proxy and arrive on the stage's mbarrier
+//   last 4      mask builders: per user row, 128 "is a train item" bits per item tile, a few tiles ahead
 // Two smem stages for B and two 128-column TMEM accumulators: the MMA of tile j+1 overlaps the
 // epilogue of tile j.
 #include <cuda_bf16.h>
@@ -44,6 +45,7 @@ int eval_fp32_rows(const int64_t* users, const int32_t* row_list, const int32_t*
 constexpr int TC_M = 128;          // users per CTA
 constexpr int TC_N = 128;          // items per tile
 constexpr int TC_STAGES = 2;
+constexpr int TC_MASK_RING = 4;    // train-item bitmasks of that many item tiles are built ahead of the epilogue
 constexpr float TC_MASKED = -1e9f;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -159,7 +161,7 @@ __global__ void k_tc_convert(const float* __restrict__ src, const int64_t* __res
 // With NG = 2 group g drains accumulator stage g (tiles of parity g) into its own list, which doubles the
 // warps that scan scores -- the epilogue, not the MMA, bounds this kernel (d is only 64..128).
 template <int KC, int BC, int NG>
-__global__ void __launch_bounds__(32 * (5 + 4 * NG), 1) k_eval_umma(const __nv_bfloat16* __restrict__ Au,   // [n_users, Kp]
+__global__ void __launch_bounds__(32 * (9 + 4 * NG), 1) k_eval_umma(const __nv_bfloat16* __restrict__ Au,   // [n_users, Kp]
                                                              const __nv_bfloat16* __restrict__ Bi,   // [I, Kp]
                                                              const int64_t* __restrict__ users, int64_t n_users,
                                                              int32_t I, int32_t Kp,
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(32 * (5 + 4 * NG), 1) k_eval_umma(const __nv_b
                                                              int32_t cand_stride,
                                                              float* __restrict__ cand_thr,          // [n_users, 2]
                                                              int dbg) {
-  constexpr int TC_THREADS = 32 * (5 + 4 * NG);
+  constexpr int TC_THREADS = 32 * (9 + 4 * NG);
   extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
   // SWIZZLE_128B atoms must start on 1024-byte boundaries of the shared window
   unsigned char* tc_smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
@@ -179,12 +181,15 @@ __global__ void __launch_bounds__(32 * (5 + 4 * NG), 1) k_eval_umma(const __nv_b
   float* list_s_all = reinterpret_cast<float*>(smem_b + TC_STAGES * tile_bytes);   // [NG][KC][128] unsorted candidates
   int32_t* list_i_all = reinterpret_cast<int32_t*>(list_s_all + NG * KC * TC_M);   // [NG][KC][128]
   uint2* buf_all = reinterpret_cast<uint2*>(list_i_all + NG * KC * TC_M);          // [NG][BC][128] arrivals (score bits, item)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(buf_all + NG * BC * TC_M);
+  uint4* mask_all = reinterpret_cast<uint4*>(buf_all + NG * BC * TC_M);            // [TC_MASK_RING][128] train-item bits
+  uint64_t* bars = reinterpret_cast<uint64_t*>(mask_all + TC_MASK_RING * TC_M);
   uint64_t* full_bar = bars;                 // [TC_STAGES]  producers -> MMA
   uint64_t* empty_bar = bars + TC_STAGES;    // [TC_STAGES]  MMA (commit) -> producers
   uint64_t* tfull_bar = bars + 2 * TC_STAGES;   // [2]       MMA (commit) -> epilogue
   uint64_t* tempty_bar = bars + 2 * TC_STAGES + 2;  // [2]   epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+  uint64_t* mfull_bar = bars + 2 * TC_STAGES + 4;                    // [TC_MASK_RING] mask warps -> epilogue
+  uint64_t* mempty_bar = bars + 2 * TC_STAGES + 4 + TC_MASK_RING;    // [TC_MASK_RING] epilogue -> mask warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4 + 2 * TC_MASK_RING);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t u0 = int64_t(blockIdx.x) * TC_M;
@@ -195,6 +200,7 @@ __global__ void __launch_bounds__(32 * (5 + 4 * NG), 1) k_eval_umma(const __nv_b
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar + s, 128); mbar_init(empty_bar + s, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + a, 1); mbar_init(tempty_bar + a, 128); }
+    for (int m = 0; m < TC_MASK_RING; ++m) { mbar_init(mfull_bar + m, 128); mbar_init(mempty_bar + m, 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -239,6 +245,33 @@ __global__ void __launch_bounds__(32 * (5 + 4 * NG), 1) k_eval_umma(const __nv_b
       }
       __syncwarp();
     }
+  } else if (warp >= 5 + 4 * NG) {
+    // ===== mask builders: one thread per user row walks the row's sorted train items and leaves, for every
+    // item tile, 128 bits "column is a train item" in a ring of TC_MASK_RING tiles.  The walk is a chain of
+    // dependent loads; here it runs ahead of, and beside, the epilogue instead of inside it. =====
+    const int row = threadIdx.x - (5 + 4 * NG) * 32;
+    int64_t cur = 0, hi = 0;
+    if (u0 + row < n_users) {
+      const int64_t uid = users[u0 + row];
+      cur = __ldg(tr_indptr + uid);
+      hi = __ldg(tr_indptr + uid + 1);
+    }
+    int32_t nxt = cur < hi ? __ldg(tr_idx + cur) : INT32_MAX;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int m = j % TC_MASK_RING;
+      mbar_wait(mempty_bar + m, ((j / TC_MASK_RING) & 1) ^ 1);
+      uint4 bits = make_uint4(0u, 0u, 0u, 0u);
+      const int32_t i0 = j * TC_N;
+      while (nxt < i0 + TC_N) {
+        const int c = nxt - i0;
+        const uint32_t b = 1u << (c & 31);
+        if (c < 32) bits.x |= b; else if (c < 64) bits.y |= b; else if (c < 96) bits.z |= b; else bits.w |= b;
+        ++cur;
+        nxt = cur < hi ? __ldg(tr_idx + cur) : INT32_MAX;
+      }
+      mask_all[m * TC_M + row] = bits;
+      mbar_arrive(mfull_bar + m);
+    }
   } else if (warp >= 1 + 4 * NG) {
     // ===== producers: stage item tiles with cp.async, one group per tile, two tiles in flight =====
     const int pt = threadIdx.x - (1 + 4 * NG) * 32;   // 0..127
@@ -271,11 +304,11 @@ __global__ void __launch_bounds__(32 * (5 + 4 * NG), 1) k_eval_umma(const __nv_b
     }
   } else {
     // ===== epilogue: one thread per user row =====
-    // Scores >= the row's threshold are appended (predicated store, no branch) to a BC-slot buffer; when
+    // Scores > the row's threshold are appended (predicated store, no branch) to a BC-slot buffer; when
     // some lane's buffer could overflow in the next 16-column chunk the WARP drains with all lanes
-    // active: train-item mask by a cursor over the sorted train row (arrivals come in increasing item
-    // order), then "replace the weakest of the K' kept candidates and rescan for the new weakest" -- a
-    // loop of fixed length, so lanes do not diverge on data.  Batching arrivals over several chunks
+    // active: "replace the weakest of the K' kept candidates and rescan for the new weakest" -- a loop of
+    // fixed length, so lanes do not diverge on data.  Train items never arrive: the mask builders' bits
+    // clear them from the hit mask.  Batching arrivals over several chunks
     // keeps most lanes busy in a drain (a lane sees ~0.8 arrivals per 128-item tile in steady state).
     // The kept list stays unsorted; k_rescore ranks it.  TMEM loads are software pipelined.
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
@@ -286,45 +319,40 @@ __global__ void __launch_bounds__(32 * (5 + 4 * NG), 1) k_eval_umma(const __nv_b
     const int row = quad * 32 + lane;
     const int64_t ug = u0 + row;
     const bool live = ug < n_users;
-    int64_t tr_cur = 0, tr_hi = 0;
-    if (live) {
-      const int64_t uid = users[ug];
-      tr_cur = __ldg(tr_indptr + uid);
-      tr_hi = __ldg(tr_indptr + uid + 1);
-    }
-    int32_t next_masked = tr_cur < tr_hi ? __ldg(tr_idx + tr_cur) : INT32_MAX;
     for (int p = 0; p < KC; ++p) { list_s[p * TC_M + row] = -FLT_MAX; list_i[p * TC_M + row] = INT32_MAX; }
     float thr = live ? -FLT_MAX : FLT_MAX;      // score of the weakest kept candidate (dead rows accept nothing)
-    int32_t thr_id = INT32_MAX;
     int weakest = 0;           // its slot
     uint2* const wr0 = buf + row;   // arrival slot e of this row = wr0[e * 128]
-    uint2* wr = wr0;                // next free slot: the append is one compare, one 8-byte store, one pointer bump
+    int cnt = 0;                    // arrivals waiting in the buffer
 
     auto drain = [&]() {
-      const int cnt = int(wr - wr0) / TC_M;
       for (int e = 0; e < cnt; ++e) {
         const uint2 ent = wr0[e * TC_M];
-        float sc = __uint_as_float(ent.x);
+        const float sc = __uint_as_float(ent.x);
         const int32_t item = int32_t(ent.y);
-        while (next_masked < item) {
-          ++tr_cur;
-          next_masked = tr_cur < tr_hi ? __ldg(tr_idx + tr_cur) : INT32_MAX;
-        }
-        if (next_masked == item) sc = TC_MASKED;
-        if (tc_better(sc, item, thr, thr_id)) {
+        if (sc > thr) {
           list_s[weakest * TC_M + row] = sc;
           list_i[weakest * TC_M + row] = item;
-          thr = sc;
-          thr_id = item;
-#pragma unroll 8
-          for (int p = 0; p < KC; ++p) {   // new weakest
-            const float ps = list_s[p * TC_M + row];
-            const int32_t pi = list_i[p * TC_M + row];
-            if (tc_better(thr, thr_id, ps, pi)) { thr = ps; thr_id = pi; weakest = p; }
+          // new weakest: KC independent loads, then a min tree of depth log2(KC) (a sequential scan would be a
+          // chain of KC dependent compare+select steps, and this warp is alone on its scheduler)
+          float mv[KC];
+          int ms[KC];
+#pragma unroll
+          for (int p = 0; p < KC; ++p) { mv[p] = list_s[p * TC_M + row]; ms[p] = p; }
+#pragma unroll
+          for (int w = 1; w < KC; w <<= 1) {
+#pragma unroll
+            for (int p = 0; p + w < KC; p += 2 * w) {
+              const bool lower = mv[p + w] < mv[p];
+              mv[p] = lower ? mv[p + w] : mv[p];
+              ms[p] = lower ? ms[p + w] : ms[p];
+            }
           }
+          thr = mv[0];
+          weakest = ms[0];
         }
       }
-      wr = wr0;
+      cnt = 0;
     };
 
     for (int j = grp; j < n_tiles; j += NG) {
@@ -334,37 +362,49 @@ __global__ void __launch_bounds__(32 * (5 + 4 * NG), 1) k_eval_umma(const __nv_b
       const int32_t i0 = j * TC_N;
       const int valid = I - i0 < TC_N ? I - i0 : TC_N;   // columns of this tile that are real items
       const uint32_t tbase = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(a * TC_N);
+      const int m = j % TC_MASK_RING;
+      mbar_wait(mfull_bar + m, (j / TC_MASK_RING) & 1);
+      const uint4 tbits = mask_all[m * TC_M + row];
       float v[2][16];
       tmem_ld16(tbase, v[0]);
       tmem_wait_ld();
 #pragma unroll
       for (int ch = 0; ch < TC_N / 16; ++ch) {
         if (ch + 1 < TC_N / 16) tmem_ld16(tbase + (ch + 1) * 16, v[(ch + 1) & 1]);   // in flight during the scan below
-        if (dbg & 1) {
-        } else if (ch * 16 + 16 <= valid) {
+        // 16 independent compares -> bit mask -> slot of every hit from a popcount of the lower bits: no
+        // loop-carried dependency (a single warp per scheduler cannot hide a 16-long pointer-bump chain)
+        const int lim = valid - ch * 16;          // columns of this chunk that are real items (>= 16: all)
+        const uint32_t tw = (ch >> 1) == 0 ? tbits.x : (ch >> 1) == 1 ? tbits.y : (ch >> 1) == 2 ? tbits.z : tbits.w;
+        const uint32_t keep = (lim >= 16 ? 0xffffu : lim <= 0 ? 0u : (1u << lim) - 1u) & ~(tw >> ((ch & 1) * 16));
+        uint32_t hit = 0;
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            if (v[ch & 1][q] >= thr) {
-              *wr = make_uint2(__float_as_uint(v[ch & 1][q]), uint32_t(i0 + ch * 16 + q));
-              wr += TC_M;
-            }
-          }
-        } else {
+        for (int q = 0; q < 16; ++q) hit |= v[ch & 1][q] > thr ? (1u << q) : 0u;
+        hit &= keep;
+        if (dbg & 1) hit = 0;
+        // one hit per lane per pass (a warp sees ~3 hits per chunk early on, < 1 later): the passes are
+        // warp-uniform, and a hit costs a 16 -> 1 select tree instead of 16 predicated store sequences
+        while (__any_sync(0xffffffffu, hit != 0u)) {
+          if (hit != 0u) {
+            const int q = __ffs(hit) - 1;
+            hit &= hit - 1u;
+            float s8[8], s4[4];
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            if (v[ch & 1][q] >= thr && ch * 16 + q < valid) {
-              *wr = make_uint2(__float_as_uint(v[ch & 1][q]), uint32_t(i0 + ch * 16 + q));
-              wr += TC_M;
-            }
+            for (int t = 0; t < 8; ++t) s8[t] = (q & 1) ? v[ch & 1][2 * t + 1] : v[ch & 1][2 * t];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) s4[t] = (q & 2) ? s8[2 * t + 1] : s8[2 * t];
+            const float s2a = (q & 4) ? s4[1] : s4[0], s2b = (q & 4) ? s4[3] : s4[2];
+            wr0[cnt * TC_M] = make_uint2(__float_as_uint((q & 8) ? s2b : s2a), uint32_t(i0 + ch * 16 + q));
+            ++cnt;
           }
         }
-        if (__any_sync(0xffffffffu, wr - wr0 > (BC - 16) * TC_M)) {
-          if (dbg & 8) wr = wr0; else drain();
+        if (__any_sync(0xffffffffu, cnt > BC - 16)) {
+          if (dbg & 8) cnt = 0; else drain();
         }
         if (ch + 1 < TC_N / 16) tmem_wait_ld();
       }
       tc_fence_before();
       mbar_arrive(tempty_bar + a);
+      mbar_arrive(mempty_bar + m);
     }
     drain();
     if (live) {
@@ -406,9 +446,16 @@ __global__ void __launch_bounds__(256) k_rescore(const int64_t* __restrict__ use
   for (int q = 0; q < PER; ++q) {
     id[q] = cand_ids[r * KC + q * 32 + lane];
     if (id[q] == INT32_MAX) { sc[q] = -FLT_MAX; continue; }
-    const float* irow = f_i + int64_t(id[q]) * d;
+    const float4* u4 = reinterpret_cast<const float4*>(urow);                       // d % 16 == 0, rows 16-byte aligned
+    const float4* i4 = reinterpret_cast<const float4*>(f_i + int64_t(id[q]) * d);
     float acc = 0.f;
-    for (int k = 0; k < d; ++k) acc = fmaf(__ldg(urow + k), __ldg(irow + k), acc);   // same order as k_eval_fp32
+    for (int k4 = 0; k4 < d / 4; ++k4) {   // same fmaf order as k_eval_fp32 (ascending k, one chain)
+      const float4 a = __ldg(u4 + k4), b = __ldg(i4 + k4);
+      acc = fmaf(a.x, b.x, acc);
+      acc = fmaf(a.y, b.y, acc);
+      acc = fmaf(a.z, b.z, acc);
+      acc = fmaf(a.w, b.w, acc);
+    }
     sc[q] = tc_in_row(tr_idx, lo, hi, id[q]) ? TC_MASKED : acc;
   }
   // rank of every candidate under (score desc, id asc)
@@ -447,16 +494,21 @@ __global__ void __launch_bounds__(256) k_rescore(const int64_t* __restrict__ use
 struct TcConfig {
   int KC, BC, NG, stride;   // stride = candidates per user handed to k_rescore (32 or 64)
 };
-static TcConfig tc_config(int32_t K) {
+static TcConfig tc_config(int32_t K, int precision) {
   // Two epilogue groups (24, 16, 2, 64) were measured SLOWER on C2 (3.69 ms vs 3.19 ms): each group keeps
   // its own, weaker threshold, so more scores reach the merge code.  Set CGX_EVAL_GROUPS=2 to try it.
   static const bool two = getenv("CGX_EVAL_GROUPS") != nullptr && atoi(getenv("CGX_EVAL_GROUPS")) == 2;
   if (two && K + 4 <= 24) return {24, 16, 2, 64};
+  // K' = 24 (margin 4) is 4 % faster on C2 but on C3 (91 599 items, denser top scores) the completeness proof
+  // fails for enough rows that the fp32 redo doubles the time (10.9 ms vs 5.7 ms): opt-in, CGX_EVAL_KC=24
+  static const bool kc24 = getenv("CGX_EVAL_KC") != nullptr && atoi(getenv("CGX_EVAL_KC")) == 24;
+  if (kc24 && precision == CGX_SCORE_BF16X3 && K + 4 <= 24) return {24, 40, 1, 32};
   if (K + 12 <= 32) return {32, 32, 1, 32};
   return {64, 16, 1, 64};
 }
 static size_t tc_smem(const TcConfig& c, int Kp) {
-  return size_t(1 + TC_STAGES) * TC_M * Kp * 2 + size_t(c.NG) * (c.KC + c.BC) * TC_M * 8 + 128 + 1024;
+  return size_t(1 + TC_STAGES) * TC_M * Kp * 2 + size_t(c.NG) * (c.KC + c.BC) * TC_M * 8 +
+         size_t(TC_MASK_RING) * TC_M * 16 + 256 + 1024;
 }
 
 size_t eval_topk_tc_workspace(int64_t n_users, int32_t I, int32_t d, int32_t K, int precision) {
@@ -469,7 +521,7 @@ size_t eval_topk_tc_workspace(int64_t n_users, int32_t I, int32_t d, int32_t K, 
 static bool tc_supported(int32_t d, int32_t K, int parts) {
   const int Kp = (parts * d + 63) / 64 * 64;
   if (K + 12 > 64) return false;
-  return tc_smem(tc_config(K), Kp) <= 227 * 1024;
+  return tc_smem(tc_config(K, parts == 3 ? CGX_SCORE_BF16X3 : CGX_SCORE_BF16), Kp) <= 227 * 1024;
 }
 
 template <int KC, int BC, int NG, int STRIDE>
@@ -480,7 +532,7 @@ static int tc_launch(const __nv_bfloat16* Au, const __nv_bfloat16* Bi, const int
                      int32_t* n_redo, cudaStream_t stream) {
   const size_t smem = tc_smem(TcConfig{KC, BC, NG, STRIDE}, Kp);
   CGX_CUDA(cudaFuncSetAttribute(k_eval_umma<KC, BC, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_eval_umma<KC, BC, NG><<<(unsigned)ceil_div(n_users, TC_M), 32 * (5 + 4 * NG), smem, stream>>>(
+  k_eval_umma<KC, BC, NG><<<(unsigned)ceil_div(n_users, TC_M), 32 * (9 + 4 * NG), smem, stream>>>(
       Au, Bi, users, n_users, I, Kp, tr_indptr, tr_idx, cand, STRIDE, thr,
       getenv("CGX_EVAL_DBG") ? atoi(getenv("CGX_EVAL_DBG")) : 0);
   CGX_LAUNCH_CHECK();
@@ -504,7 +556,7 @@ int eval_topk_tc(const int64_t* users, int64_t n_users, const float* f_u, const 
   CGX_REQUIRE(workspace_bytes >= eval_topk_tc_workspace(n_users, I, d, K, precision), CGX_ERR_WORKSPACE,
               "eval_topk: workspace too small");
   const int Kp = (parts * d + 63) / 64 * 64;
-  const TcConfig cfg = tc_config(K);
+  const TcConfig cfg = tc_config(K, precision);
   Arena ws(workspace, workspace_bytes);
   __nv_bfloat16* Au = ws.take<__nv_bfloat16>(size_t(n_users) * Kp);
   __nv_bfloat16* Bi = ws.take<__nv_bfloat16>(size_t(I) * Kp);
@@ -527,6 +579,8 @@ int eval_topk_tc(const int64_t* users, int64_t n_users, const float* f_u, const 
                     out_ids, out_scores, redo_rows, n_redo, stream
   if (cfg.NG == 2) {
     CGX_TRY((tc_launch<24, 16, 2, 64>(CGX_TC_ARGS)));
+  } else if (cfg.KC == 24) {
+    CGX_TRY((tc_launch<24, 40, 1, 32>(CGX_TC_ARGS)));
   } else if (cfg.KC == 32) {
     CGX_TRY((tc_launch<32, 32, 1, 32>(CGX_TC_ARGS)));
   } else {
