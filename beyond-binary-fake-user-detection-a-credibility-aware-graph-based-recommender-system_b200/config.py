@@ -60,6 +60,7 @@ class CFG:
     # sampled eval: False = candidates from the reference's own PCG64 stream on the host (identical lists);
     # True = candidates drawn on device (same protocol, Philox streams; no per-user Python loop)
     sampled_eval_on_device: bool = False
+    metrics_on_device: bool = True   # ranking metrics by cgx_eval_metrics (False: vectorised NumPy on the host)
 
 
 cfg = CFG()

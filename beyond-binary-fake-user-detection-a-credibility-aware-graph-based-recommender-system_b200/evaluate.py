@@ -8,6 +8,7 @@ become one device top-K (or candidate-scoring) call plus vectorised NumPy metric
 """
 from __future__ import annotations
 
+import ctypes
 import math
 
 import numpy as np
@@ -141,6 +142,84 @@ def metrics_from_ranked(ranked: np.ndarray, users: np.ndarray, test_csr, num_ite
     return out
 
 
+def metrics_sums_device(ranked_dev: torch.Tensor, users_dev, test_csr_dev, num_items: int, ks, item_pop_dev=None,
+                        total_train=0, flags_dev=None, gt_single_dev=None, with_coverage=False):
+    """(sums float64[len(ks), 7], bitmaps int32[len(ks), ceil(I/32)] | None) on the device: the per-rank part of
+    the metrics (cgx_eval_metrics); `ks` ascending."""
+    dev = ranked_dev.device
+    n = ranked_dev.shape[0]
+    out = torch.zeros(len(ks), 7, dtype=torch.float64, device=dev)
+    bitmaps = torch.zeros(len(ks), (num_items + 31) // 32, dtype=torch.int32, device=dev) if with_coverage else None
+    if n == 0:
+        return out, bitmaps
+    ranked_dev = ranked_dev.to(torch.int32).contiguous()
+    ks_host = (ctypes.c_int32 * len(ks))(*ks)
+    ws = workspace(lib().cgx_eval_metrics_workspace_bytes(n, len(ks)), dev)
+    gt = None if gt_single_dev is None else gt_single_dev.to(torch.int32).contiguous()
+    ip, ix = test_csr_dev if test_csr_dev is not None else (None, None)
+    opt = lambda t: None if t is None else ptr(t)   # noqa: E731
+    with torch.cuda.device(dev):
+        check(lib().cgx_eval_metrics(ptr(ranked_dev), n, ranked_dev.shape[1], opt(users_dev), opt(ip), opt(ix), opt(gt),
+                                     num_items, ks_host, len(ks), opt(item_pop_dev), int(total_train), opt(flags_dev),
+                                     opt(bitmaps), ptr(out), ptr(ws), ws.numel(), stream_ptr(dev)))
+    return out, bitmaps
+
+
+def coverage_counts_device(bitmaps: torch.Tensor, num_items: int) -> torch.Tensor:
+    counts = torch.empty(bitmaps.shape[0], dtype=torch.int64, device=bitmaps.device)
+    with torch.cuda.device(bitmaps.device):
+        check(lib().cgx_eval_coverage(ptr(bitmaps), num_items, bitmaps.shape[0], ptr(counts),
+                                      stream_ptr(bitmaps.device)))
+    return counts
+
+
+def metrics_result(Ks, ks, sums, counts, n: int, num_items: int, mode: str, groups=None, extra_keys=None):
+    """The reference's result dict from the device sums; groups = (n_high, n_low, cred_utility) or None."""
+    res_all = {}
+    for K in Ks:
+        ki = ks.index(int(K))
+        s = sums[ki]
+        res = {"precision": float(s[0] / n), "recall": float(s[1] / n), "ndcg": float(s[2] / n)}
+        if groups is not None:
+            n_hi, n_lo, cred_utility = groups
+            res.update({
+                "item_coverage": int(counts[ki]) / max(num_items, 1),
+                "avg_log_popularity": float(s[3] / n),
+                "avg_self_information": float(s[4] / n),
+                "cred_utility": float(cred_utility),
+                "high_cred_recall": float(s[5] / max(n_hi, 1)),
+                "low_cred_recall": float(s[6] / max(n_lo, 1)),
+                "high_users": int(n_hi), "low_users": int(n_lo),
+            })
+        res.update({"users_eval": n, "mode": mode})
+        if extra_keys:
+            res.update(extra_keys)
+        res_all[K] = res
+    return res_all
+
+
+def metrics_device(ranked_dev: torch.Tensor, users, test_csr_dev, num_items: int, Ks, mode: str, item_pop=None,
+                   total_train=0, cred_np=None, group_pct=0.20, gt_single_dev=None, extra_keys=None):
+    """metrics_from_ranked computed on the device (cgx_eval_metrics + cgx_eval_coverage): the ranked ids stay
+    in HBM and 7 sums + one count per cut-off come back.  Same result dict (double accumulation; the means
+    agree with the NumPy path to ~1e-13 relative, the order of the additions differs)."""
+    dev = ranked_dev.device
+    users_np = np.asarray(users, dtype=np.int64)
+    ks = sorted(set(int(k) for k in Ks))
+    extra = item_pop is not None and cred_np is not None
+    pop_dev = flags_dev = groups = None
+    if extra:
+        hi, lo = make_cred_groups(users_np, cred_np, group_pct)
+        in_hi, in_lo = np.isin(users_np, hi), np.isin(users_np, lo)
+        flags_dev = torch.from_numpy(in_hi.astype(np.uint8) + 2 * in_lo.astype(np.uint8)).to(dev)   # bit 0 high, bit 1 low
+        pop_dev = torch.as_tensor(np.asarray(item_pop, dtype=np.int64)).to(dev)
+        groups = (int(in_hi.sum()), int(in_lo.sum()), np.asarray(cred_np, np.float64)[users_np].mean())
+    sums, bitmaps = metrics_sums_device(ranked_dev, torch.from_numpy(users_np).to(dev), test_csr_dev, num_items, ks,
+                                        pop_dev, total_train, flags_dev, gt_single_dev, with_coverage=extra)
+    counts = coverage_counts_device(bitmaps, num_items).cpu().numpy() if extra else None
+    return metrics_result(Ks, ks, sums.cpu().numpy(), counts, users_np.size, num_items, mode, groups, extra_keys)
+
+
 def _final_tables(model):
     with torch.no_grad():
         return model.final_embeddings() if hasattr(model, "final_embeddings") else model.get_user_item_emb()
@@ -160,6 +239,9 @@ def evaluate_full_ranking(model, train_csr, test_csr, num_items: int, device=Non
     K = max(cfg.Ks)
     ids, _ = topk_device(f_u, f_i, torch.from_numpy(users), _device_csr(train_csr, f_u.device), K,
                          precision or cfg.score_precision)
+    if cfg.metrics_on_device:
+        return metrics_device(ids, users, _device_csr(test_csr, f_u.device), num_items, cfg.Ks, "full", item_pop,
+                              total_train_interactions, cred_np, cfg.cred_group_pct)
     ranked = ids.cpu().numpy()
     return metrics_from_ranked(ranked, users, (indptr_te, np.asarray(test_csr[1])), num_items, cfg.Ks, "full",
                                item_pop, total_train_interactions, cred_np, cfg.cred_group_pct)
@@ -235,6 +317,10 @@ def evaluate_sampled(model, train_csr, test_csr, num_items: int, device=None, it
         raise RuntimeError("No users with test interactions.")
     scores = score_candidates_device(f_u, f_i, torch.from_numpy(np.asarray(users)), cands_dev)
     ranked_dev = rank_candidates_device(scores, cands_dev)
+    if cfg.metrics_on_device:
+        return metrics_device(ranked_dev, users, None, num_items, cfg.Ks, "sampled(1pos+neg)", item_pop,
+                              total_train_interactions, cred_np, cfg.cred_group_pct, gt_single_dev=cands_dev[:, 0],
+                              extra_keys={"negatives": cfg.sampled_negatives})
     ranked = ranked_dev.cpu().numpy()
     cands = cands_dev.cpu().numpy()
     return metrics_from_ranked(ranked, users, te, num_items, cfg.Ks, "sampled(1pos+neg)", item_pop,

@@ -360,69 +360,64 @@ def evaluate_full_ranking_sharded(f_u_local, f_i, graph: CredGraph, test_edges_l
                                   item_pop=None, total_train=0, cred_local=None, group_pct=0.20, group=None,
                                   precision="fp32"):
     """User-sharded full-rank evaluation (Version-2/lighgcn_cu_pop.py:653-752): every rank ranks ITS users
-    against the replicated item table -- no embedding traffic -- and only per-user metric vectors of the evaluated
-    users (a few floats each) are gathered to form the global means, coverage set and credibility groups.
+    against the replicated item table -- no embedding traffic -- and reduces them to metric sums on the device
+    (cgx_eval_metrics).  Across ranks go: the 7 sums per cut-off (all-reduce, double), the coverage bitmaps
+    (all-gather, OR-ed locally) and one credibility value per evaluated user (all-gather; the high / low groups are
+    percentiles of the GLOBAL credibility order, V2:406-423).
     `graph` is the rank's local CredGraph (train mask = its duplicate-keeping user rows); `test_edges_local`
     holds the rank's users with shard-local ids."""
     from . import evaluate as ev
     from .graph import user_csr_device
     dev = f_u_local.device
     U_loc = graph.num_users
-    ip, ix = user_csr_device(test_edges_local, U_loc, num_items, dev)
-    te = (ip.cpu().numpy(), ix.cpu().numpy().astype(np.int64))
-    users = np.flatnonzero(np.diff(te[0]) > 0).astype(np.int64)
-    K = max(Ks)
-    if users.size:
-        ids, _ = ev.topk_device(f_u_local, f_i, torch.from_numpy(users), (graph.samp_indptr, graph.samp_idx), K, precision)
-        ranked = ids.cpu().numpy()
-    else:
-        ranked = np.zeros((0, K), np.int32)
-    hits = ev._hits_matrix(ranked, users, te, num_items) if users.size else np.zeros((0, K), bool)
-    n_gt = np.diff(te[0])[users]
+    te = user_csr_device(test_edges_local, U_loc, num_items, dev)
+    users_dev = torch.nonzero(te[0][1:] > te[0][:-1]).flatten()
+    n_loc = int(users_dev.numel())
     world = _world(group)
-    rank = dist.get_rank(group) if world > 1 else 0
-    payload = dict(hits=hits, n_gt=n_gt, ranked=ranked, cred=None if cred_local is None else np.asarray(cred_local)[users],
-                   rank=np.full(users.size, rank))
-    parts = [payload]
-    if world > 1:
+    K = max(Ks)
+    ks = sorted(set(int(k) for k in Ks))
+    extra = item_pop is not None and cred_local is not None
+
+    def gather(x: np.ndarray):
+        if world == 1:
+            return [x]
         parts = [None] * world
-        dist.all_gather_object(parts, payload, group=group)
-    hits = np.concatenate([p["hits"] for p in parts])
-    n_gt = np.concatenate([p["n_gt"] for p in parts])
-    ranked = np.concatenate([p["ranked"] for p in parts])
-    n = hits.shape[0]
+        dist.all_gather_object(parts, x, group=group)
+        return parts
+
+    flags_dev = pop_dev = groups = None
+    counts = gather(np.int64(n_loc))
+    n = int(sum(int(c) for c in counts))
     if n == 0:
         raise RuntimeError("No users with test interactions. Check your split or threshold.")
-    disc = 1.0 / np.log2(np.arange(K) + 2.0)
-    idcg_tab = np.concatenate([[0.0], np.cumsum(disc)])
-    extra = item_pop is not None and cred_local is not None
     if extra:
-        cred_all = np.concatenate([p["cred"] for p in parts])
+        users_np = users_dev.cpu().numpy()
+        parts = gather(np.asarray(cred_local)[users_np])
+        rank = dist.get_rank(group) if world > 1 else 0
+        first = int(sum(len(p) for p in parts[:rank]))
+        cred_all = np.concatenate(parts)
         hi, lo = ev.make_cred_groups(np.arange(n), cred_all, group_pct)
-        in_hi, in_lo = np.isin(np.arange(n), hi), np.isin(np.arange(n), lo)
-    out = {}
-    for k in Ks:
-        h = hits[:, :k]
-        nh = h.sum(1)
-        recall = nh / np.maximum(n_gt, 1)
-        idcg = idcg_tab[np.minimum(n_gt, k)]
-        ndcg = np.where(idcg > 0, (h * disc[:k]).sum(1) / np.where(idcg > 0, idcg, 1.0), 0.0)
-        res = {"precision": float((nh / k).mean()), "recall": float(recall.mean()), "ndcg": float(ndcg.mean())}
-        if extra:
-            top = ranked[:, :k].astype(np.int64)
-            pcount = item_pop[top].astype(np.float64)
-            res.update({
-                "item_coverage": np.unique(top).size / max(num_items, 1),
-                "avg_log_popularity": float(np.log(pcount + 1.0).mean(1).mean()),
-                "avg_self_information": float((-np.log2((pcount + 1.0) / (total_train + num_items))).mean(1).mean()),
-                "cred_utility": float(cred_all.astype(np.float64).mean()),
-                "high_cred_recall": float(recall[in_hi].sum() / max(int(in_hi.sum()), 1)),
-                "low_cred_recall": float(recall[in_lo].sum() / max(int(in_lo.sum()), 1)),
-                "high_users": int(in_hi.sum()), "low_users": int(in_lo.sum()),
-            })
-        res.update({"users_eval": n, "mode": "full"})
-        out[k] = res
-    return out
+        mine = np.arange(first, first + n_loc)
+        in_hi, in_lo = np.isin(mine, hi), np.isin(mine, lo)
+        flags_dev = torch.from_numpy(in_hi.astype(np.uint8) + 2 * in_lo.astype(np.uint8)).to(dev)
+        pop_dev = torch.as_tensor(np.asarray(item_pop, dtype=np.int64)).to(dev)
+        groups = (len(hi), len(lo), cred_all.astype(np.float64).mean())
+    if n_loc:
+        ids, _ = ev.topk_device(f_u_local, f_i, users_dev, (graph.samp_indptr, graph.samp_idx), K, precision)
+    else:
+        ids = torch.zeros(0, K, dtype=torch.int32, device=dev)
+    sums, bitmaps = ev.metrics_sums_device(ids, users_dev, te, num_items, ks, pop_dev, total_train, flags_dev,
+                                           with_coverage=extra)
+    if world > 1:
+        dist.all_reduce(sums, group=group)
+        if extra:   # NCCL has no bitwise-OR reduction: gather the (small) bitmaps and OR them here
+            parts = [torch.empty_like(bitmaps) for _ in range(world)]
+            dist.all_gather(parts, bitmaps, group=group)
+            for p in parts[1:]:
+                parts[0] |= p
+            bitmaps = parts[0]
+    cover = ev.coverage_counts_device(bitmaps, num_items).cpu().numpy() if extra else None
+    return ev.metrics_result(Ks, ks, sums.cpu().numpy(), cover, n, num_items, "full", groups)
 
 
 # ------------------------------------------------------------------------------------------

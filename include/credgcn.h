@@ -292,6 +292,32 @@ int cgx_eval_candidates(const int64_t* users, int64_t n_users, const int64_t* tr
 int cgx_rank_candidates(const float* scores, const int64_t* cand, int64_t n_users, int32_t n_cand,
                         int64_t* ranked, void* stream);
 
+/* Ranking metrics from ranked ids int32[n, ld] (rows of cgx_eval_topk, or cgx_rank_candidates narrowed to
+ * int32), accumulated in double like the reference's Python floats: metrics_at_k CU:469-484 / V2:514-530 and
+ * the accumulation loops of evaluate_full_ranking V2:691-752 / evaluate_sampled CU:521-546.
+ *   ground truth   gt_single != NULL: one item per row (sampled protocol), else the sorted test rows
+ *                  test_idx[test_indptr[users[r]] .. test_indptr[users[r] + 1]) (duplicates counted, as np.diff)
+ *   ks_host        HOST array of n_ks <= 8 ascending cut-offs, each <= min(ld, 256)
+ *   item_pop       nullable int64[num_items] train popularity (V2:382-388); total_train = its sum
+ *   group          nullable uint8[n]: bit 0 = row is in the high-credibility group, bit 1 = in the low one
+ *                  (make_cred_groups V2:406-423; a row can be in both when the groups overlap)
+ *   bitmaps        nullable uint32[n_ks][ceil(num_items / 32)], ZEROED BY THE CALLER: bit i of bitmap ki is set
+ *                  when item i occurs in columns [ks[ki-1], ks[ki]) of some row; a user-sharded evaluation ORs
+ *                  the bitmaps of all ranks before cgx_eval_coverage
+ *   out            device double[n_ks][7]: SUMS over rows of precision, recall, ndcg, mean_k log(pop + 1),
+ *                  mean_k -log2((pop + 1) / (total_train + num_items)), recall of group 1, recall of group 2
+ * Deterministic: block partials are combined in a fixed order. */
+size_t cgx_eval_metrics_workspace_bytes(int64_t n_users, int32_t n_ks);
+int cgx_eval_metrics(const int32_t* ranked, int64_t n_users, int32_t ld, const int64_t* users,
+                     const int64_t* test_indptr, const int32_t* test_idx, const int32_t* gt_single,
+                     int32_t num_items, const int32_t* ks_host, int32_t n_ks, const int64_t* item_pop,
+                     int64_t total_train, const uint8_t* group, uint32_t* bitmaps, double* out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* counts[ki] = distinct items in the first ks[ki] columns = popcount(bitmaps[0] | .. | bitmaps[ki])
+ * (item_coverage numerator, V2:708-712).  counts: device uint64[n_ks], overwritten. */
+int cgx_eval_coverage(const uint32_t* bitmaps, int32_t num_items, int32_t n_ks, uint64_t* counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

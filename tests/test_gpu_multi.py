@@ -95,9 +95,10 @@ def _worker(rank, world, port, out):
             ev_err = 0.0
             for kk in (10, 20):
                 for key in ("precision", "recall", "ndcg", "item_coverage", "avg_log_popularity",
-                            "avg_self_information", "cred_utility"):
+                            "avg_self_information", "cred_utility", "high_cred_recall", "low_cred_recall"):
                     ev_err = max(ev_err, abs(got[kk][key] - want[kk][key]) / max(abs(want[kk][key]), 1e-12))
                 assert got[kk]["users_eval"] == want[kk]["users_eval"]
+                assert (got[kk]["high_users"], got[kk]["low_users"]) == (want[kk]["high_users"], want[kk]["low_users"])
             res["eval"] = dict(err=ev_err, deg=0, p2p_equals_nccl=True)
             out[0] = res
     finally:

@@ -621,3 +621,55 @@ def test_evaluate_sampled_on_device_is_statistically_equivalent(cg, golden):
     want = float(g["sampled_20"][1])
     assert abs(res[20]["recall"] - want) < 5.0 * np.sqrt(max(want * (1 - want), 0.05) / n) + 0.02
     assert res[20]["mode"] == "sampled(1pos+neg)" and res[20]["negatives"] == 99
+
+
+@pytest.mark.parametrize("mode", ["full", "sampled"])
+@pytest.mark.parametrize("extra", [False, True])
+def test_device_metrics_equal_host_metrics(cg, mode, extra):
+    """cgx_eval_metrics / cgx_eval_coverage against the vectorised NumPy metrics (both accumulate in double;
+    only the order of the additions differs)."""
+    ev = cg["evaluate"]
+    rng = np.random.default_rng(5)
+    U, I, n, ld = 900, 1500, 700, 37
+    Ks = [20, 5, 37, 10]                                              # unsorted on purpose
+    users = np.sort(rng.choice(U, n, replace=False)).astype(np.int64)
+    rows = [np.sort(rng.choice(I, rng.integers(1, 40), replace=True)) for _ in range(U)]   # duplicates kept
+    te_indptr = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+    te_idx = np.concatenate(rows).astype(np.int64)
+    ranked = np.stack([rng.permutation(I)[:ld] for _ in range(n)]).astype(np.int32)
+    for r in range(0, n, 3):                                          # make sure hits exist
+        row = rows[users[r]]
+        ranked[r, rng.integers(0, ld)] = row[rng.integers(0, len(row))]
+    item_pop = rng.integers(0, 500, I).astype(np.int64) if extra else None
+    cred = rng.random(U) if extra else None
+    total = int(item_pop.sum()) if extra else 0
+    gt_single = ranked[np.arange(n), rng.integers(0, ld, n)].astype(np.int64) if mode == "sampled" else None
+    pct = 0.6 if extra else 0.2                                       # 0.6: the two credibility groups overlap
+    want = ev.metrics_from_ranked(ranked, users, (te_indptr, te_idx), I, Ks, mode, item_pop, total, cred, pct,
+                                  gt_single=gt_single, extra_keys={"negatives": 99} if mode == "sampled" else None)
+    te_dev = (torch.tensor(te_indptr, device=DEV), torch.tensor(te_idx, device=DEV, dtype=torch.int32))
+    got = ev.metrics_device(torch.tensor(ranked, device=DEV), users, None if mode == "sampled" else te_dev, I, Ks, mode,
+                            item_pop, total, cred, pct,
+                            gt_single_dev=None if gt_single is None else torch.tensor(gt_single, device=DEV),
+                            extra_keys={"negatives": 99} if mode == "sampled" else None)
+    assert list(got) == list(want)
+    for K in Ks:
+        assert got[K].keys() == want[K].keys()
+        for k, v in want[K].items():
+            if isinstance(v, float):
+                assert got[K][k] == pytest.approx(v, rel=1e-11, abs=1e-13), (K, k)
+            else:
+                assert got[K][k] == v, (K, k)
+    again = ev.metrics_device(torch.tensor(ranked, device=DEV), users, None if mode == "sampled" else te_dev, I, Ks, mode,
+                              item_pop, total, cred, pct,
+                              gt_single_dev=None if gt_single is None else torch.tensor(gt_single, device=DEV),
+                              extra_keys={"negatives": 99} if mode == "sampled" else None)
+    assert again == got                                               # deterministic to the bit
+
+
+def test_device_metrics_reject_bad_cutoffs(cg):
+    ev = cg["evaluate"]
+    ranked = torch.zeros(4, 10, dtype=torch.int32, device=DEV)
+    from credgcn._lib import CgxError
+    with pytest.raises(CgxError):
+        ev.metrics_device(ranked, np.arange(4), None, 50, [20], "sampled", gt_single_dev=torch.zeros(4, device=DEV))
