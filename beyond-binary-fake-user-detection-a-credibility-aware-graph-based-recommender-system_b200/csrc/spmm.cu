@@ -67,15 +67,21 @@ __device__ __forceinline__ unsigned group_mask() {
 }
 
 // acc[v] (v < V) += sum over nnz in [begin, end) of val * X[idx, :]; one group, lane = 0..G-1.
-template <int G, int V, int UNR, int HINT>
+// NZ: `nz[c] == 0` marks row c of X as all-zero (the loss gradient touches <= 3 * batch rows): its weight is
+// forced to 0 and rows of weight 0 are not loaded -- same sum, a fraction of the gather traffic.
+template <int G, int V, int UNR, int HINT, bool NZ = false>
 __device__ __forceinline__ void gather_batches(const int32_t* __restrict__ idx, const float* __restrict__ val,
                                                int64_t begin, int64_t end, const float4* __restrict__ X, int lane,
-                                               unsigned mask, int32_t c_nxt, float w_nxt, float4 (&acc)[V]) {
+                                               unsigned mask, int32_t c_nxt, float w_nxt, float4 (&acc)[V],
+                                               const uint8_t* __restrict__ nz = nullptr) {
   // (c_nxt, w_nxt) = this lane's column id / value of the first batch, already loaded by the caller
   constexpr int ROW4 = G * V;  // float4 per embedding row
   for (int64_t base = begin; base < end; base += G) {
     const int32_t c = c_nxt;
-    const float w = w_nxt;
+    float w = w_nxt;
+    if (NZ) {
+      if (w != 0.f && __ldg(nz + c) == 0) w = 0.f;
+    }
     const int64_t pn = base + G + lane;  // prefetch the next batch of column ids / values
     if (pn < end) {
       c_nxt = __ldg(idx + pn);
@@ -91,7 +97,7 @@ __device__ __forceinline__ void gather_batches(const int32_t* __restrict__ idx, 
         const int src = (j < G) ? j : (G - 1);
         const int32_t cj = __shfl_sync(mask, c, src, G);
         ww[t] = __shfl_sync(mask, w, src, G);
-        if (j < cnt) {
+        if (j < cnt && (!NZ || ww[t] != 0.f)) {
 #pragma unroll
           for (int v = 0; v < V; ++v) x[t][v] = ld_row<HINT>(X + int64_t(cj) * ROW4 + v * G + lane);
         } else {
@@ -149,13 +155,14 @@ struct SpmmSched {
 // partial sum; for rows up to CGX_HUGE_ROW the chunk that arrives last (per-row counter, release /
 // acquire through __threadfence) adds the partials IN CHUNK ORDER and runs the epilogue, so the
 // result does not depend on which chunk happened to be last.
-template <int G, int V, int UNR, int HINT, int MINB>
+template <int G, int V, int UNR, int HINT, int MINB, bool NZ = false>
 __global__ void __launch_bounds__(SP_THREADS, MINB) k_spmm(const int64_t* __restrict__ indptr,
                                                            const int32_t* __restrict__ idx,
                                                            const float* __restrict__ val, int32_t n_rows,
                                                            SpmmSched sc, const float4* __restrict__ X,
                                                            float4* __restrict__ Y, const float4* ACC_IN,
-                                                           float4* ACC_OUT, float acc_scale, float4* partial) {
+                                                           float4* ACC_OUT, float acc_scale, float4* partial,
+                                                           const uint8_t* __restrict__ nz) {
   constexpr int ROW4 = G * V;
   // Programmatic dependent launch: let the next kernel of the stream start its own prologue now, and run
   // THIS kernel's prologue (schedule lookups, first batch of column ids / values -- graph constants) while the
@@ -182,7 +189,7 @@ __global__ void __launch_bounds__(SP_THREADS, MINB) k_spmm(const int64_t* __rest
       wf = __ldg(val + begin + lane);
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    gather_batches<G, V, UNR, HINT>(idx, val, begin, end, X, lane, mask, cf, wf, acc);
+    gather_batches<G, V, UNR, HINT, NZ>(idx, val, begin, end, X, lane, mask, cf, wf, acc, nz);
 #pragma unroll
     for (int v = 0; v < V; ++v) __stcg(partial + item * ROW4 + v * G + lane, acc[v]);
     if (k < sc.n_huge) return;            // combined by k_spmm_finish
@@ -215,7 +222,7 @@ __global__ void __launch_bounds__(SP_THREADS, MINB) k_spmm(const int64_t* __rest
     wf = __ldg(val + begin + lane);
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  gather_batches<G, V, UNR, HINT>(idx, val, begin, end, X, lane, mask, cf, wf, acc);
+  gather_batches<G, V, UNR, HINT, NZ>(idx, val, begin, end, X, lane, mask, cf, wf, acc, nz);
   epilogue<G, V>(row, lane, acc, Y, ACC_IN, ACC_OUT, acc_scale);
 }
 
@@ -332,6 +339,23 @@ __global__ void k_scale(const float4* __restrict__ in, float4* __restrict__ out,
   if (p < n4) out[p] = scale4(in[p], s);
 }
 
+// flags[r] = 1 when row r of X (row4 float4 per row) has a non-zero entry (-0 counts as zero); flags pre-zeroed
+__global__ void k_row_flags(const uint4* __restrict__ X, int64_t n4, int32_t row4, uint8_t* __restrict__ flags) {
+  const int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= n4) return;
+  const uint4 v = X[p];
+  if ((v.x | v.y | v.z | v.w) & 0x7fffffffu) flags[p / row4] = 1;
+}
+
+static int row_flags(const float* X, int64_t n_rows, int32_t d, uint8_t* flags, cudaStream_t stream) {
+  CGX_CUDA(cudaMemsetAsync(flags, 0, size_t(n_rows), stream));
+  const int64_t n4 = n_rows * d / 4;
+  if (n4 == 0) return CGX_OK;
+  k_row_flags<<<(unsigned)ceil_div(n4, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(X), n4, d / 4, flags);
+  CGX_LAUNCH_CHECK();
+  return CGX_OK;
+}
+
 static int spmm_env(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
@@ -352,10 +376,10 @@ static int spmm_waves() {
   return v < 1 ? 1 : v;
 }
 
-template <int G, int V, int UNR, int HINT, int MINB>
+template <int G, int V, int UNR, int HINT, int MINB, bool NZ = false>
 static int launch_spmm(const cgx_csr* m, const float* val, const float* X, float* Y, const float* ACC_IN,
                        float* ACC_OUT, float acc_scale, void* workspace, size_t workspace_bytes,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, const uint8_t* nz = nullptr) {
   constexpr int GROUPS = SP_THREADS / G;
   float4* partial = nullptr;
   if (m->n_long > 0) {
@@ -366,7 +390,7 @@ static int launch_spmm(const cgx_csr* m, const float* val, const float* X, float
   }
   SpmmSched sc{m->perm, m->chunk_ptr, m->chunk_row, m->arrive, m->n_long, m->n_chunks, m->n_huge};
   const int64_t items = int64_t(m->n_chunks) + (m->n_rows - m->n_long);
-  if (m->work != nullptr && spmm_persistent()) {
+  if (!NZ && m->work != nullptr && spmm_persistent()) {
     int64_t blocks = ceil_div(items, GROUPS);
     const int64_t resident = int64_t(148) * MINB * spmm_waves();     // CTAs that fit the chip at once (x waves)
     if (blocks > resident) blocks = resident;
@@ -385,10 +409,10 @@ static int launch_spmm(const cgx_csr* m, const float* val, const float* X, float
     attr[0].val.programmaticStreamSerializationAllowed = spmm_pdl() ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CGX_CUDA(cudaLaunchKernelEx(&cfg, k_spmm<G, V, UNR, HINT, MINB>, m->indptr, m->idx, val, m->n_rows, sc,
+    CGX_CUDA(cudaLaunchKernelEx(&cfg, k_spmm<G, V, UNR, HINT, MINB, NZ>, m->indptr, m->idx, val, m->n_rows, sc,
                                 reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(Y),
                                 reinterpret_cast<const float4*>(ACC_IN), reinterpret_cast<float4*>(ACC_OUT), acc_scale,
-                                partial));
+                                partial, nz));
   }
   CGX_LAUNCH_CHECK();
   if (m->n_huge > 0) {
@@ -411,7 +435,8 @@ static int spmm_variant() {
 #define CGX_SPMM_ARGS m, val, X, Y, ACC_IN, ACC_OUT, acc_scale, ws, ws_bytes, stream
 
 static int spmm_dispatch(const cgx_csr* m, int use_bwd, int32_t d, const float* X, float* Y, const float* ACC_IN,
-                         float* ACC_OUT, float acc_scale, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                         float* ACC_OUT, float acc_scale, void* ws, size_t ws_bytes, cudaStream_t stream,
+                         const uint8_t* nz = nullptr) {
   CGX_REQUIRE(m && m->indptr && m->perm && (m->nnz == 0 || (m->idx && m->val_fwd && m->val_bwd)) && X, CGX_ERR_ARG,
               "spmm: NULL pointer");
   CGX_REQUIRE(m->n_long == 0 || (m->chunk_ptr && m->chunk_row && m->arrive), CGX_ERR_ARG,
@@ -419,6 +444,16 @@ static int spmm_dispatch(const cgx_csr* m, int use_bwd, int32_t d, const float* 
   CGX_REQUIRE(Y || ACC_OUT, CGX_ERR_ARG, "spmm: no output requested");
   const float* val = use_bwd ? m->val_bwd : m->val_fwd;
   if (m->n_rows == 0) return CGX_OK;
+  if (nz != nullptr) {   // sparse input rows: the default geometry of every width, row loads predicated on nz
+    switch (d) {
+      case 16: return launch_spmm<4, 1, 4, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
+      case 32: return launch_spmm<8, 1, 8, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
+      case 64: return launch_spmm<16, 1, 8, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
+      case 128: return launch_spmm<32, 1, 8, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
+      case 256: return launch_spmm<32, 2, 4, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
+      default: break;
+    }
+  }
   const int variant = spmm_variant();
   switch (d) {
     case 16: return launch_spmm<4, 1, 4, HINT_NC, 4>(CGX_SPMM_ARGS);
@@ -467,11 +502,24 @@ extern "C" int cgx_spmm(const cgx_csr* m, int use_bwd_values, int32_t d, const f
                        static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int cgx_spmm_sparse_rows(const cgx_csr* m, int use_bwd_values, int32_t d, const float* X,
+                                    const uint8_t* x_row_nonzero, float* Y, const float* ACC_IN, float* ACC_OUT,
+                                    float acc_scale, void* workspace, size_t workspace_bytes, void* stream) {
+  CGX_REQUIRE(x_row_nonzero != nullptr, CGX_ERR_ARG, "spmm_sparse_rows: NULL flags");
+  return spmm_dispatch(m, use_bwd_values, d, X, Y, ACC_IN, ACC_OUT, acc_scale, workspace, workspace_bytes,
+                       static_cast<cudaStream_t>(stream), x_row_nonzero);
+}
+
+extern "C" int cgx_row_flags(const float* X, int64_t n_rows, int32_t d, uint8_t* flags, void* stream) {
+  CGX_REQUIRE(X && flags && n_rows >= 0 && d > 0 && d % 4 == 0, CGX_ERR_ARG, "row_flags: bad argument");
+  return row_flags(X, n_rows, d, flags, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" size_t cgx_propagate_workspace_bytes(const cgx_csr* by_user, const cgx_csr* by_item, int32_t d) {
   if (!by_user || !by_item) return 0;
   size_t long_ws = spmm_ws(by_user, d) > spmm_ws(by_item, d) ? spmm_ws(by_user, d) : spmm_ws(by_item, d);
   return 2 * (align_up(size_t(by_user->n_rows) * d * 4) + align_up(size_t(by_item->n_rows) * d * 4)) + long_ws +
-         256;
+         align_up(size_t(by_user->n_rows)) + align_up(size_t(by_item->n_rows)) + 256;
 }
 
 extern "C" int cgx_propagate_fwd(const cgx_csr* by_user, const cgx_csr* by_item, int order, int32_t K, int32_t d,
@@ -531,29 +579,43 @@ extern "C" int cgx_propagate_bwd(const cgx_csr* by_user, const cgx_csr* by_item,
   void* lw = ws.take<char>(lws);
   CGX_REQUIRE(ws.ok, CGX_ERR_WORKSPACE, "propagate_bwd: workspace too small");
   const float s = 1.0f / float(K + 1);
+  // The incoming gradient has non-zero rows only where the batch touched the tables (<= batch users,
+  // <= 2 * batch items): the products that gather g_u / g_i directly skip the zero rows (row flags, 1 byte per
+  // row).  After one product the adjoint is dense.  CGX_SPARSE_BWD=0 switches this off.
+  static const bool sparse = spmm_env("CGX_SPARSE_BWD", 1) != 0;
+  uint8_t* nz_u = ws.take<uint8_t>(U);
+  uint8_t* nz_i = ws.take<uint8_t>(I);
+  CGX_REQUIRE(ws.ok, CGX_ERR_WORKSPACE, "propagate_bwd: workspace too small");
   // Work with the unscaled adjoints bu' = bu / s, bi' = bi / s (the recurrences are linear):
   //   Jacobi: (bu', bi') <- (g_u + C^T bi', g_i + A^T bu');  Gauss-Seidel: bi' = g_i + A^T bu'; bu' = g_u + C^T bi'
   // and fold s into the last product's epilogue.
   if (order == CGX_ORDER_JACOBI) {
     const float* bu = g_u;
     const float* bi = g_i;
+    if (sparse) {
+      CGX_TRY(row_flags(g_u, U, d, nz_u, stream));
+      CGX_TRY(row_flags(g_i, I, d, nz_i, stream));
+    }
     for (int k = 0; k < K; ++k) {
       const bool last = k == K - 1;
       float* nu = last ? d_e0_u : ub[k & 1];
       float* ni = last ? d_e0_i : ib[k & 1];
       const float sc = last ? s : 1.0f;
-      CGX_TRY(spmm_dispatch(by_user, 1, d, bi, nullptr, g_u, nu, sc, lw, lws, stream));  // g_u + C^T bi
-      CGX_TRY(spmm_dispatch(by_item, 1, d, bu, nullptr, g_i, ni, sc, lw, lws, stream));  // g_i + A^T bu
+      const bool sp = sparse && k == 0;
+      CGX_TRY(spmm_dispatch(by_user, 1, d, bi, nullptr, g_u, nu, sc, lw, lws, stream, sp ? nz_i : nullptr));  // g_u + C^T bi
+      CGX_TRY(spmm_dispatch(by_item, 1, d, bu, nullptr, g_i, ni, sc, lw, lws, stream, sp ? nz_u : nullptr));  // g_i + A^T bu
       bu = nu;
       bi = ni;
     }
   } else {
     const float* bu = g_u;
+    if (sparse) CGX_TRY(row_flags(g_u, U, d, nz_u, stream));
     for (int k = 0; k < K; ++k) {
       const bool last = k == K - 1;
       float* ni = ib[0];
       float* nu = last ? d_e0_u : ub[k & 1];
-      CGX_TRY(spmm_dispatch(by_item, 1, d, bu, nullptr, g_i, ni, 1.0f, lw, lws, stream));            // bi'
+      CGX_TRY(spmm_dispatch(by_item, 1, d, bu, nullptr, g_i, ni, 1.0f, lw, lws, stream,
+                            sparse && k == 0 ? nz_u : nullptr));                                      // bi'
       CGX_TRY(spmm_dispatch(by_user, 1, d, ni, nullptr, g_u, nu, last ? s : 1.0f, lw, lws, stream));  // bu'
       bu = nu;
     }

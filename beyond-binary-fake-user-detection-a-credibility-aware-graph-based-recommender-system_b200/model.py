@@ -66,6 +66,28 @@ def spmm(csr, x, use_bwd_values=False):
     return y
 
 
+def row_flags(x):
+    """uint8[n_rows]: 1 where the row of x has a non-zero entry (cgx_row_flags)."""
+    x = _f32c(x)
+    flags = torch.empty(x.shape[0], dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().cgx_row_flags(ptr(x), x.shape[0], x.shape[1], ptr(flags), stream_ptr(x.device)))
+    return flags
+
+
+def spmm_sparse_rows(csr, x, flags=None, use_bwd_values=False):
+    """spmm() for an x whose rows are mostly zero: rows with flags == 0 are not gathered (same result)."""
+    x = _f32c(x)
+    flags = row_flags(x) if flags is None else flags
+    d = x.shape[1]
+    y = torch.empty(csr.n_rows, d, dtype=torch.float32, device=x.device)
+    ws = workspace(lib().cgx_spmm_workspace_bytes(csr.ref(), d), x.device)
+    with torch.cuda.device(x.device):
+        check(lib().cgx_spmm_sparse_rows(csr.ref(), int(use_bwd_values), d, ptr(x), ptr(flags), ptr(y), None, None,
+                                         1.0, ptr(ws), ws.numel(), stream_ptr(x.device)))
+    return y
+
+
 def bpr_plan(graph: CredGraph, users, pos, neg, plan=None):
     """Sorted (row, entry) keys of a triple batch: the scatter plan of the fused loss (indices only)."""
     dev = graph.device

@@ -156,12 +156,14 @@ class BackendBase:
 
 class CudaBackend(BackendBase):
     """The two products of one shard, on libcredgcn.so."""
+    supports_sparse_rows = True
 
     def __init__(self, graph: CredGraph):
         self.graph = graph
         self._ws = {}
 
-    def _spmm(self, csr, x, bwd, y=None, acc_in=None, acc_out=None, scale=1.0):
+    def _spmm(self, csr, x, bwd, y=None, acc_in=None, acc_out=None, scale=1.0, sparse=False):
+        """sparse=True: x is a loss gradient (rows mostly zero) -- flag its rows and skip the zero ones."""
         x = x.contiguous()
         d = x.shape[1]
         if y is None and acc_out is None:
@@ -171,24 +173,34 @@ class CudaBackend(BackendBase):
             self._ws[key] = workspace(lib().cgx_spmm_workspace_bytes(csr.ref(), d), x.device)
         ws = self._ws[key]
         with torch.cuda.device(x.device):
-            check(lib().cgx_spmm(csr.ref(), int(bwd), d, ptr(x), ptr(y), ptr(acc_in), ptr(acc_out), float(scale),
-                                 ptr(ws), ws.numel(), stream_ptr(x.device)))
+            if sparse:
+                fkey = ("flags", x.shape[0])
+                if fkey not in self._ws:
+                    self._ws[fkey] = torch.empty(x.shape[0], dtype=torch.uint8, device=x.device)
+                flags = self._ws[fkey]
+                check(lib().cgx_row_flags(ptr(x), x.shape[0], d, ptr(flags), stream_ptr(x.device)))
+                check(lib().cgx_spmm_sparse_rows(csr.ref(), int(bwd), d, ptr(x), ptr(flags), ptr(y), ptr(acc_in),
+                                                 ptr(acc_out), float(scale), ptr(ws), ws.numel(),
+                                                 stream_ptr(x.device)))
+            else:
+                check(lib().cgx_spmm(csr.ref(), int(bwd), d, ptr(x), ptr(y), ptr(acc_in), ptr(acc_out), float(scale),
+                                     ptr(ws), ws.numel(), stream_ptr(x.device)))
         return y if y is not None else acc_out
 
-    def item_rows(self, x_u, bwd=False, out=None):
+    def item_rows(self, x_u, bwd=False, out=None, sparse=False):
         """Partial [I, d]: C x_u (bwd: A^T x_u) summed over THIS shard's users (written into `out` if given)."""
-        return self._spmm(self.graph.by_item, x_u, bwd, y=out)
+        return self._spmm(self.graph.by_item, x_u, bwd, y=out, sparse=sparse)
 
     def user_rows(self, x_i, bwd=False):
         """[U_local, d]: A x_i (bwd: C^T x_i) for this shard's users."""
         return self._spmm(self.graph.by_user, x_i, bwd)
 
-    def user_rows_acc(self, x_i, bwd, acc_in, scale, need_y=True):
+    def user_rows_acc(self, x_i, bwd, acc_in, scale, need_y=True, sparse=False):
         """Same product with the running sum / gradient seed fused into the SpMM epilogue."""
         csr = self.graph.by_user
         y = torch.empty(csr.n_rows, x_i.shape[1], dtype=torch.float32, device=x_i.device) if need_y else None
         acc = torch.empty(csr.n_rows, x_i.shape[1], dtype=torch.float32, device=x_i.device)
-        self._spmm(csr, x_i, bwd, y=y, acc_in=acc_in.contiguous(), acc_out=acc, scale=scale)
+        self._spmm(csr, x_i, bwd, y=y, acc_in=acc_in.contiguous(), acc_out=acc, scale=scale, sparse=sparse)
         return y, acc
 
 
@@ -202,10 +214,15 @@ class ShardedPropagation:
         self.b, self.K, self.order, self.group = backend, int(num_layers), order, group
         self.ex = exchange or CollectiveExchange(group)
 
-    def _item_exchange(self, x_u, bwd, shape):
-        """Partial item table of this shard -> whole item table (one exchange)."""
+    def _hint(self, sparse):
+        """`sparse=True` keyword for backends that can skip zero rows of the input (an optimisation hint)."""
+        return {"sparse": True} if sparse and getattr(self.b, "supports_sparse_rows", False) else {}
+
+    def _item_exchange(self, x_u, bwd, shape, sparse=False):
+        """Partial item table of this shard -> whole item table (one exchange).  sparse: x_u is the loss
+        gradient itself (rows mostly zero)."""
         buf = self.ex.partial_buffer(shape, x_u.device)
-        res = self.b.item_rows(x_u, bwd, out=buf)
+        res = self.b.item_rows(x_u, bwd, out=buf, **self._hint(sparse))
         if res is not buf:                      # backends without an `out` argument return a fresh tensor
             buf.copy_(res)
         return self.ex.reduce(buf)
@@ -230,15 +247,15 @@ class ShardedPropagation:
         s = 1.0 / (self.K + 1)
         if self.order == "gs":
             bu = g_u
-            for k in range(self.K):
-                bi = self._item_exchange(bu, True, tuple(g_i_total.shape)).add_(g_i_total)
+            for k in range(self.K):   # only the first product gathers the (row-sparse) loss gradient itself
+                bi = self._item_exchange(bu, True, tuple(g_i_total.shape), sparse=k == 0).add_(g_i_total)
                 _, bu = self.b.user_rows_acc(bi, True, g_u, s if k == self.K - 1 else 1.0, need_y=False)
             return bu, g_i_total.mul(s)
         bu, bi = g_u, g_i_total
         for k in range(self.K):
             last = k == self.K - 1
-            _, nu = self.b.user_rows_acc(bi, True, g_u, s if last else 1.0, need_y=False)
-            ni = self._item_exchange(bu, True, tuple(g_i_total.shape)).add_(g_i_total)
+            _, nu = self.b.user_rows_acc(bi, True, g_u, s if last else 1.0, need_y=False, **self._hint(k == 0))
+            ni = self._item_exchange(bu, True, tuple(g_i_total.shape), sparse=k == 0).add_(g_i_total)
             bu, bi = nu, (ni.mul_(s) if last else ni)
         return bu, bi
 

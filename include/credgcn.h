@@ -157,6 +157,15 @@ int cgx_spmm(const cgx_csr* m, int use_bwd_values, int32_t d, const float* X, fl
              const float* ACC_IN, float* ACC_OUT, float acc_scale,
              void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same product when most rows of X are zero (the loss gradient touches <= 3 * batch rows, so the first
+ * adjoint product of loss.backward() -- CU:651, V2:862 -- gathers mostly zeros): x_row_nonzero[c] == 0
+ * promises that row c of X is all zero, and such rows are not loaded.  Same result as cgx_spmm.
+ * cgx_row_flags writes the flags for a table (1 = the row has a non-zero entry; -0.0 counts as zero). */
+int cgx_spmm_sparse_rows(const cgx_csr* m, int use_bwd_values, int32_t d, const float* X,
+                         const uint8_t* x_row_nonzero, float* Y, const float* ACC_IN, float* ACC_OUT,
+                         float acc_scale, void* workspace, size_t workspace_bytes, void* stream);
+int cgx_row_flags(const float* X, int64_t n_rows, int32_t d, uint8_t* flags, void* stream);
+
 size_t cgx_propagate_workspace_bytes(const cgx_csr* by_user, const cgx_csr* by_item, int32_t d);
 
 /* Forward: final = mean over layers 0..K.  order JACOBI = CU:429-437, GS = V2:482-486.

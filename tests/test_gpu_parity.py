@@ -673,3 +673,29 @@ def test_device_metrics_reject_bad_cutoffs(cg):
     from credgcn._lib import CgxError
     with pytest.raises(CgxError):
         ev.metrics_device(ranked, np.arange(4), None, 50, [20], "sampled", gt_single_dev=torch.zeros(4, device=DEV))
+
+
+@pytest.mark.parametrize("d", [16, 32, 64, 128, 256])
+def test_sparse_row_spmm_equals_dense_spmm_bitwise(cg, d):
+    """cgx_spmm_sparse_rows (zero rows of X skipped by flag) returns the bits of cgx_spmm, for short, chunked
+    (> 256 nnz) and huge (> 16384 nnz) rows, both row orders, forward and adjoint values."""
+    sg = cg["synth"].make_graph("C1", duplicate_edges=300)
+    gr = cg["graph"].build_graph(sg.train_edges, sg.num_users, sg.num_items, sg.cred, "v2", DEV)
+    m = cg["model"]
+    gen = torch.Generator(device=DEV).manual_seed(d)
+    for csr, n_in in ((gr.by_user, sg.num_items), (gr.by_item, sg.num_users)):
+        x = torch.randn(n_in, d, device=DEV, generator=gen)
+        keep = torch.rand(n_in, device=DEV, generator=gen) < 0.1
+        x[~keep] = 0.0
+        x[5] = -0.0                                                   # negative zeros are zeros
+        flags = m.row_flags(x)
+        assert torch.equal(flags.bool(), (x != 0).any(1))
+        for bwd in (False, True):
+            want = m.spmm(csr, x, use_bwd_values=bwd)
+            got = m.spmm_sparse_rows(csr, x, flags, use_bwd_values=bwd)
+            assert torch.equal(got.view(torch.int32), want.view(torch.int32))
+        # all-zero and all-dense inputs
+        z = torch.zeros_like(x)
+        assert not m.spmm_sparse_rows(csr, z).any()
+        xd = torch.randn(n_in, d, device=DEV, generator=gen)
+        assert torch.equal(m.spmm_sparse_rows(csr, xd), m.spmm(csr, xd))
