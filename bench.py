@@ -387,6 +387,8 @@ def main():
             "traffic_source": "ncu --set full capture of k_spmm, profiles/r1_traffic.json" if traffic else None,
             "algorithmic_bytes_per_step": alg, "algorithmic_bytes_per_launch": alg / n_spmm,
             "avg_launch_ms": prop_ms / n_spmm,
+            "sparse_first_adjoint": os.environ.get("CGX_SPARSE_BWD", "1") != "0",   # that launch (1 of 4K; 2 in
+            # Jacobi order) skips the zero rows of the loss gradient; the algorithmic bytes still count it in full
             "note": (f"embedding tables are {table_mb:.0f} MB: they fit the 126 MB L2, so the gather-model figure "
                      "can exceed the HBM peak" if table_mb < 100 else
                      f"embedding tables are {table_mb:.0f} MB (>> L2): HBM bound; the gather model counts every "
