@@ -20,8 +20,16 @@
 //     means nobody writes a rank's `out` region before that rank's earlier kernels (the consumers of the
 //     previous result) have finished: regions can be re-used immediately.  Two regions are kept only so that
 //     the result of the previous exchange stays readable (the Jacobi order needs it).
+//   * small worlds (<= CGX_P2P_ONESHOT_MAX ranks, default 2) use the ONE-SHOT form instead: after barrier A every
+//     rank pulls ALL partials and sums the whole table locally, in rank order (same bits on every rank), into its
+//     own out[parity]; no remote store, no barrier B.  It moves (R-1) x the table per rank instead of
+//     2 (R-1)/R x, but saves a system-scope fence, a barrier and an NVLink round trip -- at 10 MB and 2 ranks the
+//     exchange is latency-bound, not wire-bound.  A peer's in[parity] is next overwritten two exchanges later,
+//     i.e. after that peer has passed barrier A of the exchange in between, which this rank only signals once
+//     this kernel has completed.
 //   * the epoch is a device-side counter (cgx_tick before every exchange) that advances identically on all
 //     ranks (the propagation schedule is deterministic), so a whole step can be replayed as a CUDA graph.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -54,7 +62,8 @@ __device__ __forceinline__ float4 ld_peer(const float4* p) {   // written by ano
 // flag page layout (uint32): [0 .. R) barrier A slots, [R .. 2R) barrier B slots, [2R] CTA arrival counter
 __global__ void __launch_bounds__(P2P_THREADS) k_p2p_allreduce(P2PPeers peers, int rank, int world, size_t in_off,
                                                                size_t out_off, size_t flag_off, int64_t n4,
-                                                               const unsigned long long* __restrict__ epoch_dev) {
+                                                               const unsigned long long* __restrict__ epoch_dev,
+                                                               int one_shot) {
   const uint32_t epoch = uint32_t(*epoch_dev);   // device-side counter: the launch is replayable in a CUDA graph
   uint32_t* my_flags = reinterpret_cast<uint32_t*>(peers.base[rank] + flag_off);
   // ---- barrier A: all partials complete ----
@@ -66,9 +75,9 @@ __global__ void __launch_bounds__(P2P_THREADS) k_p2p_allreduce(P2PPeers peers, i
     while (ld_acquire_sys(my_flags + threadIdx.x) < epoch) __nanosleep(64);
   }
   __syncthreads();
-  // ---- reduce-scatter + all-gather of my slice ----
-  const int64_t per = (n4 + world - 1) / world;
-  const int64_t lo = int64_t(rank) * per;
+  // ---- reduce-scatter + all-gather of my slice (one-shot: the whole table, stored locally only) ----
+  const int64_t per = one_shot ? n4 : (n4 + world - 1) / world;
+  const int64_t lo = one_shot ? 0 : int64_t(rank) * per;
   const int64_t hi = lo + per < n4 ? lo + per : n4;
   // P2P_UNROLL x world peer loads are issued before the first add: NVLink round trips (~2 us) overlap
   constexpr int P2P_UNROLL = 4;
@@ -97,10 +106,16 @@ __global__ void __launch_bounds__(P2P_THREADS) k_p2p_allreduce(P2PPeers peers, i
 #pragma unroll
     for (int t = 0; t < P2P_UNROLL; ++t) {
       const int64_t i = i0 + t * stride;
-      if (i < hi)
-        for (int p = 0; p < world; ++p) reinterpret_cast<float4*>(peers.base[p] + out_off)[i] = acc[t];
+      if (i < hi) {
+        if (one_shot) {
+          reinterpret_cast<float4*>(peers.base[rank] + out_off)[i] = acc[t];
+        } else {
+          for (int p = 0; p < world; ++p) reinterpret_cast<float4*>(peers.base[p] + out_off)[i] = acc[t];
+        }
+      }
     }
   }
+  if (one_shot) return;
   // ---- barrier B: every slice delivered ----
   __threadfence_system();
   __syncthreads();
@@ -167,12 +182,15 @@ extern "C" int cgx_comm_allreduce(int rank, int world, void* const* peer_bases, 
     peers.base[p] = static_cast<char*>(peer_bases[p]);
   }
   const int64_t n4 = n_floats / 4;
-  const int64_t per = ceil_div(n4, world);
+  static const int one_shot_max = getenv("CGX_P2P_ONESHOT_MAX") ? atoi(getenv("CGX_P2P_ONESHOT_MAX")) : 2;
+  const int one_shot = world <= one_shot_max ? 1 : 0;
+  const int64_t per = one_shot ? n4 : ceil_div(n4, world);
   int64_t blocks = ceil_div(per, P2P_THREADS * 4);
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
   k_p2p_allreduce<<<(unsigned)blocks, P2P_THREADS, 0, stream>>>(peers, rank, world, in_off, out_off, flag_off, n4,
-                                                             reinterpret_cast<const unsigned long long*>(epoch_dev));
+                                                             reinterpret_cast<const unsigned long long*>(epoch_dev),
+                                                             one_shot);
   CGX_LAUNCH_CHECK();
   return CGX_OK;
 }

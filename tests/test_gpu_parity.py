@@ -699,3 +699,41 @@ def test_sparse_row_spmm_equals_dense_spmm_bitwise(cg, d):
         assert not m.spmm_sparse_rows(csr, z).any()
         xd = torch.randn(n_in, d, device=DEV, generator=gen)
         assert torch.equal(m.spmm_sparse_rows(csr, xd), m.spmm(csr, xd))
+
+
+def test_ragged_last_batch_after_capture(cg):
+    """An epoch ends with a short batch (lightgcn_cu.py:608-610 slices train_users[start:start + batch]): a
+    captured TrainStep takes it through the eager path with the same device counters, so a run of full + short
+    batches equals the all-eager run bit for bit.  Batch sizes 1 and 33 (not a multiple of a warp) included."""
+    sg = cg["synth"].make_graph("C1")
+    gr = cg["graph"].build_graph(sg.train_edges, sg.num_users, sg.num_items, sg.cred, "v2", DEV)
+    users = torch.nonzero(gr.deg_u > 0).reshape(-1)
+    batches = [users[:256], users[256:512], users[512:545], users[545:546]]
+    outs = []
+    for use_graph in (False, True):
+        torch.manual_seed(3)
+        net = cg["model"].LightGCN(sg.num_users, sg.num_items, 32, 2, gr.operator("A"), gr.operator("C")).to(DEV)
+        st = cg["model"].TrainStep(net, lr=1e-2, reg_weight=1e-4, sampler=cg["sampler"].TripleSampler(gr, 0.7, 0.75, 50, seed=9))
+        if use_graph:
+            st.capture(256)
+        losses = [float(st.step(b).item()) for b in batches]
+        outs.append((losses, net.user_emb.weight.detach().clone(), net.item_emb.weight.detach().clone()))
+    assert outs[0][0] == outs[1][0] and all(np.isfinite(outs[0][0]))
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+
+
+def test_graph_without_edges(cg):
+    """E = 0: every operator is empty, the layers above 0 vanish (final = E0 / (K + 1)), nothing is masked in
+    the ranking, and the loss gradient reduces to the L2 term."""
+    U, I, d, K = 7, 45, 16, 3
+    gr = cg["graph"].build_graph(np.zeros((2, 0), np.int32), U, I, np.linspace(0, 1, U, dtype=np.float32), "v2", DEV)
+    assert gr.nnz == 0 and int(gr.deg_u.sum()) == 0 and int(gr.deg_i.sum()) == 0
+    torch.manual_seed(0)
+    eu, ei = torch.randn(U, d, device=DEV), torch.randn(I, d, device=DEV)
+    fu, fi = cg["model"].propagate_forward(gr, eu, ei, K, "gs")
+    assert torch.equal(fu, eu * (1.0 / (K + 1))) and torch.equal(fi, ei * (1.0 / (K + 1)))
+    gu, gi = cg["model"].propagate_backward(gr, torch.ones_like(eu), torch.ones_like(ei), K, "jacobi")
+    assert torch.equal(gu, torch.full_like(eu, 1.0 / (K + 1))) and torch.equal(gi, torch.full_like(ei, 1.0 / (K + 1)))
+    ids, sc = cg["evaluate"].topk_device(fu, fi, torch.arange(U, device=DEV), (gr.samp_indptr, gr.samp_idx), 10)
+    want = torch.argsort(-(fu @ fi.T), dim=1, stable=True)[:, :10]
+    assert torch.equal(ids.long(), want)
