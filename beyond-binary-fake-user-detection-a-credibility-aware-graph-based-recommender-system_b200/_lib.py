@@ -86,6 +86,7 @@ _SIGNATURES = {
     "cgx_score_candidates": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "cgx_eval_candidates": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_uint64, _P, _P]),
     "cgx_rank_candidates": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P]),
+    "cgx_eval_topk_uses_tensor_cores": (C.c_int, [C.c_int32, C.c_int32, C.c_int]),
     "cgx_eval_metrics_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "cgx_eval_metrics": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, _P, C.c_int32, _P, C.c_int32, _P, C.c_int64,
                                    _P, _P, _P, _P, C.c_size_t, _P]),

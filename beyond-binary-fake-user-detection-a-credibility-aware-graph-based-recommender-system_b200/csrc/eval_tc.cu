@@ -7,8 +7,8 @@
 // path (2 * U_eval * I * d FLOPs).
 //
 // Numerics.  The reference scores in fp32.  precision = BF16X3 splits every fp32 value into
-// hi + lo bf16 parts and contracts [a_hi | a_hi | a_lo] . [b_hi | b_lo | b_hi] (K' = 3d) on the
-// tensor cores: |error| <= ~2^-16 |a||b|.  The tensor-core pass only SELECTS K' = K + margin
+// hi + lo bf16 parts, stored once as [hi | lo], and accumulates a_hi.b_hi + a_lo.b_hi + a_hi.b_lo (3d
+// multiply-adds per score) on the tensor cores: |error| <= ~2^-16 |a||b|.  The tensor-core pass only SELECTS K' = K + margin
 // candidates per user; k_rescore then recomputes their scores exactly as the fp32 kernel does (same
 // fmaf order -> same bits), sorts by (score desc, id asc) and proves the top K complete:
 // if exact_score[K-1] > approx_score[K'-1] + eps(user) no item outside the candidate list can reach
@@ -22,14 +22,14 @@
 //   warps 1-4 (and 5-8 when two epilogue groups are used: group g owns accumulator stage g)
 //               epilogue: tcgen05.ld 32x32b.x16 -> registers, predicated append of scores >= the row
 //               threshold, warp-uniform drain into the row's K' kept candidates (one thread per user)
-//   next 4      producers: cp.async (16 B, L2-only) the next 128-item tile of the bf16 item table into
-//               shared memory in the canonical K-major SWIZZLE_128B UMMA layout (64-column k-blocks,
-//               128-byte rows, 16-byte chunks XOR-ed with row%8 -- what TMA would write), so that a
-//               row's 8 chunks are one coalesced 128-byte global read AND one conflict-free shared
-//               write; then fence to the async proxy and arrive on the stage's mbarrier
+//   next 4      producers: cp.async (16 B, L2-only) the item operand into a ring of 3..8 shared-memory stages,
+//               one 64-column k-block (128 items x 128 B) per stage, in the canonical K-major SWIZZLE_128B
+//               UMMA layout (16-byte chunks XOR-ed with row%8 -- what TMA would write), so that a row's 8
+//               chunks are one coalesced 128-byte global read AND one conflict-free shared write; then fence
+//               to the async proxy and arrive on the stage's mbarrier.  The ring is k-block granular so that
+//               wide tables fit: d = 128 with BF16X3 needs 64 KB per item tile next to 64 KB of users.
 //   last 4      mask builders: per user row, 128 "is a train item" bits per item tile, a few tiles ahead
-// Two smem stages for B and two 128-column TMEM accumulators: the MMA of tile j+1 overlaps the
-// epilogue of tile j.
+// Two 128-column TMEM accumulators: the MMA of tile j+1 overlaps the epilogue of tile j.
 #include <cuda_bf16.h>
 #include <float.h>
 #include <stdlib.h>
@@ -44,7 +44,8 @@ int eval_fp32_rows(const int64_t* users, const int32_t* row_list, const int32_t*
 
 constexpr int TC_M = 128;          // users per CTA
 constexpr int TC_N = 128;          // items per tile
-constexpr int TC_STAGES = 2;
+constexpr int TC_MAX_STAGES = 8;   // B ring: up to 8 stages of one 64-column k-block (128 items x 128 B = 16 KB)
+constexpr int TC_KB_BYTES = TC_N * 128;
 constexpr int TC_MASK_RING = 4;    // train-item bitmasks of that many item tiles are built ahead of the epilogue
 constexpr float TC_MASKED = -1e9f;
 
@@ -126,26 +127,22 @@ __device__ __forceinline__ bool tc_in_row(const int32_t* __restrict__ idx, int64
   return lo < end && __ldg(idx + lo) == item;
 }
 
-// ---- operand preparation: fp32 rows -> bf16 [hi | hi | lo] (users) / [hi | lo | hi] (items) ------
+// ---- operand preparation: fp32 rows -> bf16 [hi (Dp columns) | lo (Dp columns)], Dp = d rounded up to 64 ------
 __global__ void k_tc_convert(const float* __restrict__ src, const int64_t* __restrict__ rows, int64_t n_rows,
-                             int32_t d, int parts, int Kp, int is_item, __nv_bfloat16* __restrict__ dst,
+                             int32_t d, int parts, int Dp, __nv_bfloat16* __restrict__ dst,
                              float* __restrict__ norms, unsigned int* __restrict__ max_norm_bits) {
   const int64_t r = int64_t(blockIdx.x) * (blockDim.x / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= n_rows) return;
   const int64_t sr = rows ? rows[r] : r;
-  for (int c = parts * d + lane; c < Kp; c += 32) dst[r * Kp + c] = __float2bfloat16_rn(0.f);   // pad to 64 columns
+  const int Kp = parts * Dp;
   float ss = 0.f;
-  for (int c = lane; c < d; c += 32) {
-    const float x = src[sr * d + c];
+  for (int c = lane; c < Dp; c += 32) {
+    const float x = c < d ? src[sr * d + c] : 0.f;      // columns d..Dp of every part are zero padding
     ss = fmaf(x, x, ss);
     const __nv_bfloat16 hi = __float2bfloat16_rn(x);
     dst[r * Kp + c] = hi;
-    if (parts == 3) {
-      const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-      dst[r * Kp + d + c] = is_item ? lo : hi;
-      dst[r * Kp + 2 * d + c] = is_item ? hi : lo;
-    }
+    if (parts == 2) dst[r * Kp + Dp + c] = __float2bfloat16_rn(x - __bfloat162float(hi));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
@@ -164,7 +161,7 @@ template <int KC, int BC, int NG>
 __global__ void __launch_bounds__(32 * (9 + 4 * NG), 1) k_eval_umma(const __nv_bfloat16* __restrict__ Au,   // [n_users, Kp]
                                                              const __nv_bfloat16* __restrict__ Bi,   // [I, Kp]
                                                              const int64_t* __restrict__ users, int64_t n_users,
-                                                             int32_t I, int32_t Kp,
+                                                             int32_t I, int32_t Kp, int32_t nkb, int32_t S,
                                                              const int64_t* __restrict__ tr_indptr,
                                                              const int32_t* __restrict__ tr_idx,
                                                              int32_t* __restrict__ cand_ids,       // [n_users, cand_stride]
@@ -175,30 +172,36 @@ __global__ void __launch_bounds__(32 * (9 + 4 * NG), 1) k_eval_umma(const __nv_b
   extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
   // SWIZZLE_128B atoms must start on 1024-byte boundaries of the shared window
   unsigned char* tc_smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
-  const uint32_t tile_bytes = uint32_t(TC_M) * Kp * 2;           // one operand tile (128 rows x Kp bf16)
+  const uint32_t a_bytes = uint32_t(TC_M) * Kp * 2;              // the users' operand: Kp / 64 k-blocks, [hi | lo]
   unsigned char* smem_a = tc_smem;
-  unsigned char* smem_b = tc_smem + tile_bytes;                   // TC_STAGES tiles
-  float* list_s_all = reinterpret_cast<float*>(smem_b + TC_STAGES * tile_bytes);   // [NG][KC][128] unsorted candidates
+  unsigned char* smem_b = tc_smem + a_bytes;                      // ring of S item k-blocks
+  float* list_s_all = reinterpret_cast<float*>(smem_b + S * TC_KB_BYTES);          // [NG][KC][128] unsorted candidates
   int32_t* list_i_all = reinterpret_cast<int32_t*>(list_s_all + NG * KC * TC_M);   // [NG][KC][128]
   uint2* buf_all = reinterpret_cast<uint2*>(list_i_all + NG * KC * TC_M);          // [NG][BC][128] arrivals (score bits, item)
   uint4* mask_all = reinterpret_cast<uint4*>(buf_all + NG * BC * TC_M);            // [TC_MASK_RING][128] train-item bits
   uint64_t* bars = reinterpret_cast<uint64_t*>(mask_all + TC_MASK_RING * TC_M);
-  uint64_t* full_bar = bars;                 // [TC_STAGES]  producers -> MMA
-  uint64_t* empty_bar = bars + TC_STAGES;    // [TC_STAGES]  MMA (commit) -> producers
-  uint64_t* tfull_bar = bars + 2 * TC_STAGES;   // [2]       MMA (commit) -> epilogue
-  uint64_t* tempty_bar = bars + 2 * TC_STAGES + 2;  // [2]   epilogue -> MMA
-  uint64_t* mfull_bar = bars + 2 * TC_STAGES + 4;                    // [TC_MASK_RING] mask warps -> epilogue
-  uint64_t* mempty_bar = bars + 2 * TC_STAGES + 4 + TC_MASK_RING;    // [TC_MASK_RING] epilogue -> mask warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4 + 2 * TC_MASK_RING);
+  uint64_t* full_bar = bars;                     // [TC_MAX_STAGES]  producers -> MMA
+  uint64_t* empty_bar = bars + TC_MAX_STAGES;    // [TC_MAX_STAGES]  MMA (commit) -> producers
+  uint64_t* tfull_bar = bars + 2 * TC_MAX_STAGES;       // [2]       MMA (commit) -> epilogue
+  uint64_t* tempty_bar = bars + 2 * TC_MAX_STAGES + 2;  // [2]       epilogue -> MMA
+  uint64_t* mfull_bar = bars + 2 * TC_MAX_STAGES + 4;                    // [TC_MASK_RING] mask warps -> epilogue
+  uint64_t* mempty_bar = bars + 2 * TC_MAX_STAGES + 4 + TC_MASK_RING;    // [TC_MASK_RING] epilogue -> mask warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 4 + 2 * TC_MASK_RING);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t u0 = int64_t(blockIdx.x) * TC_M;
   const int n_tiles = (I + TC_N - 1) / TC_N;
-  const int n_kb = Kp / 64;                      // 64-column k-blocks (Kp is padded to a multiple of 64)
-  const int chunks = TC_M * n_kb * 8;            // 16-byte chunks per operand tile
+  // Kp = parts * nkb * 64: hi k-blocks 0..nkb-1, then (BF16X3) lo k-blocks nkb..2 nkb-1 -- both operands.
+  // One item tile = n_units k-blocks of B ("units"), streamed through the ring one k-block at a time so that
+  // the ring does not have to hold a whole tile (d = 128, BF16X3: 64 KB per tile).  Unit u < nkb is b_hi[u] and
+  // multiplies a_hi[u] and a_lo[u]; unit u >= nkb is b_lo[u - nkb] and multiplies a_hi[u - nkb]
+  // (a_hi b_hi + a_lo b_hi + a_hi b_lo; the lo*lo term is below the proof's eps).
+  const int n_units = Kp / 64;
+  const int64_t n_steps = int64_t(n_tiles) * n_units;
+  const int chunks = TC_M * n_units * 8;         // 16-byte chunks of the A operand
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar + s, 128); mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(full_bar + s, 128); mbar_init(empty_bar + s, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + a, 1); mbar_init(tempty_bar + a, 128); }
     for (int m = 0; m < TC_MASK_RING; ++m) { mbar_init(mfull_bar + m, 128); mbar_init(mempty_bar + m, 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -226,24 +229,37 @@ __global__ void __launch_bounds__(32 * (9 + 4 * NG), 1) k_eval_umma(const __nv_b
     // idesc: c=F32 (1<<4), a=BF16 (1<<7), b=BF16 (1<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(TC_N >> 3) << 17) | (uint32_t(TC_M >> 4) << 24);
     const uint32_t a_addr = smem_u32(smem_a);
+    int s = 0;                                      // ring position and its phase bit, advanced without dividing
+    uint32_t ph = 0;
     for (int j = 0; j < n_tiles; ++j) {
-      const int s = j % TC_STAGES, a = j & 1;
-      mbar_wait(full_bar + s, (j / TC_STAGES) & 1);
+      const int a = j & 1;
       mbar_wait(tempty_bar + a, ((j >> 1) & 1) ^ 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t b_addr = smem_u32(smem_b + s * tile_bytes);
-        for (int kb = 0; kb < ((dbg & 2) ? 0 : n_kb); ++kb) {
+      for (int u = 0; u < n_units; ++u) {
+        mbar_wait(full_bar + s, ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t b_addr = smem_u32(smem_b + s * TC_KB_BYTES);
+          const int ka = u < nkb ? u : u - nkb;                       // a_hi k-block paired with this unit
+          if (!(dbg & 2)) {
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            umma_bf16(tmem_base + a * TC_N, umma_desc_sw128(a_addr + kb * (TC_M * 128) + k4 * 32),
-                      umma_desc_sw128(b_addr + kb * (TC_N * 128) + k4 * 32), idesc, (kb | k4) ? 1u : 0u);
+            for (int k4 = 0; k4 < 4; ++k4) {
+              umma_bf16(tmem_base + a * TC_N, umma_desc_sw128(a_addr + ka * (TC_M * 128) + k4 * 32),
+                        umma_desc_sw128(b_addr + k4 * 32), idesc, (u | k4) ? 1u : 0u);
+            }
+            if (u < nkb && n_units > nkb) {                           // BF16X3: a_lo[u] . b_hi[u]
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                umma_bf16(tmem_base + a * TC_N, umma_desc_sw128(a_addr + (nkb + u) * (TC_M * 128) + k4 * 32),
+                          umma_desc_sw128(b_addr + k4 * 32), idesc, 1u);
+              }
+            }
           }
+          umma_commit(empty_bar + s);                   // ring stage reusable once these MMAs have read it
+          if (u == n_units - 1) umma_commit(tfull_bar + a);   // accumulator complete
         }
-        umma_commit(empty_bar + s);    // smem stage reusable once these MMAs have read it
-        umma_commit(tfull_bar + a);    // accumulator complete
+        __syncwarp();
+        if (++s == S) { s = 0; ph ^= 1u; }
       }
-      __syncwarp();
     }
   } else if (warp >= 5 + 4 * NG) {
     // ===== mask builders: one thread per user row walks the row's sorted train items and leaves, for every
@@ -273,33 +289,36 @@ __global__ void __launch_bounds__(32 * (9 + 4 * NG), 1) k_eval_umma(const __nv_b
       mbar_arrive(mfull_bar + m);
     }
   } else if (warp >= 1 + 4 * NG) {
-    // ===== producers: stage item tiles with cp.async, one group per tile, two tiles in flight =====
+    // ===== producers: stage item k-blocks with cp.async, one group per k-block, three groups in flight =====
     const int pt = threadIdx.x - (1 + 4 * NG) * 32;   // 0..127
-    for (int j = 0; j <= n_tiles; ++j) {
-      if (j < n_tiles) {
-        const int s = j % TC_STAGES;
-        mbar_wait(empty_bar + s, ((j / TC_STAGES) & 1) ^ 1);
-        const uint32_t dstb = smem_u32(smem_b + s * tile_bytes);
+    // thread pt owns chunk column c = pt % 8 of rows r0, r0+16, ... (128 threads cover 16 rows x 8 chunks)
+    const int c = pt & 7, r0 = pt >> 3;
+    int j = 0, u = 0;
+    int s = 0, s_done = 0;                            // ring positions of unit g and of unit g-2
+    uint32_t ph = 1;                                  // parity to wait for on empty_bar[s]: 1 on the first lap
+    for (int64_t g = 0; g < n_steps + 2; ++g) {
+      if (g < n_steps) {
+        mbar_wait(empty_bar + s, ph);
         const int64_t i0 = int64_t(j) * TC_N;
-        // thread pt owns chunk column c = pt % 8 of rows r0, r0+16, ... (128 threads cover 16 rows x 8 chunks)
-        const int c = pt & 7, r0 = pt >> 3;
-        const __nv_bfloat16* src0 = Bi + (i0 + r0) * Kp + c * 8;
-        const uint32_t dst0 = dstb + r0 * 128 + ((c ^ (r0 & 7)) << 4);     // (r0 + 16 t) % 8 == r0 % 8
+        const __nv_bfloat16* src0 = Bi + (i0 + r0) * Kp + u * 64 + c * 8;
+        const uint32_t dst0 = smem_u32(smem_b + s * TC_KB_BYTES) + r0 * 128 + ((c ^ (r0 & 7)) << 4);   // (r0 + 16 t) % 8 == r0 % 8
         const int rows_left = int((I - i0 - r0 + 15) / 16);                // rows r0 + 16 t that exist
-        for (int kb = 0; kb < ((dbg & 4) ? 0 : n_kb); ++kb) {
+        if (!(dbg & 4)) {
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
             const bool ok = t < rows_left;
-            cp_async16(dst0 + kb * (TC_N * 128) + t * 2048, ok ? src0 + int64_t(t) * 16 * Kp + kb * 64 : Bi,
-                       ok ? 16u : 0u);   // 0 -> zero fill
+            cp_async16(dst0 + t * 2048, ok ? src0 + int64_t(t) * 16 * Kp : Bi, ok ? 16u : 0u);   // 0 -> zero fill
           }
         }
+        if (++u == n_units) { u = 0; ++j; }
+        if (++s == S) { s = 0; ph ^= 1u; }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
-      if (j > 0) {   // tile j-1 has landed (at most the newest group may still be in flight)
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      if (g >= 2) {   // unit g-2 has landed (the two newest groups may still be in flight; S >= 3)
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(full_bar + (j - 1) % TC_STAGES);
+        mbar_arrive(full_bar + s_done);
+        if (++s_done == S) s_done = 0;
       }
     }
   } else {
@@ -506,34 +525,41 @@ static TcConfig tc_config(int32_t K, int precision) {
   if (K + 12 <= 32) return {32, 32, 1, 32};
   return {64, 16, 1, 64};
 }
-static size_t tc_smem(const TcConfig& c, int Kp) {
-  return size_t(1 + TC_STAGES) * TC_M * Kp * 2 + size_t(c.NG) * (c.KC + c.BC) * TC_M * 8 +
+// shared memory with a ring of S k-blocks; tc_stages picks the deepest ring that fits (0: the shape does not fit)
+static size_t tc_smem(const TcConfig& c, int Kp, int S) {
+  return size_t(TC_M) * Kp * 2 + size_t(S) * TC_KB_BYTES + size_t(c.NG) * (c.KC + c.BC) * TC_M * 8 +
          size_t(TC_MASK_RING) * TC_M * 16 + 256 + 1024;
 }
+static int tc_stages(const TcConfig& c, int Kp) {
+  for (int S = TC_MAX_STAGES; S >= 3; --S)
+    if (tc_smem(c, Kp, S) <= 227 * 1024) return S;
+  return 0;
+}
+static int tc_parts(int precision) { return precision == CGX_SCORE_BF16X3 ? 2 : 1; }   // stored parts: [hi | lo]
+static int tc_dp(int32_t d) { return (d + 63) / 64 * 64; }
 
 size_t eval_topk_tc_workspace(int64_t n_users, int32_t I, int32_t d, int32_t K, int precision) {
-  const int parts = precision == CGX_SCORE_BF16X3 ? 3 : 1;
-  const size_t Kp = size_t((parts * d + 63) / 64) * 64;
+  const size_t Kp = size_t(tc_parts(precision)) * tc_dp(d);
   return align_up(size_t(n_users) * Kp * 2) + align_up(size_t(I) * Kp * 2) + align_up(size_t(n_users) * 64 * 4) +
          4 * align_up(size_t(n_users) * 4) + 1024;
 }
 
-static bool tc_supported(int32_t d, int32_t K, int parts) {
-  const int Kp = (parts * d + 63) / 64 * 64;
+static bool tc_supported(int32_t d, int32_t K, int precision) {
   if (K + 12 > 64) return false;
-  return tc_smem(tc_config(K, parts == 3 ? CGX_SCORE_BF16X3 : CGX_SCORE_BF16), Kp) <= 227 * 1024;
+  return tc_stages(tc_config(K, precision), tc_parts(precision) * tc_dp(d)) > 0;
 }
 
 template <int KC, int BC, int NG, int STRIDE>
 static int tc_launch(const __nv_bfloat16* Au, const __nv_bfloat16* Bi, const int64_t* users, int64_t n_users,
-                     const float* f_u, const float* f_i, int32_t I, int32_t d, int Kp, const int64_t* tr_indptr,
+                     const float* f_u, const float* f_i, int32_t I, int32_t d, int Kp, int nkb, const int64_t* tr_indptr,
                      const int32_t* tr_idx, int32_t K, int32_t* cand, float* thr, const float* unorm,
                      const unsigned int* scal, float eps_rel, int32_t* out_ids, float* out_scores, int32_t* redo_rows,
                      int32_t* n_redo, cudaStream_t stream) {
-  const size_t smem = tc_smem(TcConfig{KC, BC, NG, STRIDE}, Kp);
+  const int S = tc_stages(TcConfig{KC, BC, NG, STRIDE}, Kp);
+  const size_t smem = tc_smem(TcConfig{KC, BC, NG, STRIDE}, Kp, S);
   CGX_CUDA(cudaFuncSetAttribute(k_eval_umma<KC, BC, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_eval_umma<KC, BC, NG><<<(unsigned)ceil_div(n_users, TC_M), 32 * (9 + 4 * NG), smem, stream>>>(
-      Au, Bi, users, n_users, I, Kp, tr_indptr, tr_idx, cand, STRIDE, thr,
+      Au, Bi, users, n_users, I, Kp, nkb, S, tr_indptr, tr_idx, cand, STRIDE, thr,
       getenv("CGX_EVAL_DBG") ? atoi(getenv("CGX_EVAL_DBG")) : 0);
   CGX_LAUNCH_CHECK();
   k_rescore<STRIDE><<<(unsigned)ceil_div(n_users, 8), 256, 0, stream>>>(users, n_users, f_u, f_i, d, tr_indptr, tr_idx,
@@ -546,16 +572,16 @@ static int tc_launch(const __nv_bfloat16* Au, const __nv_bfloat16* Bi, const int
 int eval_topk_tc(const int64_t* users, int64_t n_users, const float* f_u, const float* f_i, int32_t I, int32_t d,
                  const int64_t* tr_indptr, const int32_t* tr_idx, int32_t K, int precision, int32_t* out_ids,
                  float* out_scores, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  const int parts = precision == CGX_SCORE_BF16X3 ? 3 : 1;
   CGX_REQUIRE(precision == CGX_SCORE_BF16X3 || precision == CGX_SCORE_BF16, CGX_ERR_ARG, "eval_topk: bad precision %d",
               precision);
-  if (!tc_supported(d, K, parts)) {   // shapes the UMMA tile cannot hold: the exact kernel is always valid
+  const int parts = tc_parts(precision), Dp = tc_dp(d);
+  if (!tc_supported(d, K, precision)) {   // shapes the UMMA tile cannot hold: the exact kernel is always valid
     return eval_fp32_rows(users, nullptr, nullptr, n_users, f_u, f_i, I, d, tr_indptr, tr_idx, K, out_ids, out_scores,
                           stream);
   }
   CGX_REQUIRE(workspace_bytes >= eval_topk_tc_workspace(n_users, I, d, K, precision), CGX_ERR_WORKSPACE,
               "eval_topk: workspace too small");
-  const int Kp = (parts * d + 63) / 64 * 64;
+  const int Kp = parts * Dp, nkb = Dp / 64;
   const TcConfig cfg = tc_config(K, precision);
   Arena ws(workspace, workspace_bytes);
   __nv_bfloat16* Au = ws.take<__nv_bfloat16>(size_t(n_users) * Kp);
@@ -567,15 +593,15 @@ int eval_topk_tc(const int64_t* users, int64_t n_users, const float* f_u, const 
   unsigned int* scal = ws.take<unsigned int>(4);   // [0] max item norm bits, [1] redo count
   CGX_REQUIRE(ws.ok, CGX_ERR_WORKSPACE, "eval_topk: workspace too small");
   CGX_CUDA(cudaMemsetAsync(scal, 0, 16, stream));
-  k_tc_convert<<<(unsigned)ceil_div(n_users, 8), 256, 0, stream>>>(f_u, users, n_users, d, parts, Kp, 0, Au, unorm, nullptr);
+  k_tc_convert<<<(unsigned)ceil_div(n_users, 8), 256, 0, stream>>>(f_u, users, n_users, d, parts, Dp, Au, unorm, nullptr);
   CGX_LAUNCH_CHECK();
-  k_tc_convert<<<(unsigned)ceil_div(I, 8), 256, 0, stream>>>(f_i, nullptr, I, d, parts, Kp, 1, Bi, nullptr, scal);
+  k_tc_convert<<<(unsigned)ceil_div(I, 8), 256, 0, stream>>>(f_i, nullptr, I, d, parts, Dp, Bi, nullptr, scal);
   CGX_LAUNCH_CHECK();
   // bf16x3: dropped lo*lo term, bf16 rounding of lo, fp32 accumulation inside the MMA: 2^-13 |a||b| is a safe cap
   const float eps_rel = 1.0f / 8192.0f;
   int32_t* redo_rows = precision == CGX_SCORE_BF16X3 ? redo : nullptr;
   int32_t* n_redo = reinterpret_cast<int32_t*>(scal + 1);
-#define CGX_TC_ARGS Au, Bi, users, n_users, f_u, f_i, I, d, Kp, tr_indptr, tr_idx, K, cand, thr, unorm, scal, eps_rel, \
+#define CGX_TC_ARGS Au, Bi, users, n_users, f_u, f_i, I, d, Kp, nkb, tr_indptr, tr_idx, K, cand, thr, unorm, scal, eps_rel, \
                     out_ids, out_scores, redo_rows, n_redo, stream
   if (cfg.NG == 2) {
     CGX_TRY((tc_launch<24, 16, 2, 64>(CGX_TC_ARGS)));
@@ -601,3 +627,8 @@ int eval_topk_tc(const int64_t* users, int64_t n_users, const float* f_u, const 
 }
 
 }  // namespace cgx
+
+extern "C" int cgx_eval_topk_uses_tensor_cores(int32_t d, int32_t k, int precision) {
+  if (precision != CGX_SCORE_BF16X3 && precision != CGX_SCORE_BF16) return 0;
+  return cgx::tc_supported(d, k, precision) ? 1 : 0;
+}

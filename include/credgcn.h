@@ -284,6 +284,10 @@ int cgx_eval_topk(const int64_t* users, int64_t n_users, const float* f_u, const
                   int32_t k, int precision, int32_t* out_ids, float* out_scores,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* 1 when cgx_eval_topk runs the tcgen05 kernel for this (d, k, precision); 0 when it falls back to the exact
+ * fp32 kernel (precision FP32, k > 52, or a width whose operands do not fit shared memory: BF16X3 with d = 256). */
+int cgx_eval_topk_uses_tensor_cores(int32_t d, int32_t k, int precision);
+
 /* Scores of explicit candidate lists (sampled protocol, CU:521-527): cand int64[n, C] ->
  * scores float[n, C] = <f_u[users[r]], f_i[cand[r, c]]>. */
 int cgx_score_candidates(const int64_t* users, const int64_t* cand, int64_t n_users, int32_t n_cand,

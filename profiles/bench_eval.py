@@ -5,18 +5,30 @@ import numpy as np, torch
 from credgcn import evaluate, graph, model, synth
 
 name = sys.argv[1] if len(sys.argv) > 1 else "C2"
-K = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 dev = torch.device("cuda", 0)
-sg = synth.make_graph(name)
-shp = synth.SHAPES[name]
-gr = graph.build_graph(sg.train_edges, sg.num_users, sg.num_items, sg.cred, shp["variant"], dev)
 torch.manual_seed(0)
-d = shp["emb_dim"]
-eu = torch.nn.init.xavier_uniform_(torch.empty(sg.num_users, d)).to(dev)
-ei = torch.nn.init.xavier_uniform_(torch.empty(sg.num_items, d)).to(dev)
-fu, fi = model.propagate_forward(gr, eu, ei, shp["num_layers"], shp["order"])
+if name.isdigit():      # python profiles/bench_eval.py U I d [K]: random tables, every user owns 20 random train items
+    U, I, d = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+    K = int(sys.argv[4]) if len(sys.argv) > 4 else 20
+    fu = torch.randn(U, d, device=dev) * 0.1
+    fi = torch.randn(I, d, device=dev) * 0.1
+    idx = torch.sort(torch.randint(0, I, (U, 20), device=dev, dtype=torch.int32), dim=1).values.reshape(-1)
+    csr = (torch.arange(0, 20 * U + 1, 20, device=dev, dtype=torch.int64), idx.contiguous())
+    name = f"random {U}x{I}"
+
+    class sg:
+        num_users, num_items = U, I
+else:
+    K = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+    sg = synth.make_graph(name)
+    shp = synth.SHAPES[name]
+    gr = graph.build_graph(sg.train_edges, sg.num_users, sg.num_items, sg.cred, shp["variant"], dev)
+    d = shp["emb_dim"]
+    eu = torch.nn.init.xavier_uniform_(torch.empty(sg.num_users, d)).to(dev)
+    ei = torch.nn.init.xavier_uniform_(torch.empty(sg.num_items, d)).to(dev)
+    fu, fi = model.propagate_forward(gr, eu, ei, shp["num_layers"], shp["order"])
+    csr = (gr.samp_indptr, gr.samp_idx)
 users = torch.arange(sg.num_users, device=dev)
-csr = (gr.samp_indptr, gr.samp_idx)
 out = {"workload": name, "users": sg.num_users, "items": sg.num_items, "d": d, "K": K,
        "flops": 2.0 * sg.num_users * sg.num_items * d}
 ref = None

@@ -455,7 +455,7 @@ def test_errors_are_loud(cg):
 # ------------------------------------------------------------------------------------------------
 # tensor-core (tcgen05) score path
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("shape", [(300, 420, 32), (943, 1682, 64), (700, 5000, 128), (130, 257, 16)])
+@pytest.mark.parametrize("shape", [(300, 420, 32), (943, 1682, 64), (700, 5000, 128), (130, 257, 16), (260, 900, 256)])
 def test_tensor_core_topk_equals_fp32_path(cg, shape):
     """BF16x3 tensor-core selection + exact re-scoring (+ proof / redo) must return exactly what the
     fp32 kernel returns: same ids, same score bits."""
@@ -469,17 +469,23 @@ def test_tensor_core_topk_equals_fp32_path(cg, shape):
     ev = cg["evaluate"]
     users = torch.arange(0, U, 2)
     csr = ev._device_csr(tr, DEV)
+    from credgcn._lib import PRECISIONS, lib
     for K in (10, 20, 40):
+        # the tcgen05 kernel itself must be what runs (d = 256 does not fit shared memory with BF16X3)
+        assert lib().cgx_eval_topk_uses_tensor_cores(d, K, PRECISIONS["bf16x3"]) == (1 if d <= 128 else 0)
         ids0, sc0 = ev.topk_device(fu, fi, users, csr, K, "fp32")
         ids1, sc1 = ev.topk_device(fu, fi, users, csr, K, "bf16x3")
         assert torch.equal(ids0, ids1), (shape, K, int((ids0 != ids1).sum()))
         assert torch.equal(sc0, sc1)
 
 
-def test_tensor_core_single_pass_bf16_is_close(cg):
+@pytest.mark.parametrize("d", [64, 128, 256])
+def test_tensor_core_single_pass_bf16_is_close(cg, d):
     """precision='bf16' (one bf16 pass, no proof): stated tolerance = at least 97 % of the exact top-20
     ids recovered, scores of common ids exact (they are re-scored in fp32)."""
-    U, I, d = 1000, 6000, 64
+    U, I = 1000, 6000
+    from credgcn._lib import PRECISIONS, lib
+    assert lib().cgx_eval_topk_uses_tensor_cores(d, 20, PRECISIONS["bf16"]) == 1
     rng = np.random.default_rng(9)
     fu = torch.tensor((rng.standard_normal((U, d)) * 0.2).astype(np.float32), device=DEV)
     fi = torch.tensor((rng.standard_normal((I, d)) * 0.2).astype(np.float32), device=DEV)
