@@ -56,7 +56,9 @@ class CFG:
 
     # which script's behaviour train_lightgcn() follows: "cu" | "v2" | "da" | "msg" | "me"
     variant: str = "v2"
-    score_precision: str = "fp32"  # full-rank eval: "fp32" | "bf16x3" | "bf16"
+    # full-rank eval: "bf16x3" = tcgen05 candidate selection + exact fp32 re-scoring + completeness proof (the
+    # SAME ids and score bits as "fp32", 6-7x faster); "fp32" = CUDA-core kernel; "bf16" = one approximate pass
+    score_precision: str = "bf16x3"
     # sampled eval: False = candidates from the reference's own PCG64 stream on the host (identical lists);
     # True = candidates drawn on device (same protocol, Philox streams; no per-user Python loop)
     sampled_eval_on_device: bool = False
