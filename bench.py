@@ -32,7 +32,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4"])
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=3)
@@ -261,6 +261,9 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
+    if args.workload == "C5" and world == 1:
+        raise SystemExit("--workload C5 (50M users x 10M items x 1B edges) is BASELINE's 8-GPU configuration: run it "
+                         "under torchrun with --gpus N > 1 (the graph is split over the ranks)")
     from credgcn import _lib, graph, model, sampler
     if world > 1:
         from credgcn import sharded

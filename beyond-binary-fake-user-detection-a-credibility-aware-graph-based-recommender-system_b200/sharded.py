@@ -443,7 +443,12 @@ def evaluate_full_ranking_sharded(f_u_local, f_i, graph: CredGraph, test_edges_l
 def bench_main(args, rank: int, world: int, dev: torch.device):
     from . import synth
     shp = synth.SHAPES[args.workload]
-    if args.workload in ("C4", "C5"):
+    strong = args.workload == "C5"
+    if strong:      # BASELINE configs[4]: THE 50M x 10M x 1B-edge graph, its users split over the ranks
+        sg = synth.make_graph_device("C5", dev, num_users=shp["num_users"] // world,
+                                     num_edges=shp["num_edges"] // world, seed=20240 + 1000 * (rank + 1),
+                                     item_seed=20242)
+    elif args.workload == "C4":
         sg = synth.make_graph_device(args.workload, dev, seed=20240 + 1000 * (rank + 1), item_seed=20242)
     else:
         sg = synth.make_graph(args.workload, seed=20240 + 1000 * (rank + 1), item_seed=20242)
@@ -454,6 +459,12 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
     item_emb = torch.nn.init.xavier_uniform_(torch.empty(I, d, device=dev))      # identical on every rank
     torch.manual_seed(1000 + rank)
     user_emb = torch.nn.init.xavier_uniform_(torch.empty(U, d, device=dev))
+    n_eval = int(__import__("os").environ.get("CGX_BENCH_EVAL_USERS", "0"))   # per rank; 0 = no evaluation leg
+    test_edges = None
+    if n_eval:
+        te = torch.as_tensor(sg.test_edges, device=dev)
+        test_edges = te[:, te[0] < n_eval].contiguous()
+        del te
     del sg
     step = ShardedTrainStep(gr, user_emb, item_emb, K, shp["order"], mix_pop=None if shp["variant"] == "cu" else 0.7,
                             exchange=__import__("os").environ.get("CGX_EXCHANGE", "p2p"))
@@ -518,8 +529,11 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
         print(json.dumps({
             "metric": "edges/sec (3-layer cred-weighted LightGCN fwd+bwd)", "value": E / (ms / 1e3), "unit": "edges/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload} x {world}: one {U:,}-user shard per GPU ({E:,} train edges in "
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": (f"C5 split over {world} GPUs: {U * world:,} users x {I:,} items, " if strong else
+                                    f"{args.workload} x {world}: ") +
+                                   f"one {U:,}-user shard per GPU ({E:,} train edges in "
                                    f"total), {I:,} items replicated, user-sharded rows, item table all-reduced per layer",
                        "emb_dim": d, "num_layers": K, "batch_users": args.batch * world,
                        "step": "sample+fwd+loss+bwd+adam", "parallelism": f"user-shard x{world}",
@@ -530,5 +544,28 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
             "collectives_per_step": 2 * K + 1, "cuda_graph": graphed,
             "exchange": type(step.ex).__name__,
         }))
+    if n_eval:      # user-sharded full-rank evaluation of the first n_eval users of every shard (second JSON line)
+        with torch.no_grad():
+            f_u, f_i = step.prop.forward(step.eu.detach(), step.ei.detach())
+        f_u, f_i = f_u.contiguous(), f_i.contiguous()
+        res = None
+        times = []
+        for _ in range(2):
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            res = evaluate_full_ranking_sharded(f_u, f_i, gr, test_edges, I, (10, 20), precision="bf16x3")
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+        t = torch.tensor([times[-1]], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            n = res[20]["users_eval"]
+            sec = float(t.item())
+            print(json.dumps({"eval": "user-sharded full-rank Recall/NDCG@{10,20}, tcgen05 scores (bf16x3), device metrics",
+                              "users_eval": n, "items": I, "emb_dim": d, "n_gpus": world, "seconds": sec,
+                              "users_per_s": n / sec, "useful_TFLOPs_per_gpu": 2.0 * n * I * d / sec / world / 1e12,
+                              "recall@20": res[20]["recall"], "ndcg@20": res[20]["ndcg"],
+                              "projected_seconds_all_users": sec * (U * world * 0.85) / max(n, 1)}))
     dist.barrier()
     dist.destroy_process_group()
