@@ -162,7 +162,8 @@ __global__ void __launch_bounds__(SP_THREADS, MINB) k_spmm(const int64_t* __rest
                                                            SpmmSched sc, const float4* __restrict__ X,
                                                            float4* __restrict__ Y, const float4* ACC_IN,
                                                            float4* ACC_OUT, float acc_scale, float4* partial,
-                                                           const uint8_t* __restrict__ nz) {
+                                                           const uint8_t* __restrict__ nz,
+                                                           const int4* __restrict__ work) {
   constexpr int ROW4 = G * V;
   // Programmatic dependent launch: let the next kernel of the stream start its own prologue now, and run
   // THIS kernel's prologue (schedule lookups, first batch of column ids / values -- graph constants) while the
@@ -175,6 +176,48 @@ __global__ void __launch_bounds__(SP_THREADS, MINB) k_spmm(const int64_t* __rest
   float4 acc[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (work != nullptr) {
+    // Flattened schedule (cgx_row_schedule_work): ONE 16-byte descriptor {begin, length, row | long-row index}
+    // replaces the perm -> indptr chain (two dependent loads) in front of every row's first gather.
+    const int64_t n_items = int64_t(sc.n_chunks) + (n_rows - sc.n_long);
+    if (item >= n_items) return;
+    const int4 wd = __ldg(work + item);
+    const int64_t begin = (int64_t(wd.y) << 32) | uint32_t(wd.x);
+    const int64_t end = begin + wd.z;
+    int32_t cf = 0;
+    float wf = 0.f;
+    if (lane < wd.z) {
+      cf = __ldg(idx + begin + lane);
+      wf = __ldg(val + begin + lane);
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    gather_batches<G, V, UNR, HINT, NZ>(idx, val, begin, end, X, lane, mask, cf, wf, acc, nz);
+    if (item >= sc.n_chunks) {
+      epilogue<G, V>(wd.w, lane, acc, Y, ACC_IN, ACC_OUT, acc_scale);
+      return;
+    }
+    const int32_t k = wd.w;
+#pragma unroll
+    for (int v = 0; v < V; ++v) __stcg(partial + item * ROW4 + v * G + lane, acc[v]);
+    if (k < sc.n_huge) return;            // combined by k_spmm_finish
+    const int32_t c0 = __ldg(sc.chunk_ptr + k), c1 = __ldg(sc.chunk_ptr + k + 1);
+    __threadfence();                       // release: this group's partial is visible device-wide
+    __syncwarp(mask);
+    int prev = 0;
+    if (lane == 0) prev = atomicAdd(sc.arrive + k, 1);
+    prev = __shfl_sync(mask, prev, 0, G);
+    if (prev != c1 - c0 - 1) return;
+    __threadfence();                       // acquire: every other chunk's partial is visible
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = c0; c < c1; ++c) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[v] = add4(acc[v], __ldcg(partial + int64_t(c) * ROW4 + v * G + lane));
+    }
+    epilogue<G, V>(int64_t(__ldg(sc.perm + k)), lane, acc, Y, ACC_IN, ACC_OUT, acc_scale);
+    if (lane == 0) sc.arrive[k] = 0;       // self-resetting for the next launch
+    return;
+  }
   if (item < sc.n_chunks) {
     const int32_t k = __ldg(sc.chunk_row + item);
     const int32_t row = __ldg(sc.perm + k);
@@ -363,6 +406,11 @@ static int spmm_env(const char* name, int dflt) {
 // The persistent, software-pipelined kernel is kept as an experiment: measured SLOWER than one group per
 // item with hardware CTA scheduling (C2 d=64: 0.62 vs 0.43 ms fwd+bwd; 64M-edge d=128: 65.4 vs 61.2 ms;
 // profiles/r1_spmm_variants.txt), so it is off unless CGX_SPMM_PERSISTENT=1.
+// CGX_SPMM_WORK=0: k_spmm looks rows up through perm -> indptr instead of the flattened descriptors
+static bool spmm_use_work() {
+  static const bool on = spmm_env("CGX_SPMM_WORK", 1) != 0;
+  return on;
+}
 static bool spmm_persistent() {
   static const bool v = spmm_env("CGX_SPMM_PERSISTENT", 0) != 0;
   return v;
@@ -412,7 +460,7 @@ static int launch_spmm(const cgx_csr* m, const float* val, const float* X, float
     CGX_CUDA(cudaLaunchKernelEx(&cfg, k_spmm<G, V, UNR, HINT, MINB, NZ>, m->indptr, m->idx, val, m->n_rows, sc,
                                 reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(Y),
                                 reinterpret_cast<const float4*>(ACC_IN), reinterpret_cast<float4*>(ACC_OUT), acc_scale,
-                                partial, nz));
+                                partial, nz, spmm_use_work() ? static_cast<const int4*>(m->work) : nullptr));
   }
   CGX_LAUNCH_CHECK();
   if (m->n_huge > 0) {
