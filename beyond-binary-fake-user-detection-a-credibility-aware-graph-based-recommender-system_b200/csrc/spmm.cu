@@ -193,6 +193,8 @@ __global__ void __launch_bounds__(SP_THREADS, MINB) k_spmm(const int64_t* __rest
     asm volatile("griddepcontrol.wait;" ::: "memory");
     gather_batches<G, V, UNR, HINT, NZ>(idx, val, begin, end, X, lane, mask, cf, wf, acc, nz);
     if (item >= sc.n_chunks) {
+      // (loading ACC_IN[row] before the gathers, to take it off the dependency chain, was measured SLOWER: the
+      // four extra live registers spill at the 64-register cap -- C2 0.514 -> 0.553 ms, C4 155 -> 160 ms)
       epilogue<G, V>(wd.w, lane, acc, Y, ACC_IN, ACC_OUT, acc_scale);
       return;
     }
