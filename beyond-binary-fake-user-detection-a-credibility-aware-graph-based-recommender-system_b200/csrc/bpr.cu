@@ -202,7 +202,16 @@ __global__ void __launch_bounds__(BP_THREADS) k_bpr_triple(BprArgs a, float* __r
   }
 }
 
-// one group per sorted entry; run heads accumulate the whole run and write the row once
+// One group per sorted entry.  The sorted entry list is cut into blocks of BP_SEG entries; a run (= all entries of
+// one row) is accumulated in SEGMENTS: from its head to the end of the head's block, then one segment per further
+// block.  A run that stays inside one block is written straight to the gradient row by its head; a longer run
+// (popularity-weighted negatives put hundreds of entries on one item) leaves one partial sum per segment, which
+// k_bpr_combine adds in segment order.  Walking such a run in one group was a chain of ~3 dependent load latencies
+// per 4 entries and set the duration of the whole kernel (36 us for a 12 288-entry batch).
+// Partial slot of a segment that starts at entry k: 2 * (k / BP_SEG) + (k % BP_SEG != 0) -- per block at most one
+// segment starts at the block's first entry and at most one head-started segment continues past the block.
+constexpr int BP_SEG = 8;
+
 template <int G, int V>
 __global__ void __launch_bounds__(BP_THREADS) k_bpr_scatter(BprArgs a, int entry_bits,
                                                             const uint64_t* __restrict__ keys,
@@ -210,7 +219,8 @@ __global__ void __launch_bounds__(BP_THREADS) k_bpr_scatter(BprArgs a, int entry
                                                             const float* __restrict__ coef_neg,
                                                             float4* __restrict__ g_u, float4* __restrict__ g_i,
                                                             int32_t* __restrict__ ego_rows,
-                                                            float* __restrict__ ego_coef) {
+                                                            float* __restrict__ ego_coef, float4* __restrict__ part,
+                                                            int32_t* __restrict__ part_cnt) {
   constexpr int ROW4 = G * V;
   const int lane = threadIdx.x & (G - 1);
   const int64_t k = (int64_t(blockIdx.x) * BP_THREADS + threadIdx.x) / G;
@@ -220,10 +230,13 @@ __global__ void __launch_bounds__(BP_THREADS) k_bpr_scatter(BprArgs a, int entry
   const uint64_t key = keys[k];
   const int64_t row = int64_t(key >> entry_bits);
   const bool head = (k == 0) || (int64_t(keys[k - 1] >> entry_bits) != row);
+  const bool aligned = (k % BP_SEG) == 0;
   if (!head) {
     if (lane == 0) ego_rows[k] = -1;
-    return;
+    if (!aligned) return;                      // an aligned non-head entry starts a continuation segment
   }
+  const int64_t bound = (k / BP_SEG + 1) * BP_SEG;   // first entry of the next block
+  const int64_t stop = bound < n ? bound : n;
   float4 acc[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -232,14 +245,14 @@ __global__ void __launch_bounds__(BP_THREADS) k_bpr_scatter(BprArgs a, int entry
   // four are loaded before anything is accumulated (popular items give runs of 50+ entries; one dependent
   // load chain per entry would serialise ~1.5 us each).  Accumulation order stays the entry order.
   constexpr int RU = 4;
-  for (int64_t q0 = k; q0 < n; q0 += RU) {
+  for (int64_t q0 = k; q0 < stop; q0 += RU) {
     int64_t e[RU];
     int m = 0;
 #pragma unroll
     for (int t = 0; t < RU; ++t) {
-      const uint64_t kq = (q0 + t < n) ? keys[q0 + t] : ~uint64_t(0);
+      const uint64_t kq = (q0 + t < stop) ? keys[q0 + t] : ~uint64_t(0);
       e[t] = int64_t(kq & emask);
-      if (m == t && q0 + t < n && int64_t(kq >> entry_bits) == row) m = t + 1;
+      if (m == t && q0 + t < stop && int64_t(kq >> entry_bits) == row) m = t + 1;
     }
     float c0[RU], c1[RU];
     int64_t r0[RU], r1[RU];
@@ -288,6 +301,77 @@ __global__ void __launch_bounds__(BP_THREADS) k_bpr_scatter(BprArgs a, int entry
       }
     }
     mult += m;
+    if (m < RU) break;
+  }
+  // the run goes on in the next block iff this segment reached the block's end and the next block starts with the row
+  const bool cont = (k + mult == stop) && stop < n && int64_t(keys[stop] >> entry_bits) == row;
+  if (head && !cont) {
+    float4* dst = row < a.U ? g_u + row * ROW4 : g_i + (row - a.U) * ROW4;
+#pragma unroll
+    for (int v = 0; v < V; ++v) dst[v * G + lane] = acc[v];
+    if (lane == 0) {
+      ego_rows[k] = int32_t(row);
+      ego_coef[k] = float(mult) * 2.0f * a.reg / float(a.B_total);
+    }
+    return;
+  }
+  const int64_t slot = 2 * (k / BP_SEG) + (aligned ? 0 : 1);
+#pragma unroll
+  for (int v = 0; v < V; ++v) part[slot * ROW4 + v * G + lane] = acc[v];
+  if (lane == 0) {
+    part_cnt[slot] = mult;
+    if (head) ego_rows[k] = -2;                // k_bpr_combine finishes this row
+  }
+}
+
+// heads of runs that span several blocks: add the segment partials in order and write the gradient row
+template <int G, int V>
+__global__ void __launch_bounds__(BP_THREADS) k_bpr_combine(BprArgs a, int entry_bits,
+                                                            const uint64_t* __restrict__ keys,
+                                                            float4* __restrict__ g_u, float4* __restrict__ g_i,
+                                                            int32_t* __restrict__ ego_rows,
+                                                            float* __restrict__ ego_coef,
+                                                            const float4* __restrict__ part,
+                                                            const int32_t* __restrict__ part_cnt) {
+  constexpr int ROW4 = G * V;
+  const int lane = threadIdx.x & (G - 1);
+  const int64_t k = (int64_t(blockIdx.x) * BP_THREADS + threadIdx.x) / G;
+  const int64_t n = 3 * a.B;
+  if (k >= n || ego_rows[k] != -2) return;
+  const int64_t row = int64_t(keys[k] >> entry_bits);
+  const int64_t slot0 = 2 * (k / BP_SEG) + ((k % BP_SEG) ? 1 : 0);
+  float4 acc[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) acc[v] = part[slot0 * ROW4 + v * G + lane];
+  int mult = part_cnt[slot0];
+  constexpr int RU = 4;      // four blocks per pass: keys, counts and partials of all four are loaded before any add
+  for (int64_t b0 = (k / BP_SEG + 1) * BP_SEG; b0 < n; b0 += RU * BP_SEG) {
+    int m = 0;
+#pragma unroll
+    for (int t = 0; t < RU; ++t) {
+      const int64_t b = b0 + int64_t(t) * BP_SEG;
+      if (m == t && b < n && int64_t(keys[b] >> entry_bits) == row) m = t + 1;
+    }
+    float4 x[RU][V];
+    int c[RU];
+#pragma unroll
+    for (int t = 0; t < RU; ++t) {
+      const int64_t s = 2 * (b0 / BP_SEG + t);
+      c[t] = t < m ? part_cnt[s] : 0;
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        x[t][v] = t < m ? part[s * ROW4 + v * G + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int t = 0; t < RU; ++t) {
+      if (t < m) {
+        mult += c[t];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          acc[v].x += x[t][v].x; acc[v].y += x[t][v].y; acc[v].z += x[t][v].z; acc[v].w += x[t][v].w;
+        }
+      }
+    }
     if (m < RU) break;
   }
   float4* dst = row < a.U ? g_u + row * ROW4 : g_i + (row - a.U) * ROW4;
@@ -344,7 +428,11 @@ static size_t plan_ws(int64_t B) {
   if (n <= PS_MAX) return 256;
   return align_up(size_t(n) * 8) + radix_sort_temp_bytes(n) + 256;
 }
-static size_t bpr_ws(int64_t B) { return 3 * align_up(size_t(B) * 4) + 512; }
+// coefficients + loss terms + the segment partials of k_bpr_scatter (sized for the widest table, d = 256)
+static size_t bpr_part_slots(int64_t B) { return 2 * size_t(ceil_div(3 * B, BP_SEG)); }
+static size_t bpr_ws(int64_t B) {
+  return 3 * align_up(size_t(B) * 4) + align_up(bpr_part_slots(B) * 256 * 4) + align_up(bpr_part_slots(B) * 4) + 512;
+}
 
 template <int G, int V>
 static int bpr_run(const BprArgs& a, const uint64_t* plan, float* loss_out, float* g_u, float* g_i,
@@ -356,6 +444,8 @@ static int bpr_run(const BprArgs& a, const uint64_t* plan, float* loss_out, floa
   float* coef_neg = ws.take<float>(B);
   float* terms = ws.take<float>(B);
   unsigned long long* bad = ws.take<unsigned long long>(1);
+  float4* part = ws.take<float4>(bpr_part_slots(B) * G * V);
+  int32_t* part_cnt = ws.take<int32_t>(bpr_part_slots(B));
   CGX_REQUIRE(ws.ok, CGX_ERR_WORKSPACE, "bpr: workspace too small");
   constexpr int GROUPS = BP_THREADS / G;
   CGX_CUDA(cudaMemsetAsync(bad, 0, 8, stream));
@@ -363,7 +453,11 @@ static int bpr_run(const BprArgs& a, const uint64_t* plan, float* loss_out, floa
   CGX_LAUNCH_CHECK();
   k_bpr_scatter<G, V><<<(unsigned)ceil_div(n, GROUPS), BP_THREADS, 0, stream>>>(
       a, bits_for(n), plan, coef_pos, coef_neg, reinterpret_cast<float4*>(g_u), reinterpret_cast<float4*>(g_i),
-      ego_rows, ego_coef);
+      ego_rows, ego_coef, part, part_cnt);
+  CGX_LAUNCH_CHECK();
+  k_bpr_combine<G, V><<<(unsigned)ceil_div(n, GROUPS), BP_THREADS, 0, stream>>>(
+      a, bits_for(n), plan, reinterpret_cast<float4*>(g_u), reinterpret_cast<float4*>(g_i), ego_rows, ego_coef, part,
+      part_cnt);
   CGX_LAUNCH_CHECK();
   k_sum_terms<<<1, 1024, 0, stream>>>(terms, B, bad, loss_out);
   CGX_LAUNCH_CHECK();
