@@ -499,7 +499,7 @@ static int spmm_dispatch(const cgx_csr* m, int use_bwd, int32_t d, const float* 
       case 16: return launch_spmm<4, 1, 4, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
       case 32: return launch_spmm<8, 1, 8, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
       case 64: return launch_spmm<16, 1, 8, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
-      case 128: return launch_spmm<32, 1, 8, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
+      case 128: return launch_spmm<16, 2, 4, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
       case 256: return launch_spmm<32, 2, 4, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
       default: break;
     }
@@ -526,11 +526,23 @@ static int spmm_dispatch(const cgx_csr* m, int use_bwd, int32_t d, const float* 
         case 14: return launch_spmm<GG, 1, 4, HINT_NC, 4>(CGX_SPMM_ARGS);                  \
         case 15: return launch_spmm<GG, 1, 8, HINT_NC, 4>(CGX_SPMM_ARGS);                  \
         case 16: return launch_spmm<GG, 1, 8, HINT_NC, 1>(CGX_SPMM_ARGS);                  \
+        case 17: return launch_spmm<GG / 2, 2, 4, HINT_NC, 4>(CGX_SPMM_ARGS);              \
+        case 18: return launch_spmm<GG / 2, 2, 8, HINT_NC, 2>(CGX_SPMM_ARGS);              \
+        case 19: return launch_spmm<GG / 4, 4, 2, HINT_NC, 4>(CGX_SPMM_ARGS);              \
+        case 20: return launch_spmm<GG / 2, 2, 2, HINT_NC, 6>(CGX_SPMM_ARGS);              \
+        case 21: return launch_spmm<GG / 2, 2, 4, HINT_NC, 3>(CGX_SPMM_ARGS);              \
         default: return launch_spmm<GG, 1, 8, HINT_NC, 4>(CGX_SPMM_ARGS);                  \
       }
     case 64: CGX_VARIANTS(16)
-    case 128: CGX_VARIANTS(32)
-    case 256: return launch_spmm<32, 2, 4, HINT_NC, 4>(CGX_SPMM_ARGS);
+    case 128:
+      // default for d = 128: half a warp per row, two float4 per lane (twice the rows in flight per SM at the same
+      // bytes in flight per lane): 53.8 vs 58.6 ms on the HBM-bound 64M-edge shape (r1_spmm_variants.txt).  The
+      // same split LOSES at d = 64 / C2 (0.65 vs 0.43 ms: 8-wide batches double the dependent gather rounds).
+      if (variant == 0) return launch_spmm<16, 2, 4, HINT_NC, 4>(CGX_SPMM_ARGS);
+      CGX_VARIANTS(32)
+    case 256:
+      if (variant == 17) return launch_spmm<16, 4, 2, HINT_NC, 4>(CGX_SPMM_ARGS);
+      return launch_spmm<32, 2, 4, HINT_NC, 4>(CGX_SPMM_ARGS);
     default:
       set_error("spmm: emb_dim %d unsupported (16, 32, 64, 128, 256)", d);
       return CGX_ERR_UNSUPPORTED;
