@@ -474,6 +474,9 @@ static int launch_spmm(const cgx_csr* m, const float* val, const float* X, float
   return CGX_OK;
 }
 
+// gathered tables above this many bytes count as "beyond L2" (cgx_spmm_set_l2_table_bytes; default 96 MiB of 126)
+static int64_t g_l2_table_bytes = int64_t(96) << 20;
+
 static int spmm_variant() {
   static int v = [] {
     const char* e = getenv("CGX_SPMM_VARIANT");
@@ -494,12 +497,22 @@ static int spmm_dispatch(const cgx_csr* m, int use_bwd, int32_t d, const float* 
   CGX_REQUIRE(Y || ACC_OUT, CGX_ERR_ARG, "spmm: no output requested");
   const float* val = use_bwd ? m->val_bwd : m->val_fwd;
   if (m->n_rows == 0) return CGX_OK;
+  // Group geometry by regime (profiles/r1_spmm_variants.txt).  Gathered table in L2 (C2/C3: latency-bound): d/4 lanes
+  // per row, one float4 per lane, 8 gathers in flight.  Gathered table beyond L2 (HBM-bound): d/8 lanes per row, two
+  // float4 per lane, 4 gathers in flight -- twice the rows in flight per SM at the same bytes in flight per lane
+  // (d = 64: 27.3 vs 30.1 ms, d = 128: 53.8 vs 58.6 ms on the 64M-edge shape; on C2 the same split LOSES, 0.65 vs
+  // 0.43 ms at d = 64 and 0.71 vs 0.61 ms at d = 128).
+  const bool beyond_l2 = int64_t(m->n_cols) * int64_t(d) * 4 > g_l2_table_bytes;
   if (nz != nullptr) {   // sparse input rows: the default geometry of every width, row loads predicated on nz
     switch (d) {
       case 16: return launch_spmm<4, 1, 4, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
       case 32: return launch_spmm<8, 1, 8, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
-      case 64: return launch_spmm<16, 1, 8, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
-      case 128: return launch_spmm<16, 2, 4, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
+      case 64:
+        if (beyond_l2) return launch_spmm<8, 2, 4, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
+        return launch_spmm<16, 1, 8, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
+      case 128:
+        if (beyond_l2) return launch_spmm<16, 2, 4, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
+        return launch_spmm<32, 1, 8, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
       case 256: return launch_spmm<32, 2, 4, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
       default: break;
     }
@@ -533,12 +546,11 @@ static int spmm_dispatch(const cgx_csr* m, int use_bwd, int32_t d, const float* 
         case 21: return launch_spmm<GG / 2, 2, 4, HINT_NC, 3>(CGX_SPMM_ARGS);              \
         default: return launch_spmm<GG, 1, 8, HINT_NC, 4>(CGX_SPMM_ARGS);                  \
       }
-    case 64: CGX_VARIANTS(16)
+    case 64:
+      if (variant == 0 && beyond_l2) return launch_spmm<8, 2, 4, HINT_NC, 4>(CGX_SPMM_ARGS);
+      CGX_VARIANTS(16)
     case 128:
-      // default for d = 128: half a warp per row, two float4 per lane (twice the rows in flight per SM at the same
-      // bytes in flight per lane): 53.8 vs 58.6 ms on the HBM-bound 64M-edge shape (r1_spmm_variants.txt).  The
-      // same split LOSES at d = 64 / C2 (0.65 vs 0.43 ms: 8-wide batches double the dependent gather rounds).
-      if (variant == 0) return launch_spmm<16, 2, 4, HINT_NC, 4>(CGX_SPMM_ARGS);
+      if (variant == 0 && beyond_l2) return launch_spmm<16, 2, 4, HINT_NC, 4>(CGX_SPMM_ARGS);
       CGX_VARIANTS(32)
     case 256:
       if (variant == 17) return launch_spmm<16, 4, 2, HINT_NC, 4>(CGX_SPMM_ARGS);
@@ -570,6 +582,12 @@ extern "C" int cgx_spmm_sparse_rows(const cgx_csr* m, int use_bwd_values, int32_
   CGX_REQUIRE(x_row_nonzero != nullptr, CGX_ERR_ARG, "spmm_sparse_rows: NULL flags");
   return spmm_dispatch(m, use_bwd_values, d, X, Y, ACC_IN, ACC_OUT, acc_scale, workspace, workspace_bytes,
                        static_cast<cudaStream_t>(stream), x_row_nonzero);
+}
+
+extern "C" int64_t cgx_spmm_set_l2_table_bytes(int64_t bytes) {
+  const int64_t old = g_l2_table_bytes;
+  g_l2_table_bytes = bytes < 0 ? (int64_t(96) << 20) : bytes;
+  return old;
 }
 
 extern "C" int cgx_row_flags(const float* X, int64_t n_rows, int32_t d, uint8_t* flags, void* stream) {

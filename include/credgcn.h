@@ -166,6 +166,11 @@ int cgx_spmm_sparse_rows(const cgx_csr* m, int use_bwd_values, int32_t d, const 
                          float acc_scale, void* workspace, size_t workspace_bytes, void* stream);
 int cgx_row_flags(const float* X, int64_t n_rows, int32_t d, uint8_t* flags, void* stream);
 
+/* cgx_spmm picks its thread geometry by regime: a gathered table X of more than this many bytes is treated as
+ * HBM-resident (narrower groups, more rows in flight), a smaller one as L2-resident.  Default 96 MiB; a negative
+ * value restores the default.  Returns the previous value.  Results do not depend on it (tests force both). */
+int64_t cgx_spmm_set_l2_table_bytes(int64_t bytes);
+
 size_t cgx_propagate_workspace_bytes(const cgx_csr* by_user, const cgx_csr* by_item, int32_t d);
 
 /* Forward: final = mean over layers 0..K.  order JACOBI = CU:429-437, GS = V2:482-486.

@@ -743,3 +743,31 @@ def test_graph_without_edges(cg):
     ids, sc = cg["evaluate"].topk_device(fu, fi, torch.arange(U, device=DEV), (gr.samp_indptr, gr.samp_idx), 10)
     want = torch.argsort(-(fu @ fi.T), dim=1, stable=True)[:, :10]
     assert torch.equal(ids.long(), want)
+
+
+@pytest.mark.parametrize("d", [64, 128])
+def test_spmm_geometry_for_tables_beyond_l2_gives_the_same_bits(cg, d):
+    """cgx_spmm switches to narrower groups (two float4 per lane) when the gathered table exceeds L2; the sums are
+    formed in the same order, so forcing that geometry on a small graph must reproduce the default bits -- dense
+    and sparse-row products, forward and adjoint propagation."""
+    from credgcn._lib import lib
+    sg = cg["synth"].make_graph("C1", duplicate_edges=300)
+    gr = cg["graph"].build_graph(sg.train_edges, sg.num_users, sg.num_items, sg.cred, "v2", DEV)
+    m = cg["model"]
+    gen = torch.Generator(device=DEV).manual_seed(d)
+    xu = torch.randn(sg.num_users, d, device=DEV, generator=gen)
+    xi = torch.randn(sg.num_items, d, device=DEV, generator=gen)
+    xs = xu.clone()
+    xs[torch.rand(sg.num_users, device=DEV, generator=gen) < 0.9] = 0.0
+
+    def run():
+        return (m.spmm(gr.by_user, xi), m.spmm(gr.by_item, xu, use_bwd_values=True), m.spmm_sparse_rows(gr.by_item, xs),
+                *m.propagate_forward(gr, xu, xi, 3, "gs"), *m.propagate_backward(gr, xs, xi, 2, "jacobi"))
+    want = run()
+    old = lib().cgx_spmm_set_l2_table_bytes(0)
+    try:
+        got = run()
+    finally:
+        lib().cgx_spmm_set_l2_table_bytes(old)
+    for a, b in zip(got, want):
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32))
