@@ -139,9 +139,11 @@ class HostView:
         self.train_edges, self.cred, self.fraction = e, cred, fraction
 
 
-def cpu_baseline(sg, shp, e0_u, e0_i, batches, steps, reg, edge_fraction=1.0):
+def cpu_baseline(sg, shp, e0_u, e0_i, batches, steps, reg, edge_fraction=1.0, device="cpu"):
     """The reference's CPU execution strategy (COO torch.sparse.mm + autograd + Adam), timed on this
-    box's host cores via the oracle port.  Returns (edges_per_s, ms_per_step, cores, sample_text)."""
+    box's host cores via the oracle port.  Returns (edges_per_s, ms_per_step, cores, sample_text).
+    device="cuda": the same script-level code with stock ATen / cuSPARSE kernels on the GPU (what the reference
+    does when a GPU is present) -- SURVEY 8d's "existing GPU path"."""
     sys.path.insert(0, str(ROOT / "oracle"))
     import credgcn_oracle as orc
     torch.set_num_threads(os.cpu_count() or 1)
@@ -150,12 +152,15 @@ def cpu_baseline(sg, shp, e0_u, e0_i, batches, steps, reg, edge_fraction=1.0):
         keep = np.random.default_rng(0).random(edges.shape[1]) < edge_fraction
         edges = edges[:, keep]
     ops = orc.Operators(edges, sg.num_users, sg.num_items, sg.cred, shp["variant"])
-    base = orc.TorchCpuBaseline(ops, e0_u, e0_i, shp["num_layers"], shp["order"])
+    base = orc.TorchCpuBaseline(ops, e0_u, e0_i, shp["num_layers"], shp["order"], device=device)
+    on_gpu = device != "cpu"
     ts = []
     for s in range(steps + 1):
         u, p, n = batches[s % len(batches)]
+        if on_gpu:
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
-        base.step(u, p, n, reg)
+        base.step(u, p, n, reg)             # ends with loss.item(): the step is complete when it returns
         ts.append(time.perf_counter() - t0)
     ts = ts[1:] if len(ts) > 1 else ts            # first step pays allocator/first-touch costs
     ms = 1e3 * float(np.mean(ts))
@@ -163,7 +168,8 @@ def cpu_baseline(sg, shp, e0_u, e0_i, batches, steps, reg, edge_fraction=1.0):
     edge_fraction = edge_fraction * getattr(sg, "fraction", 1.0)
     sample = (f"{len(ts)} full training steps (fwd+loss+bwd+Adam) of workload {sg.name} on "
               f"{E:,} train edges" + (f" (a {edge_fraction:.3f} edge subsample)" if edge_fraction < 1 else "")
-              + ", torch CPU sparse COO path, oracle port")
+              + (", stock torch CUDA sparse COO path (ATen/cuSPARSE), oracle port" if on_gpu else
+                 ", torch CPU sparse COO path, oracle port"))
     return E / (ms / 1e3), ms, torch.get_num_threads(), sample
 
 
@@ -389,6 +395,8 @@ def main():
             "peak_source": peak_src, "traffic": traffic,
             "traffic_source": "ncu --set full capture of k_spmm, profiles/r1_traffic.json" if traffic else None,
             "algorithmic_bytes_per_step": alg, "algorithmic_bytes_per_launch": alg / n_spmm,
+            # every source row read once instead of once per edge
+            "compulsory_bytes_per_step": 2 * (K * (2 * gr.nnz * 8 + 2 * (U + I) * 4 * d) + 2 * K * (U + I) * 4 * d),
             "avg_launch_ms": prop_ms / n_spmm,
             "sparse_first_adjoint": os.environ.get("CGX_SPARSE_BWD", "1") != "0",   # that launch (1 of 4K; 2 in
             # Jacobi order) skips the zero rows of the loss gradient; the algorithmic bytes still count it in full
@@ -414,6 +422,11 @@ def main():
         v, cms, cores, sample = cpu_baseline(hv, shp, e0_u, e0_i, bt, args.cpu_steps, 1e-4)
         line["cpu_baseline"] = {"value": v, "unit": "edges/s", "cores": cores, "kind": "port",
                                 "sample": sample, "ms_per_step": cms}
+        if E <= 20_000_000:      # the reference's own GPU path: same script-level code, stock torch kernels
+            torch.cuda.empty_cache()
+            v, gms, _, sample = cpu_baseline(hv, shp, e0_u, e0_i, bt, 20, 1e-4, device=str(dev))
+            line["torch_gpu_baseline"] = {"value": v, "unit": "edges/s", "ms_per_step": gms, "kind": "port",
+                                          "sample": sample}
     print(json.dumps(line))
 
 

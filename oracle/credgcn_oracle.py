@@ -419,16 +419,19 @@ class TorchCpuBaseline:
     """Port of the reference's CPU path for timing: coalesced COO operators, K layers of
     torch.sparse.mm (CU:429-437 / V2:482-486), stack+mean, BPR+L2, autograd backward, Adam."""
 
-    def __init__(self, ops: Operators, e0_u, e0_i, num_layers, order, lr=1e-3):
+    def __init__(self, ops: Operators, e0_u, e0_i, num_layers, order, lr=1e-3, device="cpu"):
+        """device="cuda": the same script-level code on the GPU, i.e. stock ATen / cuSPARSE kernels -- the
+        reference's own GPU path (its scripts run with cfg.device = "cuda" when a GPU is present)."""
         import torch
         self.torch = torch
         self.K, self.order = num_layers, order
+        self.device = torch.device(device)
         mk = lambda r, c, v, shape: torch.sparse_coo_tensor(
-            torch.from_numpy(np.vstack([r, c])), torch.from_numpy(v), size=shape).coalesce()
+            torch.from_numpy(np.vstack([r, c])), torch.from_numpy(v), size=shape).coalesce().to(self.device)
         self.A = mk(ops.A_row, ops.A_col, ops.A_val, (ops.U, ops.I))
         self.C = mk(ops.C_row, ops.C_col, ops.C_val, (ops.I, ops.U))
-        self.eu = torch.nn.Parameter(torch.from_numpy(np.array(e0_u, dtype=F32)))
-        self.ei = torch.nn.Parameter(torch.from_numpy(np.array(e0_i, dtype=F32)))
+        self.eu = torch.nn.Parameter(torch.from_numpy(np.array(e0_u, dtype=F32)).to(self.device))
+        self.ei = torch.nn.Parameter(torch.from_numpy(np.array(e0_i, dtype=F32)).to(self.device))
         self.opt = torch.optim.Adam([self.eu, self.ei], lr=lr)
 
     def forward(self):
@@ -455,7 +458,7 @@ class TorchCpuBaseline:
 
     def step(self, users, pos, neg, reg, fair=0.0, pop=None, optimize=True):
         torch = self.torch
-        users, pos, neg = (torch.as_tensor(x, dtype=torch.long) for x in (users, pos, neg))
+        users, pos, neg = (torch.as_tensor(x, dtype=torch.long).to(self.device) for x in (users, pos, neg))
         fu, fi = self.forward()
         loss = self.loss(fu, fi, users, pos, neg, reg, fair, pop)
         self.opt.zero_grad()
