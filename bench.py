@@ -416,6 +416,33 @@ def main():
         "loss": loss_host,
     }
 
+    # ---- full-rank evaluation leg (north_star 4): all users x all items, top-20, on the trained tables ----
+    if E <= 20_000_000:
+        from credgcn import evaluate
+        with torch.no_grad():
+            f_u, f_i = model.propagate_forward(gr, net.user_emb.weight.detach(), net.item_emb.weight.detach(), K,
+                                               shp["order"])
+        all_users = torch.arange(U, device=dev)
+        csr = (gr.samp_indptr, gr.samp_idx)
+        ev = {"users": U, "items": I, "k": 20, "flops": 2.0 * U * I * d}
+        ids_ref = None
+        for prec in ("fp32", "bf16x3"):
+            for _ in range(2):
+                ids, _ = evaluate.topk_device(f_u, f_i, all_users, csr, 20, prec)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ids, _ = evaluate.topk_device(f_u, f_i, all_users, csr, 20, prec)
+            b.record()
+            torch.cuda.synchronize()
+            t = a.elapsed_time(b)
+            ev[prec] = {"ms": t, "useful_tflops": ev["flops"] / t / 1e9, "users_per_s": U / (t / 1e3)}
+            if ids_ref is None:
+                ids_ref = ids
+            else:
+                ev[prec]["ids_equal_fp32"] = bool(torch.equal(ids, ids_ref))
+                ev[prec]["kernel"] = "tcgen05 selection + exact fp32 re-scoring + completeness proof"
+        line["eval_full_rank"] = ev
+
     if not args.no_cpu_baseline:
         hv = HostView(sg, 1.0 if E <= 20_000_000 else 1.0 / 16.0)
         bt = host_triples(hv, host_batches[:8])
@@ -427,6 +454,14 @@ def main():
             v, gms, _, sample = cpu_baseline(hv, shp, e0_u, e0_i, bt, 20, 1e-4, device=str(dev))
             line["torch_gpu_baseline"] = {"value": v, "unit": "edges/s", "ms_per_step": gms, "kind": "port",
                                           "sample": sample}
+            # the reference's evaluator (per-user fp32 scores + mask + sort), oracle port, 256 users on the host
+            sys.path.insert(0, str(ROOT / "oracle"))
+            import credgcn_oracle as orc
+            fu_h, fi_h = f_u.cpu().numpy(), f_i.cpu().numpy()
+            tr = (gr.samp_indptr.cpu().numpy(), gr.samp_idx.cpu().numpy().astype(np.int64))
+            t0 = time.perf_counter()
+            orc.full_rank_topk(fu_h, fi_h, np.arange(256), tr, 20)
+            line["eval_full_rank"]["cpu_port_ms_per_user"] = 1e3 * (time.perf_counter() - t0) / 256
     print(json.dumps(line))
 
 

@@ -510,6 +510,103 @@ __global__ void __launch_bounds__(256) k_rescore(const int64_t* __restrict__ use
   }
 }
 
+// ---- exact redo of the rows whose proof failed: one CTA per row, items spread over the threads -----------
+// The tiled fp32 kernel (eval.cu) streams the whole catalogue through ONE CTA per 64 users: ~3 ms on C2 however
+// few of the 64 rows are live, which tripled the evaluation time when 4 rows of 31 668 needed the redo.  Here a
+// row's items are scored by 256 threads (same fmaf chain -> same bits), every thread keeps its best K in shared
+// memory (replace-the-weakest), and K rounds of a block-wide arg-best emit the row in (score desc, id asc) order.
+constexpr int ER_THREADS = 256;
+
+__global__ void __launch_bounds__(ER_THREADS) k_eval_redo_rows(const int64_t* __restrict__ users,
+                                                               const int32_t* __restrict__ row_list,
+                                                               const int32_t* __restrict__ n_rows_dev,
+                                                               const float* __restrict__ f_u,
+                                                               const float* __restrict__ f_i, int32_t I, int32_t d,
+                                                               const int64_t* __restrict__ tr_indptr,
+                                                               const int32_t* __restrict__ tr_idx, int32_t K,
+                                                               int32_t* __restrict__ out_ids,
+                                                               float* __restrict__ out_scores) {
+  extern __shared__ __align__(16) unsigned char er_smem[];
+  float* urow = reinterpret_cast<float*>(er_smem);                       // [d]
+  float* ls = urow + d;                                                  // [K][ER_THREADS]
+  int32_t* li = reinterpret_cast<int32_t*>(ls + size_t(K) * ER_THREADS);  // [K][ER_THREADS]
+  __shared__ float red_s[ER_THREADS / 32];
+  __shared__ int32_t red_i[ER_THREADS / 32];
+  __shared__ int red_t[ER_THREADS / 32];
+  __shared__ int win_t;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_rows = *n_rows_dev;
+  for (int rr = blockIdx.x; rr < n_rows; rr += gridDim.x) {
+    const int64_t r = row_list[rr];
+    const int64_t uid = users[r];
+    const int64_t lo = __ldg(tr_indptr + uid), hi = __ldg(tr_indptr + uid + 1);
+    __syncthreads();                                                     // previous row's lists are consumed
+    for (int k = tid; k < d; k += ER_THREADS) urow[k] = f_u[uid * d + k];
+    for (int p = 0; p < K; ++p) { ls[p * ER_THREADS + tid] = -FLT_MAX; li[p * ER_THREADS + tid] = INT32_MAX; }
+    __syncthreads();
+    float thr = -FLT_MAX;                 // weakest kept entry of this thread's list (empty slots: -FLT_MAX / INT32_MAX)
+    int32_t thr_id = INT32_MAX;
+    int weakest = 0;
+    const float4* u4 = reinterpret_cast<const float4*>(urow);
+    for (int32_t i = tid; i < I; i += ER_THREADS) {
+      const float4* i4 = reinterpret_cast<const float4*>(f_i + int64_t(i) * d);
+      float acc = 0.f;
+      for (int k4 = 0; k4 < d / 4; ++k4) {   // same fmaf order as k_eval_fp32 / k_rescore
+        const float4 a = u4[k4], b = __ldg(i4 + k4);
+        acc = fmaf(a.x, b.x, acc);
+        acc = fmaf(a.y, b.y, acc);
+        acc = fmaf(a.z, b.z, acc);
+        acc = fmaf(a.w, b.w, acc);
+      }
+      const float sc = tc_in_row(tr_idx, lo, hi, i) ? TC_MASKED : acc;
+      if (tc_better(sc, i, thr, thr_id)) {
+        ls[weakest * ER_THREADS + tid] = sc;
+        li[weakest * ER_THREADS + tid] = i;
+        thr = sc;
+        thr_id = i;
+        for (int p = 0; p < K; ++p) {        // new weakest
+          const float ps = ls[p * ER_THREADS + tid];
+          const int32_t pi = li[p * ER_THREADS + tid];
+          if (tc_better(thr, thr_id, ps, pi)) { thr = ps; thr_id = pi; weakest = p; }
+        }
+      }
+    }
+    // K rounds: every thread offers the best entry it still holds, the block picks the overall best
+    for (int out = 0; out < K; ++out) {
+      float bs = -FLT_MAX;
+      int32_t bi = INT32_MAX;
+      int bp = 0;
+      for (int p = 0; p < K; ++p) {
+        const float ps = ls[p * ER_THREADS + tid];
+        const int32_t pi = li[p * ER_THREADS + tid];
+        if (tc_better(ps, pi, bs, bi)) { bs = ps; bi = pi; bp = p; }
+      }
+      float ws = bs;
+      int32_t wi = bi;
+      int wt = tid;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float os = __shfl_xor_sync(0xffffffffu, ws, o);
+        const int32_t oi = __shfl_xor_sync(0xffffffffu, wi, o);
+        const int ot = __shfl_xor_sync(0xffffffffu, wt, o);
+        if (tc_better(os, oi, ws, wi)) { ws = os; wi = oi; wt = ot; }
+      }
+      if (lane == 0) { red_s[warp] = ws; red_i[warp] = wi; red_t[warp] = wt; }
+      __syncthreads();
+      if (tid == 0) {
+        for (int w = 1; w < ER_THREADS / 32; ++w)
+          if (tc_better(red_s[w], red_i[w], ws, wi)) { ws = red_s[w]; wi = red_i[w]; wt = red_t[w]; }
+        out_ids[r * K + out] = wi;
+        out_scores[r * K + out] = ws;
+        win_t = wt;
+      }
+      __syncthreads();
+      if (tid == win_t) { ls[bp * ER_THREADS + tid] = -FLT_MAX; li[bp * ER_THREADS + tid] = INT32_MAX; }   // taken
+      __syncthreads();
+    }
+  }
+}
+
 struct TcConfig {
   int KC, BC, NG, stride;   // stride = candidates per user handed to k_rescore (32 or 64)
 };
@@ -614,8 +711,12 @@ int eval_topk_tc(const int64_t* users, int64_t n_users, const float* f_u, const 
   }
 #undef CGX_TC_ARGS
   if (redo_rows != nullptr) {   // rows whose completeness proof failed: exact kernel, count read on device
-    CGX_TRY(eval_fp32_rows(users, redo, n_redo, n_users, f_u, f_i, I, d, tr_indptr, tr_idx, K, out_ids, out_scores,
-                           stream));
+    const size_t er_smem = size_t(d) * 4 + size_t(K) * ER_THREADS * 8;
+    CGX_CUDA(cudaFuncSetAttribute(k_eval_redo_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)er_smem));
+    const int64_t er_grid = n_users < 148 * 2 ? n_users : 148 * 2;   // persistent over the device-side row list
+    k_eval_redo_rows<<<(unsigned)er_grid, ER_THREADS, er_smem, stream>>>(users, redo, n_redo, f_u, f_i, I, d, tr_indptr,
+                                                                        tr_idx, K, out_ids, out_scores);
+    CGX_LAUNCH_CHECK();
     if (getenv("CGX_DEBUG_EVAL") != nullptr) {   // diagnostics only: synchronises
       unsigned int h[2];
       CGX_CUDA(cudaMemcpyAsync(h, scal, 8, cudaMemcpyDeviceToHost, stream));

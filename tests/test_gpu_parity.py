@@ -771,3 +771,22 @@ def test_spmm_geometry_for_tables_beyond_l2_gives_the_same_bits(cg, d):
         lib().cgx_spmm_set_l2_table_bytes(old)
     for a, b in zip(got, want):
         assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+
+
+@pytest.mark.parametrize("K", [5, 20, 40])
+def test_tensor_core_topk_redo_rows_when_every_score_ties(cg, K):
+    """All items identical: every approximate score ties, no completeness proof can hold, and every row goes
+    through the exact per-row redo kernel -- the answer must still be the fp32 kernel's (lowest unmasked ids first,
+    masked train items last with -1e9)."""
+    U, I, d = 300, 1000, 64
+    sg = cg["synth"].make_graph("C1", num_users=U, num_items=I, num_edges=20_000)
+    rng = np.random.default_rng(K)
+    fu = torch.tensor((rng.standard_normal((U, d)) * 0.3).astype(np.float32), device=DEV)
+    fi = torch.tensor(np.repeat((rng.standard_normal((1, d)) * 0.3).astype(np.float32), I, 0), device=DEV)
+    fi[500:] *= 0.5                                   # two plateaus, so that the sign of the user's score matters
+    ev = cg["evaluate"]
+    csr = ev._device_csr(orc.edges_to_user_csr(sg.train_edges, U), DEV)
+    users = torch.arange(U)
+    ids0, sc0 = ev.topk_device(fu, fi, users, csr, K, "fp32")
+    ids1, sc1 = ev.topk_device(fu, fi, users, csr, K, "bf16x3")
+    assert torch.equal(ids0, ids1) and torch.equal(sc0, sc1)
