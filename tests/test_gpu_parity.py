@@ -8,8 +8,12 @@ import numpy as np
 import pytest
 import torch
 
+import pathlib
+
 import credgcn_oracle as orc
 from conftest import ORDER, VARIANTS, load_golden, rel_err
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -790,3 +794,35 @@ def test_tensor_core_topk_redo_rows_when_every_score_ties(cg, K):
     ids0, sc0 = ev.topk_device(fu, fi, users, csr, K, "fp32")
     ids1, sc1 = ev.topk_device(fu, fi, users, csr, K, "bf16x3")
     assert torch.equal(ids0, ids1) and torch.equal(sc0, sc1)
+
+
+@pytest.mark.parametrize("variant", ["v2", "cu", "da"])
+def test_file_driven_main_jsonl_to_checkpoint(cg, variant, tmp_path, capsys):
+    """The reference's main() end to end on its own formats: review JSONL -> md5 split -> npy/pkl graph files ->
+    credibility CSV -> training with validation -> best_model*.pt with the reference's state_dict keys ->
+    test metrics (lightgcn_cu.py:690-703, 555-688).  73 items only, so K is cut to 5 / 10."""
+    import pickle
+    config, train = cg["config"], cg["train"]
+    saved = config.cfg
+    cfg = config.CFG()
+    cfg.jsonl_path = str(ROOT / "tests" / "golden" / "tiny_reviews.jsonl")
+    cfg.out_dir, cfg.device, cfg.variant = str(tmp_path), "cuda:0", variant
+    cfg.epochs, cfg.eval_every, cfg.batch_size, cfg.emb_dim, cfg.num_layers = 4, 2, 32, 16, 2
+    cfg.Ks, cfg.sampled_negatives = [5, 10], 20
+    cfg.cred_csv_path = str(tmp_path / "cred.csv")
+    config.cfg = cfg
+    try:
+        from credgcn import ingest
+        ingest.build_graph_from_jsonl(cfg)
+        u2 = pickle.load(open(tmp_path / "model" / "user2idx.pkl", "rb"))
+        with open(cfg.cred_csv_path, "w") as f:
+            f.write("user_id,credibility\n" + "".join(f"{u},{(k % 10) / 9:.4f}\n" for k, u in enumerate(u2)))
+        train.main()                                     # graph files exist -> "Skipping construction" -> train
+    finally:
+        config.cfg = saved
+    out = capsys.readouterr().out
+    assert "Graph files exist. Skipping construction." in out and "TEST metrics" in out and "Epoch" in out
+    ck = tmp_path / "model" / ("best_model_cred.pt" if variant == "cu" else "best_model.pt")
+    sd = torch.load(ck, map_location="cpu")
+    assert set(sd) == {"user_emb.weight", "item_emb.weight"}
+    assert sd["user_emb.weight"].shape == (len(u2), 16) and torch.isfinite(sd["item_emb.weight"]).all()
