@@ -81,6 +81,12 @@ _SIGNATURES = {
     "cgx_comm_ipc_close": (C.c_int, [_P]),
     "cgx_comm_allreduce": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_size_t, C.c_size_t, C.c_size_t,
                                      C.c_int64, _P, _P]),
+    "cgx_comm_timing": (C.c_int, [_P]),
+    "cgx_spmm_set_push_peers": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "cgx_spmm_push": (C.c_int, [_CSR, C.c_int, C.c_int32, _P, _P, C.c_size_t, C.c_int, C.c_int, C.c_int32, _P,
+                                C.c_size_t, _P]),
+    "cgx_comm_allreduce_pushed": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_size_t, C.c_size_t,
+                                            C.c_size_t, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
     "cgx_eval_topk_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int]),
     "cgx_eval_topk": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.c_int, _P,
                                 _P, _P, C.c_size_t, _P]),

@@ -27,6 +27,8 @@
 //     exchange is latency-bound, not wire-bound.  A peer's in[parity] is next overwritten two exchanges later,
 //     i.e. after that peer has passed barrier A of the exchange in between, which this rank only signals once
 //     this kernel has completed.
+//   * above 2 ranks the propagation uses the PUSHED form (k_p2p_reduce_pushed, below): the SpMM epilogue has already
+//     stored every partial row into its owner's staging slot, so the reduce needs local loads only.
 //   * the epoch is a device-side counter (cgx_tick before every exchange) that advances identically on all
 //     ranks (the propagation schedule is deterministic), so a whole step can be replayed as a CUDA graph.
 #include <stdlib.h>
@@ -59,11 +61,20 @@ __device__ __forceinline__ float4 ld_peer(const float4* p) {   // written by ano
   return r;
 }
 
+__device__ __forceinline__ unsigned long long p2p_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // flag page layout (uint32): [0 .. R) barrier A slots, [R .. 2R) barrier B slots, [2R] CTA arrival counter
 __global__ void __launch_bounds__(P2P_THREADS) k_p2p_allreduce(P2PPeers peers, int rank, int world, size_t in_off,
                                                                size_t out_off, size_t flag_off, int64_t n4,
                                                                const unsigned long long* __restrict__ epoch_dev,
-                                                               int one_shot) {
+                                                               int one_shot, unsigned long long* dbg) {
+  // dbg (CGX_P2P_TIMING=1): ns spent in [0] barrier A, [1] reduce + delivery, [2] barrier B; [3] launches; [4] scratch
+  unsigned long long t0 = 0;
+  if (dbg && blockIdx.x == 0 && threadIdx.x == 0) t0 = p2p_now();
   const uint32_t epoch = uint32_t(*epoch_dev);   // device-side counter: the launch is replayable in a CUDA graph
   uint32_t* my_flags = reinterpret_cast<uint32_t*>(peers.base[rank] + flag_off);
   // ---- barrier A: all partials complete ----
@@ -75,6 +86,12 @@ __global__ void __launch_bounds__(P2P_THREADS) k_p2p_allreduce(P2PPeers peers, i
     while (ld_acquire_sys(my_flags + threadIdx.x) < epoch) __nanosleep(64);
   }
   __syncthreads();
+  if (dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+    const unsigned long long t1 = p2p_now();
+    dbg[0] += t1 - t0;
+    dbg[3] += 1;
+    dbg[4] = t1;
+  }
   // ---- reduce-scatter + all-gather of my slice (one-shot: the whole table, stored locally only) ----
   const int64_t per = one_shot ? n4 : (n4 + world - 1) / world;
   const int64_t lo = one_shot ? 0 : int64_t(rank) * per;
@@ -115,7 +132,10 @@ __global__ void __launch_bounds__(P2P_THREADS) k_p2p_allreduce(P2PPeers peers, i
       }
     }
   }
-  if (one_shot) return;
+  if (one_shot) {
+    if (dbg && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) dbg[1] += p2p_now() - dbg[4];   // one CTA's view
+    return;
+  }
   // ---- barrier B: every slice delivered ----
   __threadfence_system();
   __syncthreads();
@@ -123,12 +143,83 @@ __global__ void __launch_bounds__(P2P_THREADS) k_p2p_allreduce(P2PPeers peers, i
   if (threadIdx.x == 0) last = atomicAdd(my_flags + 2 * world, 1u) == gridDim.x - 1;
   __syncthreads();
   if (!last) return;
+  unsigned long long t2 = 0;
+  if (dbg && threadIdx.x == 0) {
+    t2 = p2p_now();
+    dbg[1] += t2 - dbg[4];
+  }
   if (threadIdx.x == 0) my_flags[2 * world] = 0;   // self-resetting
   if (threadIdx.x < world) {
     __threadfence_system();
     st_release_sys(reinterpret_cast<uint32_t*>(peers.base[threadIdx.x] + flag_off) + world + rank, epoch);
     while (ld_acquire_sys(my_flags + world + threadIdx.x) < epoch) __nanosleep(64);
   }
+  __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[2] += p2p_now() - t2;
+}
+
+// Pushed form (cgx_spmm_push + cgx_comm_allreduce_pushed): the SpMM already stored every partial row into the
+// staging area of the row's OWNER, slot = source rank, so after barrier A the owner sums its rows_per rows over the
+// world slots with LOCAL loads (rank order, same bits as the pull form), stores the reduced rows into every rank's
+// out region, and barrier B closes the exchange.  No remote load is left on the path.
+__global__ void __launch_bounds__(P2P_THREADS) k_p2p_reduce_pushed(P2PPeers peers, int rank, int world,
+                                                                   size_t stage_off, size_t out_off, size_t flag_off,
+                                                                   int64_t n_rows, int32_t row4, int32_t rows_per,
+                                                                   const unsigned long long* __restrict__ epoch_dev,
+                                                                   unsigned long long* dbg) {
+  unsigned long long t0 = 0;
+  if (dbg && blockIdx.x == 0 && threadIdx.x == 0) t0 = p2p_now();
+  const uint32_t epoch = uint32_t(*epoch_dev);
+  uint32_t* my_flags = reinterpret_cast<uint32_t*>(peers.base[rank] + flag_off);
+  // ---- barrier A: every peer's SpMM (the kernel before its exchange kernel) has completed its pushes ----
+  if (blockIdx.x == 0 && threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<uint32_t*>(peers.base[threadIdx.x] + flag_off) + rank, epoch);
+  }
+  if (threadIdx.x < world) {
+    while (ld_acquire_sys(my_flags + threadIdx.x) < epoch) __nanosleep(64);
+  }
+  __syncthreads();
+  if (dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+    const unsigned long long t1 = p2p_now();
+    dbg[0] += t1 - t0;
+    dbg[3] += 1;
+    dbg[4] = t1;
+  }
+  const int64_t lo_row = int64_t(rank) * rows_per;
+  const int64_t hi_row = lo_row + rows_per < n_rows ? lo_row + rows_per : n_rows;
+  const int64_t n4 = hi_row > lo_row ? (hi_row - lo_row) * row4 : 0;
+  const int64_t slot4 = int64_t(rows_per) * row4;
+  const float4* stage = reinterpret_cast<const float4*>(peers.base[rank] + stage_off);
+  const int64_t stride = int64_t(gridDim.x) * P2P_THREADS;
+  for (int64_t i = int64_t(blockIdx.x) * P2P_THREADS + threadIdx.x; i < n4; i += stride) {
+    float4 acc = ld_peer(stage + i);                       // written by rank 0's SpMM (maybe a remote GPU): no L1
+    for (int p = 1; p < world; ++p) {
+      const float4 v = ld_peer(stage + int64_t(p) * slot4 + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    for (int p = 0; p < world; ++p) reinterpret_cast<float4*>(peers.base[p] + out_off)[lo_row * row4 + i] = acc;
+  }
+  // ---- barrier B: every slice delivered ----
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(my_flags + 2 * world, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  unsigned long long t2 = 0;
+  if (dbg && threadIdx.x == 0) {
+    t2 = p2p_now();
+    dbg[1] += t2 - dbg[4];
+  }
+  if (threadIdx.x == 0) my_flags[2 * world] = 0;   // self-resetting
+  if (threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<uint32_t*>(peers.base[threadIdx.x] + flag_off) + world + rank, epoch);
+    while (ld_acquire_sys(my_flags + world + threadIdx.x) < epoch) __nanosleep(64);
+  }
+  __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[2] += p2p_now() - t2;
 }
 
 }  // namespace cgx
@@ -168,6 +259,57 @@ extern "C" int cgx_comm_ipc_close(void* peer_base) {
   return CGX_OK;
 }
 
+static unsigned long long* g_p2p_dbg = nullptr;
+
+/* CGX_P2P_TIMING=1 diagnostics: ns accumulated in {barrier A, reduce + delivery, barrier B} and the number of
+ * exchanges since the last call (synchronises the device; zeros when timing is off). */
+extern "C" int cgx_comm_timing(uint64_t* out4) {
+  CGX_REQUIRE(out4 != nullptr, CGX_ERR_ARG, "comm_timing: NULL pointer");
+  for (int i = 0; i < 4; ++i) out4[i] = 0;
+  if (g_p2p_dbg == nullptr) return CGX_OK;
+  CGX_CUDA(cudaDeviceSynchronize());
+  CGX_CUDA(cudaMemcpy(out4, g_p2p_dbg, 32, cudaMemcpyDeviceToHost));
+  CGX_CUDA(cudaMemset(g_p2p_dbg, 0, 64));
+  return CGX_OK;
+}
+
+static int p2p_dbg_buffer(unsigned long long** out) {
+  static unsigned long long* dbg = nullptr;
+  if (dbg == nullptr && getenv("CGX_P2P_TIMING") != nullptr) {
+    CGX_CUDA(cudaMalloc(&dbg, 64));
+    CGX_CUDA(cudaMemset(dbg, 0, 64));
+    g_p2p_dbg = dbg;
+  }
+  *out = dbg;
+  return CGX_OK;
+}
+
+extern "C" int cgx_comm_allreduce_pushed(int rank, int world, void* const* peer_bases, size_t stage_off, size_t out_off,
+                                         size_t flag_off, int64_t n_rows, int32_t d, int32_t rows_per,
+                                         const uint64_t* epoch_dev, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CGX_REQUIRE(world >= 1 && world <= P2P_MAX_RANKS && rank >= 0 && rank < world && peer_bases, CGX_ERR_ARG,
+              "comm_allreduce_pushed: bad rank/world");
+  CGX_REQUIRE(n_rows > 0 && d > 0 && d % 4 == 0 && rows_per > 0 && int64_t(rows_per) * world >= n_rows &&
+                  stage_off % 16 == 0 && out_off % 16 == 0 && flag_off % 16 == 0 && epoch_dev != nullptr,
+              CGX_ERR_ARG, "comm_allreduce_pushed: bad sizes/offsets");
+  P2PPeers peers;
+  for (int p = 0; p < world; ++p) {
+    CGX_REQUIRE(peer_bases[p] != nullptr, CGX_ERR_ARG, "comm_allreduce_pushed: NULL peer buffer");
+    peers.base[p] = static_cast<char*>(peer_bases[p]);
+  }
+  unsigned long long* dbg = nullptr;
+  CGX_TRY(p2p_dbg_buffer(&dbg));
+  int64_t blocks = ceil_div(int64_t(rows_per) * (d / 4), P2P_THREADS);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  k_p2p_reduce_pushed<<<(unsigned)blocks, P2P_THREADS, 0, stream>>>(
+      peers, rank, world, stage_off, out_off, flag_off, n_rows, d / 4, rows_per,
+      reinterpret_cast<const unsigned long long*>(epoch_dev), dbg);
+  CGX_LAUNCH_CHECK();
+  return CGX_OK;
+}
+
 extern "C" int cgx_comm_allreduce(int rank, int world, void* const* peer_bases, size_t in_off, size_t out_off,
                                   size_t flag_off, int64_t n_floats, const uint64_t* epoch_dev, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -184,13 +326,15 @@ extern "C" int cgx_comm_allreduce(int rank, int world, void* const* peer_bases, 
   const int64_t n4 = n_floats / 4;
   static const int one_shot_max = getenv("CGX_P2P_ONESHOT_MAX") ? atoi(getenv("CGX_P2P_ONESHOT_MAX")) : 2;
   const int one_shot = world <= one_shot_max ? 1 : 0;
+  unsigned long long* dbg = nullptr;
+  CGX_TRY(p2p_dbg_buffer(&dbg));
   const int64_t per = one_shot ? n4 : ceil_div(n4, world);
   int64_t blocks = ceil_div(per, P2P_THREADS * 4);
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
   k_p2p_allreduce<<<(unsigned)blocks, P2P_THREADS, 0, stream>>>(peers, rank, world, in_off, out_off, flag_off, n4,
                                                              reinterpret_cast<const unsigned long long*>(epoch_dev),
-                                                             one_shot);
+                                                             one_shot, dbg);
   CGX_LAUNCH_CHECK();
   return CGX_OK;
 }

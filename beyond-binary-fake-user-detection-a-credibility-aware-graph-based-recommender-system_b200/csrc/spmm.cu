@@ -128,13 +128,32 @@ __device__ __forceinline__ void gather_range(const int32_t* __restrict__ idx, co
   gather_batches<G, V, UNR, HINT>(idx, val, begin, end, X, lane, mask, c, w, acc);
 }
 
+// Push mode of the user-sharded propagation (cgx_spmm_push): output row r is not stored to Y but straight into the
+// staging area of the rank that OWNS row r (rows_per consecutive rows per rank), slot `rank` -- a posted store over
+// NVLink, issued row by row while the rest of the product is still being gathered.  The exchange kernel
+// (comm.cu, pushed form) then sums the slots with local reads only.
+__constant__ char* c_push_base[16];        // peer-mapped communication buffers, index = rank (cgx_spmm_set_push_peers)
+struct SpmmPush {
+  unsigned long long off;                  // byte offset of the staging area inside every communication buffer
+  int32_t rows_per;                        // rows owned by each rank; 0 = push mode off
+  int32_t rank;
+};
+
 template <int G, int V>
 __device__ __forceinline__ void epilogue(int64_t row, int lane, const float4 (&y)[V], float4* __restrict__ Y,
-                                         const float4* ACC_IN, float4* ACC_OUT, float acc_scale) {
+                                         const float4* ACC_IN, float4* ACC_OUT, float acc_scale,
+                                         const SpmmPush ps = SpmmPush{0ull, 0, 0}) {
   constexpr int ROW4 = G * V;
+  float4* ypush = nullptr;
+  if (ps.rows_per > 0) {
+    const int owner = int(row / ps.rows_per);
+    ypush = reinterpret_cast<float4*>(c_push_base[owner] + ps.off) +
+            (int64_t(ps.rank) * ps.rows_per + (row - int64_t(owner) * ps.rows_per)) * ROW4;
+  }
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     const int64_t o = row * ROW4 + v * G + lane;
+    if (ypush) ypush[v * G + lane] = y[v];
     if (Y) Y[o] = y[v];
     if (ACC_OUT) {
       float4 a = ACC_IN ? ACC_IN[o] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -155,7 +174,7 @@ struct SpmmSched {
 // partial sum; for rows up to CGX_HUGE_ROW the chunk that arrives last (per-row counter, release /
 // acquire through __threadfence) adds the partials IN CHUNK ORDER and runs the epilogue, so the
 // result does not depend on which chunk happened to be last.
-template <int G, int V, int UNR, int HINT, int MINB, bool NZ = false>
+template <int G, int V, int UNR, int HINT, int MINB, bool NZ = false, bool PUSH = false>
 __global__ void __launch_bounds__(SP_THREADS, MINB) k_spmm(const int64_t* __restrict__ indptr,
                                                            const int32_t* __restrict__ idx,
                                                            const float* __restrict__ val, int32_t n_rows,
@@ -163,7 +182,9 @@ __global__ void __launch_bounds__(SP_THREADS, MINB) k_spmm(const int64_t* __rest
                                                            float4* __restrict__ Y, const float4* ACC_IN,
                                                            float4* ACC_OUT, float acc_scale, float4* partial,
                                                            const uint8_t* __restrict__ nz,
-                                                           const int4* __restrict__ work) {
+                                                           const int4* __restrict__ work, const SpmmPush ps_in) {
+  // PUSH = false: a compile-time "off", so that the ordinary instantiations carry no trace of the push path
+  const SpmmPush ps = PUSH ? ps_in : SpmmPush{0ull, 0, 0};
   constexpr int ROW4 = G * V;
   // Programmatic dependent launch: let the next kernel of the stream start its own prologue now, and run
   // THIS kernel's prologue (schedule lookups, first batch of column ids / values -- graph constants) while the
@@ -195,7 +216,7 @@ __global__ void __launch_bounds__(SP_THREADS, MINB) k_spmm(const int64_t* __rest
     if (item >= sc.n_chunks) {
       // (loading ACC_IN[row] before the gathers, to take it off the dependency chain, was measured SLOWER: the
       // four extra live registers spill at the 64-register cap -- C2 0.514 -> 0.553 ms, C4 155 -> 160 ms)
-      epilogue<G, V>(wd.w, lane, acc, Y, ACC_IN, ACC_OUT, acc_scale);
+      epilogue<G, V>(wd.w, lane, acc, Y, ACC_IN, ACC_OUT, acc_scale, ps);
       return;
     }
     const int32_t k = wd.w;
@@ -216,7 +237,7 @@ __global__ void __launch_bounds__(SP_THREADS, MINB) k_spmm(const int64_t* __rest
 #pragma unroll
       for (int v = 0; v < V; ++v) acc[v] = add4(acc[v], __ldcg(partial + int64_t(c) * ROW4 + v * G + lane));
     }
-    epilogue<G, V>(int64_t(__ldg(sc.perm + k)), lane, acc, Y, ACC_IN, ACC_OUT, acc_scale);
+    epilogue<G, V>(int64_t(__ldg(sc.perm + k)), lane, acc, Y, ACC_IN, ACC_OUT, acc_scale, ps);
     if (lane == 0) sc.arrive[k] = 0;       // self-resetting for the next launch
     return;
   }
@@ -252,7 +273,7 @@ __global__ void __launch_bounds__(SP_THREADS, MINB) k_spmm(const int64_t* __rest
 #pragma unroll
       for (int v = 0; v < V; ++v) acc[v] = add4(acc[v], __ldcg(partial + int64_t(c) * ROW4 + v * G + lane));
     }
-    epilogue<G, V>(row, lane, acc, Y, ACC_IN, ACC_OUT, acc_scale);
+    epilogue<G, V>(row, lane, acc, Y, ACC_IN, ACC_OUT, acc_scale, ps);
     if (lane == 0) sc.arrive[k] = 0;       // self-resetting for the next launch
     return;
   }
@@ -268,7 +289,7 @@ __global__ void __launch_bounds__(SP_THREADS, MINB) k_spmm(const int64_t* __rest
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
   gather_batches<G, V, UNR, HINT, NZ>(idx, val, begin, end, X, lane, mask, cf, wf, acc, nz);
-  epilogue<G, V>(row, lane, acc, Y, ACC_IN, ACC_OUT, acc_scale);
+  epilogue<G, V>(row, lane, acc, Y, ACC_IN, ACC_OUT, acc_scale, ps);
 }
 
 // Persistent, software-pipelined form of k_spmm: a fixed grid of groups walks the flattened work list
@@ -351,7 +372,7 @@ __global__ void __launch_bounds__(SP_THREADS, MINB) k_spmm_p(const int4* __restr
 template <int G, int V>
 __global__ void __launch_bounds__(SP_THREADS) k_spmm_finish(SpmmSched sc, const float4* __restrict__ partial,
                                                             float4* __restrict__ Y, const float4* ACC_IN,
-                                                            float4* ACC_OUT, float acc_scale) {
+                                                            float4* ACC_OUT, float acc_scale, const SpmmPush ps) {
   constexpr int GROUPS = SP_THREADS / G;
   constexpr int ROW4 = G * V;
   __shared__ float4 red[GROUPS][ROW4];
@@ -375,7 +396,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_spmm_finish(SpmmSched sc, const 
       for (int g = 1; g < GROUPS; ++g) s = add4(s, red[g][v * G + lane]);
       acc[v] = s;
     }
-    epilogue<G, V>(int64_t(__ldg(sc.perm + k)), lane, acc, Y, ACC_IN, ACC_OUT, acc_scale);
+    epilogue<G, V>(int64_t(__ldg(sc.perm + k)), lane, acc, Y, ACC_IN, ACC_OUT, acc_scale, ps);
   }
 }
 
@@ -426,10 +447,10 @@ static int spmm_waves() {
   return v < 1 ? 1 : v;
 }
 
-template <int G, int V, int UNR, int HINT, int MINB, bool NZ = false>
+template <int G, int V, int UNR, int HINT, int MINB, bool NZ = false, bool PUSH = false>
 static int launch_spmm(const cgx_csr* m, const float* val, const float* X, float* Y, const float* ACC_IN,
                        float* ACC_OUT, float acc_scale, void* workspace, size_t workspace_bytes,
-                       cudaStream_t stream, const uint8_t* nz = nullptr) {
+                       cudaStream_t stream, const uint8_t* nz = nullptr, const SpmmPush ps = SpmmPush{0ull, 0, 0}) {
   constexpr int GROUPS = SP_THREADS / G;
   float4* partial = nullptr;
   if (m->n_long > 0) {
@@ -440,7 +461,7 @@ static int launch_spmm(const cgx_csr* m, const float* val, const float* X, float
   }
   SpmmSched sc{m->perm, m->chunk_ptr, m->chunk_row, m->arrive, m->n_long, m->n_chunks, m->n_huge};
   const int64_t items = int64_t(m->n_chunks) + (m->n_rows - m->n_long);
-  if (!NZ && m->work != nullptr && spmm_persistent()) {
+  if (!NZ && ps.rows_per == 0 && m->work != nullptr && spmm_persistent()) {
     int64_t blocks = ceil_div(items, GROUPS);
     const int64_t resident = int64_t(148) * MINB * spmm_waves();     // CTAs that fit the chip at once (x waves)
     if (blocks > resident) blocks = resident;
@@ -459,16 +480,16 @@ static int launch_spmm(const cgx_csr* m, const float* val, const float* X, float
     attr[0].val.programmaticStreamSerializationAllowed = spmm_pdl() ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CGX_CUDA(cudaLaunchKernelEx(&cfg, k_spmm<G, V, UNR, HINT, MINB, NZ>, m->indptr, m->idx, val, m->n_rows, sc,
+    CGX_CUDA(cudaLaunchKernelEx(&cfg, k_spmm<G, V, UNR, HINT, MINB, NZ, PUSH>, m->indptr, m->idx, val, m->n_rows, sc,
                                 reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(Y),
                                 reinterpret_cast<const float4*>(ACC_IN), reinterpret_cast<float4*>(ACC_OUT), acc_scale,
-                                partial, nz, spmm_use_work() ? static_cast<const int4*>(m->work) : nullptr));
+                                partial, nz, spmm_use_work() ? static_cast<const int4*>(m->work) : nullptr, ps));
   }
   CGX_LAUNCH_CHECK();
   if (m->n_huge > 0) {
     k_spmm_finish<G, V><<<(unsigned)m->n_huge, SP_THREADS, 0, stream>>>(
         sc, partial, reinterpret_cast<float4*>(Y), reinterpret_cast<const float4*>(ACC_IN),
-        reinterpret_cast<float4*>(ACC_OUT), acc_scale);
+        reinterpret_cast<float4*>(ACC_OUT), acc_scale, ps);
     CGX_LAUNCH_CHECK();
   }
   return CGX_OK;
@@ -485,16 +506,16 @@ static int spmm_variant() {
   return v;
 }
 
-#define CGX_SPMM_ARGS m, val, X, Y, ACC_IN, ACC_OUT, acc_scale, ws, ws_bytes, stream
+#define CGX_SPMM_ARGS m, val, X, Y, ACC_IN, ACC_OUT, acc_scale, ws, ws_bytes, stream, nz, ps
 
 static int spmm_dispatch(const cgx_csr* m, int use_bwd, int32_t d, const float* X, float* Y, const float* ACC_IN,
                          float* ACC_OUT, float acc_scale, void* ws, size_t ws_bytes, cudaStream_t stream,
-                         const uint8_t* nz = nullptr) {
+                         const uint8_t* nz = nullptr, const SpmmPush ps = SpmmPush{0ull, 0, 0}) {
   CGX_REQUIRE(m && m->indptr && m->perm && (m->nnz == 0 || (m->idx && m->val_fwd && m->val_bwd)) && X, CGX_ERR_ARG,
               "spmm: NULL pointer");
   CGX_REQUIRE(m->n_long == 0 || (m->chunk_ptr && m->chunk_row && m->arrive), CGX_ERR_ARG,
               "spmm: chunk tables missing");
-  CGX_REQUIRE(Y || ACC_OUT, CGX_ERR_ARG, "spmm: no output requested");
+  CGX_REQUIRE(Y || ACC_OUT || ps.rows_per > 0, CGX_ERR_ARG, "spmm: no output requested");
   const float* val = use_bwd ? m->val_bwd : m->val_fwd;
   if (m->n_rows == 0) return CGX_OK;
   // Group geometry by regime (profiles/r1_spmm_variants.txt).  Gathered table in L2 (C2/C3: latency-bound): d/4 lanes
@@ -503,17 +524,37 @@ static int spmm_dispatch(const cgx_csr* m, int use_bwd, int32_t d, const float* 
   // (d = 64: 27.3 vs 30.1 ms, d = 128: 53.8 vs 58.6 ms on the 64M-edge shape; on C2 the same split LOSES, 0.65 vs
   // 0.43 ms at d = 64 and 0.71 vs 0.61 ms at d = 128).
   const bool beyond_l2 = int64_t(m->n_cols) * int64_t(d) * 4 > g_l2_table_bytes;
+  if (ps.rows_per > 0) {   // push mode (user-sharded item products): default geometries, with or without row flags
+#define CGX_PUSH_CASE(GG, VV, UU)                                                              \
+    return nz ? launch_spmm<GG, VV, UU, HINT_NC, 4, true, true>(CGX_SPMM_ARGS)                \
+              : launch_spmm<GG, VV, UU, HINT_NC, 4, false, true>(CGX_SPMM_ARGS)
+    switch (d) {
+      case 16: CGX_PUSH_CASE(4, 1, 4);
+      case 32: CGX_PUSH_CASE(8, 1, 8);
+      case 64:
+        if (beyond_l2) { CGX_PUSH_CASE(8, 2, 4); }
+        CGX_PUSH_CASE(16, 1, 8);
+      case 128:
+        if (beyond_l2) { CGX_PUSH_CASE(16, 2, 4); }
+        CGX_PUSH_CASE(32, 1, 8);
+      case 256: CGX_PUSH_CASE(32, 2, 4);
+      default:
+        set_error("spmm: emb_dim %d unsupported (16, 32, 64, 128, 256)", d);
+        return CGX_ERR_UNSUPPORTED;
+    }
+#undef CGX_PUSH_CASE
+  }
   if (nz != nullptr) {   // sparse input rows: the default geometry of every width, row loads predicated on nz
     switch (d) {
-      case 16: return launch_spmm<4, 1, 4, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
-      case 32: return launch_spmm<8, 1, 8, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
+      case 16: return launch_spmm<4, 1, 4, HINT_NC, 4, true>(CGX_SPMM_ARGS);
+      case 32: return launch_spmm<8, 1, 8, HINT_NC, 4, true>(CGX_SPMM_ARGS);
       case 64:
-        if (beyond_l2) return launch_spmm<8, 2, 4, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
-        return launch_spmm<16, 1, 8, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
+        if (beyond_l2) return launch_spmm<8, 2, 4, HINT_NC, 4, true>(CGX_SPMM_ARGS);
+        return launch_spmm<16, 1, 8, HINT_NC, 4, true>(CGX_SPMM_ARGS);
       case 128:
-        if (beyond_l2) return launch_spmm<16, 2, 4, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
-        return launch_spmm<32, 1, 8, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
-      case 256: return launch_spmm<32, 2, 4, HINT_NC, 4, true>(CGX_SPMM_ARGS, nz);
+        if (beyond_l2) return launch_spmm<16, 2, 4, HINT_NC, 4, true>(CGX_SPMM_ARGS);
+        return launch_spmm<32, 1, 8, HINT_NC, 4, true>(CGX_SPMM_ARGS);
+      case 256: return launch_spmm<32, 2, 4, HINT_NC, 4, true>(CGX_SPMM_ARGS);
       default: break;
     }
   }
@@ -588,6 +629,25 @@ extern "C" int64_t cgx_spmm_set_l2_table_bytes(int64_t bytes) {
   const int64_t old = g_l2_table_bytes;
   g_l2_table_bytes = bytes < 0 ? (int64_t(96) << 20) : bytes;
   return old;
+}
+
+extern "C" int cgx_spmm_set_push_peers(void* const* peer_bases, int world) {
+  CGX_REQUIRE(peer_bases != nullptr && world >= 1 && world <= 16, CGX_ERR_ARG, "spmm_set_push_peers: bad argument");
+  char* h[16] = {nullptr};
+  for (int p = 0; p < world; ++p) h[p] = static_cast<char*>(peer_bases[p]);
+  CGX_CUDA(cudaMemcpyToSymbol(c_push_base, h, sizeof(h)));
+  return CGX_OK;
+}
+
+extern "C" int cgx_spmm_push(const cgx_csr* m, int use_bwd_values, int32_t d, const float* X,
+                             const uint8_t* x_row_nonzero, size_t stage_off, int rank, int world, int32_t rows_per,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  CGX_REQUIRE(m != nullptr && world >= 1 && world <= 16 && rank >= 0 && rank < world && rows_per > 0 &&
+                  int64_t(rows_per) * world >= m->n_rows && stage_off % 16 == 0,
+              CGX_ERR_ARG, "spmm_push: bad rank / world / rows_per");
+  const SpmmPush ps{(unsigned long long)stage_off, rows_per, rank};
+  return spmm_dispatch(m, use_bwd_values, d, X, nullptr, nullptr, nullptr, 1.0f, workspace, workspace_bytes,
+                       static_cast<cudaStream_t>(stream), x_row_nonzero, ps);
 }
 
 extern "C" int cgx_row_flags(const float* X, int64_t n_rows, int32_t d, uint8_t* flags, void* stream) {

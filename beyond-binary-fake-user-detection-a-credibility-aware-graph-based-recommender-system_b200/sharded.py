@@ -18,6 +18,7 @@ the product backend is `CudaBackend` (libcredgcn.so) and there is no CPU backend
 from __future__ import annotations
 
 import json
+import os
 import time
 
 import numpy as np
@@ -111,6 +112,7 @@ class P2PExchange:
                     peer = C.c_void_p()
                     check(lib().cgx_comm_ipc_open(C.c_char_p(handles[p]), C.byref(peer)))
                     self.bases[p] = peer.value
+            check(lib().cgx_spmm_set_push_peers(self.bases, self.world))   # targets of the fused product + exchange
         self.base = base
         self.bytes = torch.as_tensor(_RawCuda(base.value, total), device=self.device)
         self.epoch_dev = torch.zeros(1, dtype=torch.int64, device=self.device)   # exchanges done so far
@@ -131,6 +133,31 @@ class P2PExchange:
         if 4 * int(np.prod(shape)) > self.region:
             raise _lib.CgxError("P2PExchange: payload larger than the communication regions")
         return self._view(self.slot * self.region, shape)
+
+    def push_enabled(self) -> bool:
+        """Fused SpMM -> owner push + local reduce (cgx_spmm_push / cgx_comm_allreduce_pushed): the default above
+        2 ranks (4 ranks: 0.896 vs 0.975 ms/step).  At 2 ranks the one-shot pull kernel has one barrier less and
+        wins (0.793 vs 0.812 ms).  CGX_P2P_PUSH=1 / 0 forces it on / off."""
+        env = os.environ.get("CGX_P2P_PUSH")
+        return self.world > 1 and (env == "1" or (env is None and self.world > 2))
+
+    def exchange_pushed(self, shape, push_product):
+        """One item-table exchange in pushed form.  `push_product(stage_off, rank, world, rows_per)` must launch the
+        product whose rows are pushed to their owners (CudaBackend.item_rows_push); returns the reduced table."""
+        n_rows, d = int(shape[0]), int(shape[1])
+        rows_per = (n_rows + self.world - 1) // self.world
+        if 4 * self.world * rows_per * d > self.region:
+            raise _lib.CgxError("P2PExchange: payload larger than the communication regions")
+        par = self.slot
+        self.slot ^= 1
+        push_product(par * self.region, self.rank, self.world, rows_per)
+        with torch.cuda.device(self.device):
+            st = stream_ptr(self.device)
+            check(lib().cgx_tick(ptr(self.epoch_dev), st))
+            check(lib().cgx_comm_allreduce_pushed(self.rank, self.world, self.bases, par * self.region,
+                                                  (2 + par) * self.region, self.flag_off, n_rows, d, rows_per,
+                                                  ptr(self.epoch_dev), st))
+        return self._view((2 + par) * self.region, (n_rows, d))
 
     def reduce(self, buf):
         par = self.slot
@@ -191,6 +218,26 @@ class CudaBackend(BackendBase):
         """Partial [I, d]: C x_u (bwd: A^T x_u) summed over THIS shard's users (written into `out` if given)."""
         return self._spmm(self.graph.by_item, x_u, bwd, y=out, sparse=sparse)
 
+    def item_rows_push(self, x_u, bwd, stage_off, rank, world, rows_per, sparse=False):
+        """item_rows whose output rows go straight to their owner rank's staging area (cgx_spmm_push)."""
+        csr = self.graph.by_item
+        x = x_u.contiguous()
+        d = x.shape[1]
+        key = (id(csr), d)
+        if key not in self._ws:
+            self._ws[key] = workspace(lib().cgx_spmm_workspace_bytes(csr.ref(), d), x.device)
+        ws = self._ws[key]
+        with torch.cuda.device(x.device):
+            flags = None
+            if sparse:
+                fkey = ("flags", x.shape[0])
+                if fkey not in self._ws:
+                    self._ws[fkey] = torch.empty(x.shape[0], dtype=torch.uint8, device=x.device)
+                flags = self._ws[fkey]
+                check(lib().cgx_row_flags(ptr(x), x.shape[0], d, ptr(flags), stream_ptr(x.device)))
+            check(lib().cgx_spmm_push(csr.ref(), int(bwd), d, ptr(x), None if flags is None else ptr(flags), stage_off,
+                                      rank, world, rows_per, ptr(ws), ws.numel(), stream_ptr(x.device)))
+
     def user_rows(self, x_i, bwd=False):
         """[U_local, d]: A x_i (bwd: C^T x_i) for this shard's users."""
         return self._spmm(self.graph.by_user, x_i, bwd)
@@ -221,6 +268,10 @@ class ShardedPropagation:
     def _item_exchange(self, x_u, bwd, shape, sparse=False):
         """Partial item table of this shard -> whole item table (one exchange).  sparse: x_u is the loss
         gradient itself (rows mostly zero)."""
+        if hasattr(self.b, "item_rows_push") and getattr(self.ex, "push_enabled", lambda: False)():
+            return self.ex.exchange_pushed(
+                shape, lambda off, rank, world, rows_per: self.b.item_rows_push(x_u, bwd, off, rank, world, rows_per,
+                                                                              sparse))
         buf = self.ex.partial_buffer(shape, x_u.device)
         res = self.b.item_rows(x_u, bwd, out=buf, **self._hint(sparse))
         if res is not buf:                      # backends without an `out` argument return a fresh tensor

@@ -277,6 +277,27 @@ int cgx_comm_ipc_close(void* peer_base);
 int cgx_comm_allreduce(int rank, int world, void* const* peer_bases, size_t in_off, size_t out_off,
                        size_t flag_off, int64_t n_floats, const uint64_t* epoch_dev, void* stream);
 
+/* Fused product + exchange of the user-sharded propagation.  cgx_spmm_push is cgx_spmm(Y only) whose output row r is
+ * stored straight into the communication buffer of the rank that owns row r (rows_per consecutive rows per rank,
+ * owner = r / rows_per), at stage_off + ((rank * rows_per + r % rows_per) * d) floats -- posted NVLink stores issued
+ * from the SpMM epilogue while the rest of the product is still being gathered (x_row_nonzero: optional row flags,
+ * as in cgx_spmm_sparse_rows).  cgx_spmm_set_push_peers registers the peer-mapped buffers once (index = rank).
+ * cgx_comm_allreduce_pushed then sums, on every owner, the `world` staged copies of its rows with LOCAL loads (rank
+ * order: the bits of cgx_comm_allreduce), stores the reduced rows into every rank's out region (float[n_rows, d] at
+ * out_off) and returns when all rows of all owners have arrived.  Needs world * rows_per * d * 4 bytes at stage_off. */
+int cgx_spmm_set_push_peers(void* const* peer_bases, int world);
+int cgx_spmm_push(const cgx_csr* m, int use_bwd_values, int32_t d, const float* X, const uint8_t* x_row_nonzero,
+                  size_t stage_off, int rank, int world, int32_t rows_per,
+                  void* workspace, size_t workspace_bytes, void* stream);
+int cgx_comm_allreduce_pushed(int rank, int world, void* const* peer_bases, size_t stage_off, size_t out_off,
+                              size_t flag_off, int64_t n_rows, int32_t d, int32_t rows_per,
+                              const uint64_t* epoch_dev, void* stream);
+
+/* Diagnostics (CGX_P2P_TIMING=1 in the environment): nanoseconds accumulated inside cgx_comm_allreduce's kernel in
+ * {barrier A, reduce + delivery, barrier B} and the number of exchanges since the last call; out4 is a HOST array.
+ * Synchronises the device.  All zeros when timing is off. */
+int cgx_comm_timing(uint64_t* out4);
+
 /* ------------------------------------------------------------------------------------------
  * Full-rank evaluation.  Replaces the per-user loop of evaluate_full_ranking (V2:691-704):
  * scores of `users` against every item, train items forced to -1e9, best K by

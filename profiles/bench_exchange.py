@@ -19,6 +19,15 @@ for n in (38048 * 64, 2 * 38048 * 64 + 4, 2_000_000 * 128):
             b = ex.partial_buffer((n,), dev); r = ex.reduce(b)
         e.record(); torch.cuda.synchronize()
         out[f"{name}_{n*4/1e6:.1f}MB_us"] = round(a.elapsed_time(e) * 50, 1)
+        if name == "p2p" and os.environ.get("CGX_P2P_TIMING"):
+            import ctypes
+            from credgcn._lib import lib
+            t = (ctypes.c_uint64 * 4)()
+            lib().cgx_comm_timing(t)
+            if t[3]:
+                out[f"p2p_{n*4/1e6:.1f}MB_phases_us"] = {"barrier_a": round(t[0] / t[3] / 1e3, 1),
+                                                        "reduce": round(t[1] / t[3] / 1e3, 1),
+                                                        "barrier_b": round(t[2] / t[3] / 1e3, 1), "n": int(t[3])}
     del p2p
 if rank == 0: print(json.dumps({"world": world, **out}))
 dist.barrier(); dist.destroy_process_group()

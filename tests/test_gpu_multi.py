@@ -42,7 +42,9 @@ def _worker(rank, world, port, out):
         for variant, order in (("v2", "gs"), ("cu", "jacobi"), ("da", "gs")):
           gl = build_local_graph(shard_edges(sg.train_edges, bounds, rank), hi - lo, I, sg.cred[lo:hi], variant, dev)
           outs = {}
-          for ex_name, ex in (("nccl", CollectiveExchange()), ("p2p", p2p)):
+          # p2p = pull kernel (partials read over NVLink); p2p_push = rows pushed to their owner from the SpMM epilogue
+          for ex_name, ex in (("nccl", CollectiveExchange()), ("p2p", p2p), ("p2p_push", p2p)):
+            os.environ["CGX_P2P_PUSH"] = "1" if ex_name == "p2p_push" else "0"
             prop = ShardedPropagation(CudaBackend(gl), K, order, exchange=ex)
             eu_l, ei_d = eu[lo:hi].to(dev).contiguous(), ei.to(dev)
             f_u, f_i = prop.forward(eu_l, ei_d)
@@ -58,7 +60,9 @@ def _worker(rank, world, port, out):
             d_u, d_i = prop.backward(g_u, gi2[0])
             d_u, d_i = d_u + ego_u, d_i + gi2[1]
             outs[ex_name] = (f_u.clone(), f_i.clone(), d_u.clone(), d_i.clone())
-          same = all(torch.equal(a, b) for a, b in zip(outs["nccl"], outs["p2p"]))
+          os.environ.pop("CGX_P2P_PUSH", None)
+          same = (all(torch.equal(a, b) for a, b in zip(outs["nccl"], outs["p2p"])) and
+                  all(torch.equal(a, b) for a, b in zip(outs["nccl"], outs["p2p_push"])))
           if True:
             if rank == 0:      # single-GPU truth on the whole graph
                 gr = graph.build_graph(sg.train_edges, U, I, sg.cred, variant, dev)
