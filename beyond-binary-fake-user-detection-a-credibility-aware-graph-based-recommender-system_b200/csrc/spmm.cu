@@ -562,6 +562,11 @@ static int spmm_dispatch(const cgx_csr* m, int use_bwd, int32_t d, const float* 
   switch (d) {
     case 16: return launch_spmm<4, 1, 4, HINT_NC, 4>(CGX_SPMM_ARGS);
     case 32: return launch_spmm<8, 1, 8, HINT_NC, 4>(CGX_SPMM_ARGS);
+  // The gather-loop / geometry variants measured in profiles/r1_spmm_variants.txt (CGX_SPMM_VARIANT=<id>) are only
+  // compiled with `make EXTRA=-DCGX_SPMM_TUNING` (profiles/tune_spmm.py): 40 extra instantiations of k_spmm.
+#ifndef CGX_SPMM_TUNING
+#define CGX_VARIANTS(GG) return launch_spmm<GG, 1, 8, HINT_NC, 4>(CGX_SPMM_ARGS);
+#else
 #define CGX_VARIANTS(GG)                                                                   \
       switch (variant) {                                                                   \
         case 1: return launch_spmm<GG, 1, 16, HINT_NC, 1>(CGX_SPMM_ARGS);                  \
@@ -587,6 +592,7 @@ static int spmm_dispatch(const cgx_csr* m, int use_bwd, int32_t d, const float* 
         case 21: return launch_spmm<GG / 2, 2, 4, HINT_NC, 3>(CGX_SPMM_ARGS);              \
         default: return launch_spmm<GG, 1, 8, HINT_NC, 4>(CGX_SPMM_ARGS);                  \
       }
+#endif
     case 64:
       if (variant == 0 && beyond_l2) return launch_spmm<8, 2, 4, HINT_NC, 4>(CGX_SPMM_ARGS);
       CGX_VARIANTS(16)
@@ -594,7 +600,9 @@ static int spmm_dispatch(const cgx_csr* m, int use_bwd, int32_t d, const float* 
       if (variant == 0 && beyond_l2) return launch_spmm<16, 2, 4, HINT_NC, 4>(CGX_SPMM_ARGS);
       CGX_VARIANTS(32)
     case 256:
+#ifdef CGX_SPMM_TUNING
       if (variant == 17) return launch_spmm<16, 4, 2, HINT_NC, 4>(CGX_SPMM_ARGS);
+#endif
       return launch_spmm<32, 2, 4, HINT_NC, 4>(CGX_SPMM_ARGS);
     default:
       set_error("spmm: emb_dim %d unsupported (16, 32, 64, 128, 256)", d);

@@ -1,4 +1,5 @@
 """Time one K=3 forward + backward propagation for the SpMM variant in $CGX_SPMM_VARIANT.
+    make -C <package>/csrc clean all EXTRA=-DCGX_SPMM_TUNING     (the variants are not in the default build)
     CGX_SPMM_VARIANT=n python profiles/tune_spmm.py <shape> <d>
 shape: C2 | mid (4M x 1M x 64M, device generated) | C4"""
 import json, os, pathlib, sys, time
