@@ -102,3 +102,19 @@ def test_sampled_candidates_match_reference_stream(golden):
     np.testing.assert_array_equal(np.sort(cands, 1)[:, :0].shape[0], g["sampled_ranked"].shape[0])
     for r in range(len(users)):
         assert set(g["sampled_ranked"][r].tolist()) <= set(cands[r].tolist())
+
+
+def test_plain_c_caller_links_and_runs(tmp_path):
+    """tests/c/abi_smoke.c is compiled with gcc against include/credgcn.h and linked to libcredgcn.so: the boundary
+    is a C ABI (no C++ / torch types), usable from any host language's FFI.  Host-side entry points only."""
+    import shutil
+    import subprocess
+    from credgcn import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = tmp_path / "abi_smoke"
+    lib_dir = _lib.LIB_PATH.parent
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", f"-I{ROOT / 'include'}", str(ROOT / "tests" / "c" / "abi_smoke.c"),
+                    "-o", str(exe), f"-L{lib_dir}", "-lcredgcn", f"-Wl,-rpath,{lib_dir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "0 failure(s)" in out.stdout, out.stdout + out.stderr
