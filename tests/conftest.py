@@ -18,6 +18,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")
 
 
+def pytest_sessionstart(session):
+    """libcredgcn.so is a git-ignored build product: a fresh checkout builds it once (nvcc cross-compiles sm_100a
+    without a GPU, ~20 s) so that the C-ABI tests do not depend on who ran __graft_entry__.build() before."""
+    import shutil
+    so = next(ROOT.glob("*_b200")) / "libcredgcn.so"
+    if not so.exists() and shutil.which("nvcc") is not None:
+        import __graft_entry__
+        __graft_entry__.build()
+
+
 def load_golden(case: str, tag: str):
     z = np.load(GOLDEN / f"{case}_{tag}.npz")
     return {k: z[k] for k in z.files}
