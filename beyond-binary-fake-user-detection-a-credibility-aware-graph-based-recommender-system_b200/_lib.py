@@ -3,6 +3,7 @@ non-CUDA tensor is an error, raised loudly."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 import pathlib
 import subprocess
 
@@ -15,6 +16,10 @@ CSRC_DIR = PKG_DIR / "csrc"
 VARIANTS = {"cu": 0, "v2": 1, "da": 2}
 ORDERS = {"jacobi": 0, "gs": 1}
 PRECISIONS = {"fp32": 0, "bf16x3": 1, "bf16": 2}
+# cgx_option (include/credgcn.h).  The library reads no environment variables; for experiments this binding maps
+# CGX_OPT_<NAME>=<int> onto cgx_set_option when the library is loaded.
+OPTIONS = {"L2_TABLE_BYTES": 0, "SPARSE_FIRST_ADJOINT": 1, "PDL": 2, "P2P_ONESHOT_MAX": 3, "P2P_TIMING": 4,
+           "P2P_TIMEOUT_MS": 5, "EVAL_DEBUG": 6, "HOT_ROWS": 7, "SPMM_RING": 8}
 LONG_ROW = 256
 CHUNK = 256
 
@@ -31,6 +36,7 @@ class CsrStruct(C.Structure):
         ("perm", C.c_void_p), ("n_long", C.c_int32), ("n_chunks", C.c_int32),
         ("chunk_ptr", C.c_void_p), ("chunk_row", C.c_void_p),
         ("n_huge", C.c_int32), ("reserved_", C.c_int32), ("arrive", C.c_void_p), ("work", C.c_void_p),
+        ("idx_hint", C.c_void_p),
     ]
 
 
@@ -41,6 +47,11 @@ _SIGNATURES = {
     "cgx_version": (C.c_int, []),
     "cgx_launch_count": (C.c_uint64, []),
     "cgx_emb_dim_supported": (C.c_int, [C.c_int32]),
+    "cgx_set_option": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_int64)]),
+    "cgx_get_option": (C.c_int64, [C.c_int]),
+    "cgx_hot_hints_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "cgx_hot_hints": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int32, _P, _P, C.c_size_t, _P]),
+    "cgx_comm_status": (C.c_int, [_P, C.c_size_t, C.c_int, C.POINTER(C.c_uint32)]),
     "cgx_graph_build_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
     "cgx_graph_build": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int, _P, _P, _P, _P, _P, _P,
                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P, C.c_size_t, _P]),
@@ -127,7 +138,22 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)        # AttributeError here = header/library drift: fail loudly
             fn.restype, fn.argtypes = res, args
         _lib = handle
+        for name, key in OPTIONS.items():
+            env = os.environ.get(f"CGX_OPT_{name}")
+            if env is not None:
+                handle.cgx_set_option(key, int(env), None)
     return _lib
+
+
+def set_option(name: str, value: int) -> int:
+    """cgx_set_option by name; returns the previous value (negative value = restore the default)."""
+    prev = C.c_int64(0)
+    check(lib().cgx_set_option(OPTIONS[name], int(value), C.byref(prev)))
+    return int(prev.value)
+
+
+def get_option(name: str) -> int:
+    return int(lib().cgx_get_option(OPTIONS[name]))
 
 
 def check(status: int) -> None:

@@ -12,6 +12,8 @@
 // the row once.  Entry order is fixed by the stable sort, so the result is bitwise reproducible.
 // The plan depends on the indices only, so callers may build it on a side stream while the
 // forward propagation runs.
+#include <atomic>
+
 #include "common.cuh"
 
 namespace cgx {
@@ -481,10 +483,15 @@ extern "C" int cgx_bpr_plan(const int64_t* users, const int64_t* pos, const int6
   const int entry_bits = bits_for(n), row_bits = bits_for(int64_t(U) + I);
   if (n <= PS_MAX) {
     const size_t smem = plan_small_smem();
-    static bool attr_set = false;   // once per process: keeps the call out of CUDA-graph captures after warm-up
-    if (!attr_set) {
+    // the shared-memory opt-in is a per-DEVICE attribute: set it once per device (a bit per ordinal), which also
+    // keeps the call out of CUDA-graph captures after warm-up
+    static std::atomic<unsigned long long> attr_set{0};
+    int dev = 0;
+    CGX_CUDA(cudaGetDevice(&dev));
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(attr_set.load(std::memory_order_acquire) & bit)) {
       CGX_CUDA(cudaFuncSetAttribute(k_plan_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
+      attr_set.fetch_or(bit, std::memory_order_release);
     }
     k_plan_small<<<1, PS_THREADS, smem, stream>>>(users, pos, neg, batch, U, I, entry_bits, row_bits, plan);
     CGX_LAUNCH_CHECK();

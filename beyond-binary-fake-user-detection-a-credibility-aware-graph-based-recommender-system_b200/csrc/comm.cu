@@ -20,7 +20,7 @@
 //     means nobody writes a rank's `out` region before that rank's earlier kernels (the consumers of the
 //     previous result) have finished: regions can be re-used immediately.  Two regions are kept only so that
 //     the result of the previous exchange stays readable (the Jacobi order needs it).
-//   * small worlds (<= CGX_P2P_ONESHOT_MAX ranks, default 2) use the ONE-SHOT form instead: after barrier A every
+//   * small worlds (<= CGX_OPT_P2P_ONESHOT_MAX ranks, default 2) use the ONE-SHOT form instead: after barrier A every
 //     rank pulls ALL partials and sums the whole table locally, in rank order (same bits on every rank), into its
 //     own out[parity]; no remote store, no barrier B.  It moves (R-1) x the table per rank instead of
 //     2 (R-1)/R x, but saves a system-scope fence, a barrier and an NVLink round trip -- at 10 MB and 2 ranks the
@@ -67,12 +67,35 @@ __device__ __forceinline__ unsigned long long p2p_now() {
   return t;
 }
 
-// flag page layout (uint32): [0 .. R) barrier A slots, [R .. 2R) barrier B slots, [2R] CTA arrival counter
+// Bounded wait for `*p >= epoch` (a flag another GPU writes).  A peer that died or lost step with this rank would
+// otherwise hang every GPU of the job inside a replayed CUDA graph: after timeout_ns the waiter records
+// (barrier << 8 | peer + 1) in the flag page's error word (first failure wins; read by cgx_comm_status) and goes
+// on -- the exchange's result is then unusable, but every kernel terminates and the host can report it.
+__device__ __forceinline__ void wait_flag(const uint32_t* p, uint32_t epoch, unsigned long long timeout_ns,
+                                          uint32_t* err, uint32_t code) {
+  unsigned long long t0 = 0;
+  unsigned spins = 0;
+  while (ld_acquire_sys(p) < epoch) {
+    __nanosleep(64);
+    if ((++spins & 255u) == 0) {                 // look at the clock every ~16 us of waiting
+      const unsigned long long now = p2p_now();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > timeout_ns) {
+        atomicCAS(err, 0u, code);
+        return;
+      }
+    }
+  }
+}
+
+// flag page layout (uint32): [0 .. R) barrier A slots, [R .. 2R) barrier B slots, [2R] CTA arrival counter,
+// [2R + 1] error word (0 = no barrier has timed out)
 __global__ void __launch_bounds__(P2P_THREADS) k_p2p_allreduce(P2PPeers peers, int rank, int world, size_t in_off,
                                                                size_t out_off, size_t flag_off, int64_t n4,
                                                                const unsigned long long* __restrict__ epoch_dev,
-                                                               int one_shot, unsigned long long* dbg) {
-  // dbg (CGX_P2P_TIMING=1): ns spent in [0] barrier A, [1] reduce + delivery, [2] barrier B; [3] launches; [4] scratch
+                                                               int one_shot, unsigned long long timeout_ns,
+                                                               unsigned long long* dbg) {
+  // dbg (CGX_OPT_P2P_TIMING): ns spent in [0] barrier A, [1] reduce + delivery, [2] barrier B; [3] launches; [4] scratch
   unsigned long long t0 = 0;
   if (dbg && blockIdx.x == 0 && threadIdx.x == 0) t0 = p2p_now();
   const uint32_t epoch = uint32_t(*epoch_dev);   // device-side counter: the launch is replayable in a CUDA graph
@@ -82,9 +105,8 @@ __global__ void __launch_bounds__(P2P_THREADS) k_p2p_allreduce(P2PPeers peers, i
     __threadfence_system();
     st_release_sys(reinterpret_cast<uint32_t*>(peers.base[threadIdx.x] + flag_off) + rank, epoch);
   }
-  if (threadIdx.x < world) {
-    while (ld_acquire_sys(my_flags + threadIdx.x) < epoch) __nanosleep(64);
-  }
+  if (threadIdx.x < world)
+    wait_flag(my_flags + threadIdx.x, epoch, timeout_ns, my_flags + 2 * world + 1, (1u << 8) | (threadIdx.x + 1));
   __syncthreads();
   if (dbg && blockIdx.x == 0 && threadIdx.x == 0) {
     const unsigned long long t1 = p2p_now();
@@ -152,7 +174,8 @@ __global__ void __launch_bounds__(P2P_THREADS) k_p2p_allreduce(P2PPeers peers, i
   if (threadIdx.x < world) {
     __threadfence_system();
     st_release_sys(reinterpret_cast<uint32_t*>(peers.base[threadIdx.x] + flag_off) + world + rank, epoch);
-    while (ld_acquire_sys(my_flags + world + threadIdx.x) < epoch) __nanosleep(64);
+    wait_flag(my_flags + world + threadIdx.x, epoch, timeout_ns, my_flags + 2 * world + 1,
+              (2u << 8) | (threadIdx.x + 1));
   }
   __syncthreads();
   if (dbg && threadIdx.x == 0) dbg[2] += p2p_now() - t2;
@@ -166,6 +189,7 @@ __global__ void __launch_bounds__(P2P_THREADS) k_p2p_reduce_pushed(P2PPeers peer
                                                                    size_t stage_off, size_t out_off, size_t flag_off,
                                                                    int64_t n_rows, int32_t row4, int32_t rows_per,
                                                                    const unsigned long long* __restrict__ epoch_dev,
+                                                                   unsigned long long timeout_ns,
                                                                    unsigned long long* dbg) {
   unsigned long long t0 = 0;
   if (dbg && blockIdx.x == 0 && threadIdx.x == 0) t0 = p2p_now();
@@ -176,9 +200,8 @@ __global__ void __launch_bounds__(P2P_THREADS) k_p2p_reduce_pushed(P2PPeers peer
     __threadfence_system();
     st_release_sys(reinterpret_cast<uint32_t*>(peers.base[threadIdx.x] + flag_off) + rank, epoch);
   }
-  if (threadIdx.x < world) {
-    while (ld_acquire_sys(my_flags + threadIdx.x) < epoch) __nanosleep(64);
-  }
+  if (threadIdx.x < world)
+    wait_flag(my_flags + threadIdx.x, epoch, timeout_ns, my_flags + 2 * world + 1, (1u << 8) | (threadIdx.x + 1));
   __syncthreads();
   if (dbg && blockIdx.x == 0 && threadIdx.x == 0) {
     const unsigned long long t1 = p2p_now();
@@ -216,7 +239,8 @@ __global__ void __launch_bounds__(P2P_THREADS) k_p2p_reduce_pushed(P2PPeers peer
   if (threadIdx.x < world) {
     __threadfence_system();
     st_release_sys(reinterpret_cast<uint32_t*>(peers.base[threadIdx.x] + flag_off) + world + rank, epoch);
-    while (ld_acquire_sys(my_flags + world + threadIdx.x) < epoch) __nanosleep(64);
+    wait_flag(my_flags + world + threadIdx.x, epoch, timeout_ns, my_flags + 2 * world + 1,
+              (2u << 8) | (threadIdx.x + 1));
   }
   __syncthreads();
   if (dbg && threadIdx.x == 0) dbg[2] += p2p_now() - t2;
@@ -261,7 +285,7 @@ extern "C" int cgx_comm_ipc_close(void* peer_base) {
 
 static unsigned long long* g_p2p_dbg = nullptr;
 
-/* CGX_P2P_TIMING=1 diagnostics: ns accumulated in {barrier A, reduce + delivery, barrier B} and the number of
+/* CGX_OPT_P2P_TIMING diagnostics: ns accumulated in {barrier A, reduce + delivery, barrier B} and the number of
  * exchanges since the last call (synchronises the device; zeros when timing is off). */
 extern "C" int cgx_comm_timing(uint64_t* out4) {
   CGX_REQUIRE(out4 != nullptr, CGX_ERR_ARG, "comm_timing: NULL pointer");
@@ -273,9 +297,11 @@ extern "C" int cgx_comm_timing(uint64_t* out4) {
   return CGX_OK;
 }
 
+static unsigned long long p2p_timeout_ns() { return (unsigned long long)option(CGX_OPT_P2P_TIMEOUT_MS) * 1000000ull; }
+
 static int p2p_dbg_buffer(unsigned long long** out) {
   static unsigned long long* dbg = nullptr;
-  if (dbg == nullptr && getenv("CGX_P2P_TIMING") != nullptr) {
+  if (dbg == nullptr && option(CGX_OPT_P2P_TIMING) != 0) {
     CGX_CUDA(cudaMalloc(&dbg, 64));
     CGX_CUDA(cudaMemset(dbg, 0, 64));
     g_p2p_dbg = dbg;
@@ -305,8 +331,17 @@ extern "C" int cgx_comm_allreduce_pushed(int rank, int world, void* const* peer_
   if (blocks < 1) blocks = 1;
   k_p2p_reduce_pushed<<<(unsigned)blocks, P2P_THREADS, 0, stream>>>(
       peers, rank, world, stage_off, out_off, flag_off, n_rows, d / 4, rows_per,
-      reinterpret_cast<const unsigned long long*>(epoch_dev), dbg);
+      reinterpret_cast<const unsigned long long*>(epoch_dev), p2p_timeout_ns(), dbg);
   CGX_LAUNCH_CHECK();
+  return CGX_OK;
+}
+
+extern "C" int cgx_comm_status(const void* base, size_t flag_off, int world, uint32_t* error_out) {
+  CGX_REQUIRE(base && error_out && world >= 1 && world <= P2P_MAX_RANKS && flag_off % 16 == 0, CGX_ERR_ARG,
+              "comm_status: bad argument");
+  CGX_CUDA(cudaDeviceSynchronize());
+  CGX_CUDA(cudaMemcpy(error_out, static_cast<const char*>(base) + flag_off + 4 * (2 * size_t(world) + 1), 4,
+                      cudaMemcpyDeviceToHost));
   return CGX_OK;
 }
 
@@ -324,8 +359,7 @@ extern "C" int cgx_comm_allreduce(int rank, int world, void* const* peer_bases, 
     peers.base[p] = static_cast<char*>(peer_bases[p]);
   }
   const int64_t n4 = n_floats / 4;
-  static const int one_shot_max = getenv("CGX_P2P_ONESHOT_MAX") ? atoi(getenv("CGX_P2P_ONESHOT_MAX")) : 2;
-  const int one_shot = world <= one_shot_max ? 1 : 0;
+  const int one_shot = world <= option(CGX_OPT_P2P_ONESHOT_MAX) ? 1 : 0;
   unsigned long long* dbg = nullptr;
   CGX_TRY(p2p_dbg_buffer(&dbg));
   const int64_t per = one_shot ? n4 : ceil_div(n4, world);
@@ -334,7 +368,7 @@ extern "C" int cgx_comm_allreduce(int rank, int world, void* const* peer_bases, 
   if (blocks < 1) blocks = 1;
   k_p2p_allreduce<<<(unsigned)blocks, P2P_THREADS, 0, stream>>>(peers, rank, world, in_off, out_off, flag_off, n4,
                                                              reinterpret_cast<const unsigned long long*>(epoch_dev),
-                                                             one_shot, dbg);
+                                                             one_shot, p2p_timeout_ns(), dbg);
   CGX_LAUNCH_CHECK();
   return CGX_OK;
 }

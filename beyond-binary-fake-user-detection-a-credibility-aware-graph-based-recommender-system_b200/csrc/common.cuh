@@ -9,6 +9,7 @@
 namespace cgx {
 
 void set_error(const char* fmt, ...);
+int64_t option(int which);   // current value of a cgx_option (cgx_set_option)
 
 #define CGX_CUDA(expr)                                                                   \
   do {                                                                                   \

@@ -611,14 +611,11 @@ struct TcConfig {
   int KC, BC, NG, stride;   // stride = candidates per user handed to k_rescore (32 or 64)
 };
 static TcConfig tc_config(int32_t K, int precision) {
-  // Two epilogue groups (24, 16, 2, 64) were measured SLOWER on C2 (3.69 ms vs 3.19 ms): each group keeps
-  // its own, weaker threshold, so more scores reach the merge code.  Set CGX_EVAL_GROUPS=2 to try it.
-  static const bool two = getenv("CGX_EVAL_GROUPS") != nullptr && atoi(getenv("CGX_EVAL_GROUPS")) == 2;
-  if (two && K + 4 <= 24) return {24, 16, 2, 64};
-  // K' = 24 (margin 4) is 4 % faster on C2 but on C3 (91 599 items, denser top scores) the completeness proof
-  // fails for enough rows that the fp32 redo doubles the time (10.9 ms vs 5.7 ms): opt-in, CGX_EVAL_KC=24
-  static const bool kc24 = getenv("CGX_EVAL_KC") != nullptr && atoi(getenv("CGX_EVAL_KC")) == 24;
-  if (kc24 && precision == CGX_SCORE_BF16X3 && K + 4 <= 24) return {24, 40, 1, 32};
+  // Measured and rejected in round 1 (no longer compiled): two epilogue groups (24, 16, 2, 64) -- SLOWER on C2
+  // (3.69 vs 3.19 ms): each group keeps its own, weaker threshold, so more scores reach the merge code; K' = 24
+  // (margin 4) -- 4 % faster on C2, but on C3 the completeness proof fails for enough rows that the exact redo
+  // doubles the time (10.9 vs 5.7 ms).
+  (void)precision;
   if (K + 12 <= 32) return {32, 32, 1, 32};
   return {64, 16, 1, 64};
 }
@@ -657,7 +654,7 @@ static int tc_launch(const __nv_bfloat16* Au, const __nv_bfloat16* Bi, const int
   CGX_CUDA(cudaFuncSetAttribute(k_eval_umma<KC, BC, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_eval_umma<KC, BC, NG><<<(unsigned)ceil_div(n_users, TC_M), 32 * (9 + 4 * NG), smem, stream>>>(
       Au, Bi, users, n_users, I, Kp, nkb, S, tr_indptr, tr_idx, cand, STRIDE, thr,
-      getenv("CGX_EVAL_DBG") ? atoi(getenv("CGX_EVAL_DBG")) : 0);
+      int(option(CGX_OPT_EVAL_DEBUG) >> 1));
   CGX_LAUNCH_CHECK();
   k_rescore<STRIDE><<<(unsigned)ceil_div(n_users, 8), 256, 0, stream>>>(users, n_users, f_u, f_i, d, tr_indptr, tr_idx,
                                                                        cand, thr, unorm, scal, eps_rel, K, out_ids,
@@ -700,11 +697,7 @@ int eval_topk_tc(const int64_t* users, int64_t n_users, const float* f_u, const 
   int32_t* n_redo = reinterpret_cast<int32_t*>(scal + 1);
 #define CGX_TC_ARGS Au, Bi, users, n_users, f_u, f_i, I, d, Kp, nkb, tr_indptr, tr_idx, K, cand, thr, unorm, scal, eps_rel, \
                     out_ids, out_scores, redo_rows, n_redo, stream
-  if (cfg.NG == 2) {
-    CGX_TRY((tc_launch<24, 16, 2, 64>(CGX_TC_ARGS)));
-  } else if (cfg.KC == 24) {
-    CGX_TRY((tc_launch<24, 40, 1, 32>(CGX_TC_ARGS)));
-  } else if (cfg.KC == 32) {
+  if (cfg.KC == 32) {
     CGX_TRY((tc_launch<32, 32, 1, 32>(CGX_TC_ARGS)));
   } else {
     CGX_TRY((tc_launch<64, 16, 1, 64>(CGX_TC_ARGS)));
@@ -717,7 +710,7 @@ int eval_topk_tc(const int64_t* users, int64_t n_users, const float* f_u, const 
     k_eval_redo_rows<<<(unsigned)er_grid, ER_THREADS, er_smem, stream>>>(users, redo, n_redo, f_u, f_i, I, d, tr_indptr,
                                                                         tr_idx, K, out_ids, out_scores);
     CGX_LAUNCH_CHECK();
-    if (getenv("CGX_DEBUG_EVAL") != nullptr) {   // diagnostics only: synchronises
+    if (option(CGX_OPT_EVAL_DEBUG) & 1) {   // diagnostics only: synchronises
       unsigned int h[2];
       CGX_CUDA(cudaMemcpyAsync(h, scal, 8, cudaMemcpyDeviceToHost, stream));
       CGX_CUDA(cudaStreamSynchronize(stream));

@@ -21,6 +21,25 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// Tuning options (cgx_set_option): the only process-wide mutable state of the library besides the launch tally.
+// The library reads no environment variables; the Python binding maps CGX_OPT_<NAME> onto these for experiments.
+static const int64_t k_option_defaults[CGX_OPT_COUNT_] = {
+    int64_t(96) << 20,  // CGX_OPT_L2_TABLE_BYTES
+    1,                  // CGX_OPT_SPARSE_FIRST_ADJOINT
+    1,                  // CGX_OPT_PDL
+    2,                  // CGX_OPT_P2P_ONESHOT_MAX
+    0,                  // CGX_OPT_P2P_TIMING
+    20000,              // CGX_OPT_P2P_TIMEOUT_MS
+    0,                  // CGX_OPT_EVAL_DEBUG
+    1,                  // CGX_OPT_HOT_ROWS
+    1,                  // CGX_OPT_SPMM_RING
+};
+static std::atomic<int64_t> g_options[CGX_OPT_COUNT_] = {
+    {k_option_defaults[0]}, {k_option_defaults[1]}, {k_option_defaults[2]}, {k_option_defaults[3]},
+    {k_option_defaults[4]}, {k_option_defaults[5]}, {k_option_defaults[6]}, {k_option_defaults[7]},
+    {k_option_defaults[8]}};
+int64_t option(int which) { return g_options[which].load(std::memory_order_relaxed); }
+
 // --------------------------------------------------------------------------------------------
 // scan
 // --------------------------------------------------------------------------------------------
@@ -238,7 +257,17 @@ int radix_sort_u64(uint64_t* keys, uint64_t* alt, int64_t n, int bits, void* tem
 }  // namespace cgx
 
 extern "C" const char* cgx_last_error(void) { return cgx::g_err; }
-extern "C" int cgx_version(void) { return 100; }
+extern "C" int cgx_version(void) { return 200; }
+extern "C" int cgx_set_option(int which, int64_t value, int64_t* previous) {
+  CGX_REQUIRE(which >= 0 && which < CGX_OPT_COUNT_, CGX_ERR_ARG, "set_option: unknown option %d", which);
+  if (value < 0) value = cgx::k_option_defaults[which];   // negative = restore the default
+  const int64_t old = cgx::g_options[which].exchange(value, std::memory_order_relaxed);
+  if (previous) *previous = old;
+  return CGX_OK;
+}
+extern "C" int64_t cgx_get_option(int which) {
+  return which >= 0 && which < CGX_OPT_COUNT_ ? cgx::option(which) : -1;
+}
 extern "C" uint64_t cgx_launch_count(void) { return cgx::g_launches.load(std::memory_order_relaxed); }
 extern "C" int cgx_emb_dim_supported(int32_t d) {
   return d == 16 || d == 32 || d == 64 || d == 128 || d == 256;

@@ -21,7 +21,7 @@
 // Tuning (profiles/r1_spmm_variants.txt): 8 gathers in flight per lane with the register budget
 // capped for 4 CTAs/SM is within 3 % of the best variant on both the L2-resident C2 shape and the
 // HBM-bound 64M-edge shape; higher unrolls lose occupancy (d=128: 86 registers -> 2 CTAs/SM).
-#include <stdlib.h>
+#include <atomic>
 
 #include "common.cuh"
 
@@ -29,23 +29,6 @@ namespace cgx {
 
 constexpr int SP_THREADS = 256;
 
-// Tuning knobs of the gather loop (selected per width in spmm_dispatch; CGX_SPMM_VARIANT overrides
-// them for experiments): UNR = embedding-row gathers in flight per lane, HINT = cache policy of
-// those gathers, MINB = CTAs per SM the register allocation must allow.
-enum { HINT_NC = 0, HINT_CG = 1, HINT_NC_NOALLOC = 2 };
-
-template <int HINT>
-__device__ __forceinline__ float4 ld_row(const float4* p) {
-  if (HINT == HINT_CG) return __ldcg(p);
-  if (HINT == HINT_NC_NOALLOC) {
-    float4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-                 : "l"(p));
-    return r;
-  }
-  return __ldg(p);
-}
 __device__ __forceinline__ void fma4(float4& a, float v, const float4& x) {
   a.x = fmaf(v, x.x, a.x);
   a.y = fmaf(v, x.y, a.y);
@@ -59,6 +42,69 @@ __device__ __forceinline__ float4 scale4(const float4& a, float s) {
   return make_float4(a.x * s, a.y * s, a.z * s, a.w * s);
 }
 
+// 256-bit global accesses with an L2 eviction priority (sm_100: LDG.E.{EF,EL,EN}L2.256 / STG.E.*.256).  The priority
+// is how "hot (high-degree) rows are staged" when the gathered table is larger than the 126 MB L2: rows named hot by
+// cgx_hot_hints are loaded evict_last and stay resident, everything else -- cold rows, the streamed column ids /
+// values, the epilogue's running sums and outputs -- goes through evict_first and does not displace them.
+enum { POL_NORMAL = 0, POL_FIRST = 1, POL_LAST = 2 };
+template <int POL>
+__device__ __forceinline__ void ld256(const float4* p, float4& a, float4& b) {
+  if (POL == POL_LAST) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+  } else if (POL == POL_FIRST) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+  } else {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+  }
+}
+// plain (coherent) 256-bit load: ACC_IN may alias ACC_OUT, which this kernel writes -- never through the .nc path
+template <int POL>
+__device__ __forceinline__ void ld256_rw(const float4* p, float4& a, float4& b) {
+  if (POL == POL_FIRST) {
+    asm volatile("ld.global.L1::no_allocate.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p)
+                 : "memory");
+  } else {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p)
+                 : "memory");
+  }
+}
+template <int POL>
+__device__ __forceinline__ void st256(float4* p, const float4& a, const float4& b) {
+  if (POL == POL_FIRST) {
+    asm volatile("st.global.L2::evict_first.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y),
+                 "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
+                 : "memory");
+  } else {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w),
+                 "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
+                 : "memory");
+  }
+}
+template <bool STREAM>
+__device__ __forceinline__ int32_t ld_idx(const int32_t* p) {
+  if (!STREAM) return __ldg(p);
+  int32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));   // (L2 priorities need 256-bit accesses)
+  return v;
+}
+template <bool STREAM>
+__device__ __forceinline__ float ld_val(const float* p) {
+  if (!STREAM) return __ldg(p);
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
 template <int G>
 __device__ __forceinline__ unsigned group_mask() {
   if (G == 32) return 0xffffffffu;
@@ -66,28 +112,49 @@ __device__ __forceinline__ unsigned group_mask() {
   return ((1u << (G & 31)) - 1u) << (lane & ~(G - 1));
 }
 
+// Lane `lane` of a group owns float4 slots lane*V .. lane*V+V-1 of a row (V = 2: 32 contiguous bytes, one 256-bit
+// access; V = 1: 16 bytes).  x[v] = X[row c][lane*V + v].
+template <int G, int V, bool HOT>
+__device__ __forceinline__ void ld_row(const float4* __restrict__ X, int32_t c, int lane, float4 (&x)[V]) {
+  constexpr int ROW4 = G * V;
+  if constexpr (V == 2) {
+    if constexpr (HOT) {   // bit 31 of a hinted column id = "hot row"
+      const float4* p = X + int64_t(c & 0x7fffffff) * ROW4 + 2 * lane;
+      if (c < 0) ld256<POL_LAST>(p, x[0], x[1]);
+      else ld256<POL_FIRST>(p, x[0], x[1]);
+    } else {
+      ld256<POL_NORMAL>(X + int64_t(c) * ROW4 + 2 * lane, x[0], x[1]);
+    }
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; ++v) x[v] = __ldg(X + int64_t(c) * ROW4 + lane * V + v);
+  }
+}
+
 // acc[v] (v < V) += sum over nnz in [begin, end) of val * X[idx, :]; one group, lane = 0..G-1.
 // NZ: `nz[c] == 0` marks row c of X as all-zero (the loss gradient touches <= 3 * batch rows): its weight is
 // forced to 0 and rows of weight 0 are not loaded -- same sum, a fraction of the gather traffic.
-template <int G, int V, int UNR, int HINT, bool NZ = false>
+// HOT: idx carries the hot-row hint in bit 31 (cgx_hot_hints) and the streams use evict_first.
+template <int G, int V, int UNR, bool NZ, bool HOT>
 __device__ __forceinline__ void gather_batches(const int32_t* __restrict__ idx, const float* __restrict__ val,
-                                               int64_t begin, int64_t end, const float4* __restrict__ X, int lane,
+                                               int32_t len, const float4* __restrict__ X, int lane,
                                                unsigned mask, int32_t c_nxt, float w_nxt, float4 (&acc)[V],
-                                               const uint8_t* __restrict__ nz = nullptr) {
+                                               const uint8_t* __restrict__ nz) {
+  // idx / val point at the work item's first non-zero; len <= CGX_CHUNK, so 32-bit offsets do.
   // (c_nxt, w_nxt) = this lane's column id / value of the first batch, already loaded by the caller
-  constexpr int ROW4 = G * V;  // float4 per embedding row
-  for (int64_t base = begin; base < end; base += G) {
+  idx += G + lane;   // this lane's slot of the NEXT batch
+  val += G + lane;
+  for (int32_t rem = len; rem > 0; rem -= G, idx += G, val += G) {
     const int32_t c = c_nxt;
     float w = w_nxt;
     if (NZ) {
       if (w != 0.f && __ldg(nz + c) == 0) w = 0.f;
     }
-    const int64_t pn = base + G + lane;  // prefetch the next batch of column ids / values
-    if (pn < end) {
-      c_nxt = __ldg(idx + pn);
-      w_nxt = __ldg(val + pn);
+    if (G + lane < rem) {                // prefetch the next batch of column ids / values
+      c_nxt = ld_idx<HOT>(idx);
+      w_nxt = ld_val<HOT>(val);
     }
-    const int cnt = (end - base) < G ? int(end - base) : G;
+    const int cnt = rem < G ? rem : G;
     for (int j0 = 0; j0 < cnt; j0 += UNR) {
       float4 x[UNR][V];
       float ww[UNR];
@@ -98,8 +165,7 @@ __device__ __forceinline__ void gather_batches(const int32_t* __restrict__ idx, 
         const int32_t cj = __shfl_sync(mask, c, src, G);
         ww[t] = __shfl_sync(mask, w, src, G);
         if (j < cnt && (!NZ || ww[t] != 0.f)) {
-#pragma unroll
-          for (int v = 0; v < V; ++v) x[t][v] = ld_row<HINT>(X + int64_t(cj) * ROW4 + v * G + lane);
+          ld_row<G, V, HOT>(X, cj, lane, x[t]);
         } else {
           ww[t] = 0.f;
 #pragma unroll
@@ -115,19 +181,6 @@ __device__ __forceinline__ void gather_batches(const int32_t* __restrict__ idx, 
   }
 }
 
-template <int G, int V, int UNR, int HINT>
-__device__ __forceinline__ void gather_range(const int32_t* __restrict__ idx, const float* __restrict__ val,
-                                             int64_t begin, int64_t end, const float4* __restrict__ X, int lane,
-                                             unsigned mask, float4 (&acc)[V]) {
-  int32_t c = 0;
-  float w = 0.f;
-  if (begin + lane < end) {
-    c = __ldg(idx + begin + lane);
-    w = __ldg(val + begin + lane);
-  }
-  gather_batches<G, V, UNR, HINT>(idx, val, begin, end, X, lane, mask, c, w, acc);
-}
-
 // Push mode of the user-sharded propagation (cgx_spmm_push): output row r is not stored to Y but straight into the
 // staging area of the rank that OWNS row r (rows_per consecutive rows per rank), slot `rank` -- a posted store over
 // NVLink, issued row by row while the rest of the product is still being gathered.  The exchange kernel
@@ -139,25 +192,46 @@ struct SpmmPush {
   int32_t rank;
 };
 
-template <int G, int V>
+// acc_nz (nullable): acc_nz[row] == 0 promises that ACC_IN[row] is all zero, and it is then not read (the adjoint's
+// ACC_IN is the loss gradient: <= 3 * batch non-zero rows of millions).
+template <int G, int V, bool STREAM>
 __device__ __forceinline__ void epilogue(int64_t row, int lane, const float4 (&y)[V], float4* __restrict__ Y,
                                          const float4* ACC_IN, float4* ACC_OUT, float acc_scale,
-                                         const SpmmPush ps = SpmmPush{0ull, 0, 0}) {
+                                         const uint8_t* __restrict__ acc_nz, const SpmmPush ps) {
   constexpr int ROW4 = G * V;
-  float4* ypush = nullptr;
+  constexpr int POL = STREAM ? POL_FIRST : POL_NORMAL;
+  const int64_t o = row * ROW4 + lane * V;
+  float4 a[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) a[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ACC_OUT != nullptr && ACC_IN != nullptr && (acc_nz == nullptr || __ldg(acc_nz + row) != 0)) {
+    if constexpr (V == 2) ld256_rw<POL>(ACC_IN + o, a[0], a[1]);
+    else {
+#pragma unroll
+      for (int v = 0; v < V; ++v) a[v] = ACC_IN[o + v];
+    }
+  }
   if (ps.rows_per > 0) {
     const int owner = int(row / ps.rows_per);
-    ypush = reinterpret_cast<float4*>(c_push_base[owner] + ps.off) +
-            (int64_t(ps.rank) * ps.rows_per + (row - int64_t(owner) * ps.rows_per)) * ROW4;
-  }
+    float4* ypush = reinterpret_cast<float4*>(c_push_base[owner] + ps.off) +
+                    (int64_t(ps.rank) * ps.rows_per + (row - int64_t(owner) * ps.rows_per)) * ROW4 + lane * V;
 #pragma unroll
-  for (int v = 0; v < V; ++v) {
-    const int64_t o = row * ROW4 + v * G + lane;
-    if (ypush) ypush[v * G + lane] = y[v];
-    if (Y) Y[o] = y[v];
-    if (ACC_OUT) {
-      float4 a = ACC_IN ? ACC_IN[o] : make_float4(0.f, 0.f, 0.f, 0.f);
-      ACC_OUT[o] = scale4(add4(a, y[v]), acc_scale);
+    for (int v = 0; v < V; ++v) ypush[v] = y[v];
+  }
+  if (Y != nullptr) {
+    if constexpr (V == 2) st256<POL>(Y + o, y[0], y[1]);
+    else {
+#pragma unroll
+      for (int v = 0; v < V; ++v) Y[o + v] = y[v];
+    }
+  }
+  if (ACC_OUT != nullptr) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) a[v] = scale4(add4(a[v], y[v]), acc_scale);
+    if constexpr (V == 2) st256<POL>(ACC_OUT + o, a[0], a[1]);
+    else {
+#pragma unroll
+      for (int v = 0; v < V; ++v) ACC_OUT[o + v] = a[v];
     }
   }
 }
@@ -165,214 +239,250 @@ __device__ __forceinline__ void epilogue(int64_t row, int lane, const float4 (&y
 struct SpmmSched {
   const int32_t* perm;
   const int32_t* chunk_ptr;
-  const int32_t* chunk_row;
   int32_t* arrive;
-  int32_t n_long, n_chunks, n_huge;
+  int32_t n_chunks, n_huge;
 };
 
-// One group per work item: chunk items first, then rows in descending degree.  A chunk stores its
-// partial sum; for rows up to CGX_HUGE_ROW the chunk that arrives last (per-row counter, release /
-// acquire through __threadfence) adds the partials IN CHUNK ORDER and runs the epilogue, so the
-// result does not depend on which chunk happened to be last.
-template <int G, int V, int UNR, int HINT, int MINB, bool NZ = false, bool PUSH = false>
-__global__ void __launch_bounds__(SP_THREADS, MINB) k_spmm(const int64_t* __restrict__ indptr,
-                                                           const int32_t* __restrict__ idx,
-                                                           const float* __restrict__ val, int32_t n_rows,
+// One group per work item of the flattened schedule (cgx_row_schedule_work): ONE 16-byte descriptor
+// {begin, length, row | long-row index} per item -- chunk items first, then rows in descending degree.  A chunk
+// stores its partial sum; for rows up to CGX_HUGE_ROW the chunk that arrives last (per-row counter, release /
+// acquire through __threadfence) adds the partials IN CHUNK ORDER and runs the epilogue, so the result does not
+// depend on which chunk happened to be last.
+template <int G, int V, int UNR, int MINB, bool NZ, bool PUSH, bool HOT>
+__global__ void __launch_bounds__(SP_THREADS, MINB) k_spmm(const int32_t* __restrict__ idx,
+                                                           const float* __restrict__ val, int64_t n_items,
                                                            SpmmSched sc, const float4* __restrict__ X,
                                                            float4* __restrict__ Y, const float4* ACC_IN,
                                                            float4* ACC_OUT, float acc_scale, float4* partial,
                                                            const uint8_t* __restrict__ nz,
+                                                           const uint8_t* __restrict__ acc_nz,
                                                            const int4* __restrict__ work, const SpmmPush ps_in) {
   // PUSH = false: a compile-time "off", so that the ordinary instantiations carry no trace of the push path
   const SpmmPush ps = PUSH ? ps_in : SpmmPush{0ull, 0, 0};
   constexpr int ROW4 = G * V;
   // Programmatic dependent launch: let the next kernel of the stream start its own prologue now, and run
-  // THIS kernel's prologue (schedule lookups, first batch of column ids / values -- graph constants) while the
+  // THIS kernel's prologue (descriptor, first batch of column ids / values -- graph constants) while the
   // previous kernel is still draining.  Nothing the previous kernel wrote is read, and nothing is written,
   // before griddepcontrol.wait returns.
   asm volatile("griddepcontrol.launch_dependents;");
   const int lane = threadIdx.x & (G - 1);
-  const int64_t item = (int64_t(blockIdx.x) * SP_THREADS + threadIdx.x) / G;
+  const uint32_t item = (blockIdx.x * uint32_t(SP_THREADS) + threadIdx.x) / G;   // < 2^32 / G items
   const unsigned mask = group_mask<G>();
   float4 acc[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (work != nullptr) {
-    // Flattened schedule (cgx_row_schedule_work): ONE 16-byte descriptor {begin, length, row | long-row index}
-    // replaces the perm -> indptr chain (two dependent loads) in front of every row's first gather.
-    const int64_t n_items = int64_t(sc.n_chunks) + (n_rows - sc.n_long);
-    if (item >= n_items) return;
-    const int4 wd = __ldg(work + item);
-    const int64_t begin = (int64_t(wd.y) << 32) | uint32_t(wd.x);
-    const int64_t end = begin + wd.z;
-    int32_t cf = 0;
-    float wf = 0.f;
-    if (lane < wd.z) {
-      cf = __ldg(idx + begin + lane);
-      wf = __ldg(val + begin + lane);
-    }
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    gather_batches<G, V, UNR, HINT, NZ>(idx, val, begin, end, X, lane, mask, cf, wf, acc, nz);
-    if (item >= sc.n_chunks) {
-      // (loading ACC_IN[row] before the gathers, to take it off the dependency chain, was measured SLOWER: the
-      // four extra live registers spill at the 64-register cap -- C2 0.514 -> 0.553 ms, C4 155 -> 160 ms)
-      epilogue<G, V>(wd.w, lane, acc, Y, ACC_IN, ACC_OUT, acc_scale, ps);
-      return;
-    }
-    const int32_t k = wd.w;
-#pragma unroll
-    for (int v = 0; v < V; ++v) __stcg(partial + item * ROW4 + v * G + lane, acc[v]);
-    if (k < sc.n_huge) return;            // combined by k_spmm_finish
-    const int32_t c0 = __ldg(sc.chunk_ptr + k), c1 = __ldg(sc.chunk_ptr + k + 1);
-    __threadfence();                       // release: this group's partial is visible device-wide
-    __syncwarp(mask);
-    int prev = 0;
-    if (lane == 0) prev = atomicAdd(sc.arrive + k, 1);
-    prev = __shfl_sync(mask, prev, 0, G);
-    if (prev != c1 - c0 - 1) return;
-    __threadfence();                       // acquire: every other chunk's partial is visible
-#pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c = c0; c < c1; ++c) {
-#pragma unroll
-      for (int v = 0; v < V; ++v) acc[v] = add4(acc[v], __ldcg(partial + int64_t(c) * ROW4 + v * G + lane));
-    }
-    epilogue<G, V>(int64_t(__ldg(sc.perm + k)), lane, acc, Y, ACC_IN, ACC_OUT, acc_scale, ps);
-    if (lane == 0) sc.arrive[k] = 0;       // self-resetting for the next launch
-    return;
-  }
-  if (item < sc.n_chunks) {
-    const int32_t k = __ldg(sc.chunk_row + item);
-    const int32_t row = __ldg(sc.perm + k);
-    const int32_t c0 = __ldg(sc.chunk_ptr + k);
-    const int64_t rbeg = __ldg(indptr + row), rend = __ldg(indptr + row + 1);
-    const int64_t begin = rbeg + int64_t(int32_t(item) - c0) * CGX_CHUNK;
-    const int64_t end = begin + CGX_CHUNK < rend ? begin + CGX_CHUNK : rend;
-    int32_t cf = 0;
-    float wf = 0.f;
-    if (begin + lane < end) {
-      cf = __ldg(idx + begin + lane);
-      wf = __ldg(val + begin + lane);
-    }
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    gather_batches<G, V, UNR, HINT, NZ>(idx, val, begin, end, X, lane, mask, cf, wf, acc, nz);
-#pragma unroll
-    for (int v = 0; v < V; ++v) __stcg(partial + item * ROW4 + v * G + lane, acc[v]);
-    if (k < sc.n_huge) return;            // combined by k_spmm_finish
-    const int32_t c1 = __ldg(sc.chunk_ptr + k + 1);
-    __threadfence();                       // release: this group's partial is visible device-wide
-    __syncwarp(mask);
-    int prev = 0;
-    if (lane == 0) prev = atomicAdd(sc.arrive + k, 1);
-    prev = __shfl_sync(mask, prev, 0, G);
-    if (prev != c1 - c0 - 1) return;
-    __threadfence();                       // acquire: every other chunk's partial is visible
-#pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c = c0; c < c1; ++c) {
-#pragma unroll
-      for (int v = 0; v < V; ++v) acc[v] = add4(acc[v], __ldcg(partial + int64_t(c) * ROW4 + v * G + lane));
-    }
-    epilogue<G, V>(row, lane, acc, Y, ACC_IN, ACC_OUT, acc_scale, ps);
-    if (lane == 0) sc.arrive[k] = 0;       // self-resetting for the next launch
-    return;
-  }
-  const int64_t r = item - sc.n_chunks + sc.n_long;
-  if (r >= n_rows) return;
-  const int32_t row = __ldg(sc.perm + r);
-  const int64_t begin = __ldg(indptr + row), end = __ldg(indptr + row + 1);
+  if (item >= n_items) return;
+  const int4 wd = __ldg(work + item);
+  const int64_t begin = (int64_t(wd.y) << 32) | uint32_t(wd.x);
+  idx += begin;
+  val += begin;
   int32_t cf = 0;
   float wf = 0.f;
-  if (begin + lane < end) {
-    cf = __ldg(idx + begin + lane);
-    wf = __ldg(val + begin + lane);
+  if (lane < wd.z) {
+    cf = ld_idx<HOT>(idx + lane);
+    wf = ld_val<HOT>(val + lane);
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  gather_batches<G, V, UNR, HINT, NZ>(idx, val, begin, end, X, lane, mask, cf, wf, acc, nz);
-  epilogue<G, V>(row, lane, acc, Y, ACC_IN, ACC_OUT, acc_scale, ps);
+  gather_batches<G, V, UNR, NZ, HOT>(idx, val, wd.z, X, lane, mask, cf, wf, acc, nz);
+  if (item >= sc.n_chunks) {
+    // (loading ACC_IN[row] before the gathers, to take it off the dependency chain, was measured SLOWER: the
+    // four extra live registers spill at the 64-register cap -- C2 0.514 -> 0.553 ms, C4 155 -> 160 ms)
+    epilogue<G, V, HOT>(wd.w, lane, acc, Y, ACC_IN, ACC_OUT, acc_scale, acc_nz, ps);
+    return;
+  }
+  const int32_t k = wd.w;
+#pragma unroll
+  for (int v = 0; v < V; ++v) __stcg(partial + int64_t(item) * ROW4 + lane * V + v, acc[v]);
+  if (k < sc.n_huge) return;            // combined by k_spmm_finish
+  const int32_t c0 = __ldg(sc.chunk_ptr + k), c1 = __ldg(sc.chunk_ptr + k + 1);
+  __threadfence();                       // release: this group's partial is visible device-wide
+  __syncwarp(mask);
+  int prev = 0;
+  if (lane == 0) prev = atomicAdd(sc.arrive + k, 1);
+  prev = __shfl_sync(mask, prev, 0, G);
+  if (prev != c1 - c0 - 1) return;
+  __threadfence();                       // acquire: every other chunk's partial is visible
+#pragma unroll
+  for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = c0; c < c1; ++c) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = add4(acc[v], __ldcg(partial + int64_t(c) * ROW4 + lane * V + v));
+  }
+  epilogue<G, V, HOT>(int64_t(__ldg(sc.perm + k)), lane, acc, Y, ACC_IN, ACC_OUT, acc_scale, acc_nz, ps);
+  if (lane == 0) sc.arrive[k] = 0;       // self-resetting for the next launch
 }
 
-// Persistent, software-pipelined form of k_spmm: a fixed grid of groups walks the flattened work list
-// (cgx_row_schedule_work) round-robin -- group g takes items g, g + n_groups, ... so every round hands
-// neighbouring groups items of equal weight, heaviest rounds first -- and while an item's rows are
-// being gathered the NEXT item's 16-byte descriptor and its first batch of column ids / values are
-// already in flight.  That removes the per-row pointer chase (perm -> indptr -> idx -> rows) from the
-// critical path, which is what bounds rows of 10-40 non-zeros.
-template <int G, int V, int UNR, int HINT, int MINB>
-__global__ void __launch_bounds__(SP_THREADS, MINB) k_spmm_p(const int4* __restrict__ work, int64_t n_items,
-                                                             const int32_t* __restrict__ idx,
-                                                             const float* __restrict__ val, SpmmSched sc,
-                                                             const float4* __restrict__ X, float4* __restrict__ Y,
-                                                             const float4* ACC_IN, float4* ACC_OUT, float acc_scale,
-                                                             float4* partial) {
+// ---- ring form of k_spmm: gathered rows staged through shared memory by cp.async -------------------------------
+// The register form above keeps UNR rows in flight per group and drains them before it issues the next UNR: a row of
+// 16 non-zeros is a chain of ~7 dependent memory latencies (descriptor, ids, 4 x gathers, ACC_IN) of which only the
+// gathers carry payload, and 64 registers per thread cap the SM at 64 groups.  When the gathered table lives in HBM
+// that chain, not the DRAM pipe, sets the pace of the short-row (user-row) products (ncu: 68 % of DRAM peak, long
+// scoreboard stalls, 45 % of the warp slots filled).  Here a lane moves its 32 bytes of every gathered row with two
+// 16-byte cp.async (LDGSTS: global -> shared memory without passing through registers) into a ring of R row slots
+// per group and reads them back itself -- shared memory is a per-lane staging area, so no barrier is needed, only
+// cp.async.wait_group.  The ring never drains inside a work item: row q + R is issued the moment row q has been
+// consumed, ACC_IN of the epilogue is fetched into a slot of its own before the first gather, and without the
+// x[UNR][V] registers the kernel fits 48 registers: 5 CTAs = 80 groups per SM, each with R = 4 rows in flight.
+// cp.async takes the L2 eviction priority of the hot-row hints as a cache-policy operand.
+// Same sums in the same order as the register form: bit-identical results.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint64_t policy) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int G, int V, int R, int MINB, bool PUSH, bool HOT>
+__global__ void __launch_bounds__(SP_THREADS, MINB) k_spmm_ring(const int32_t* __restrict__ idx,
+                                                                const float* __restrict__ val, int64_t n_items,
+                                                                SpmmSched sc, const float4* __restrict__ X,
+                                                                float4* __restrict__ Y, const float4* ACC_IN,
+                                                                float4* ACC_OUT, float acc_scale, float4* partial,
+                                                                const uint8_t* __restrict__ acc_nz,
+                                                                const int4* __restrict__ work, const SpmmPush ps_in) {
+  static_assert(V == 2 && R <= G && (R & (R - 1)) == 0, "ring form: 32 bytes per lane, power-of-two ring within a batch");
+  extern __shared__ __align__(16) float4 sp_ring[];   // [groups per CTA][R + 1][ROW4]; slot R holds ACC_IN
+  const SpmmPush ps = PUSH ? ps_in : SpmmPush{0ull, 0, 0};
   constexpr int ROW4 = G * V;
+  asm volatile("griddepcontrol.launch_dependents;");
   const int lane = threadIdx.x & (G - 1);
+  const uint32_t item = (blockIdx.x * uint32_t(SP_THREADS) + threadIdx.x) / G;   // < 2^32 / G items
   const unsigned mask = group_mask<G>();
-  const int64_t n_groups = int64_t(gridDim.x) * (SP_THREADS / G);
-  int64_t item = (int64_t(blockIdx.x) * SP_THREADS + threadIdx.x) / G;
   if (item >= n_items) return;
-  int4 cur = __ldg(work + item);
-  int64_t begin = (int64_t(cur.y) << 32) | uint32_t(cur.x);
-  int32_t c0v = 0;
-  float w0v = 0.f;
-  if (lane < cur.z) {
-    c0v = __ldg(idx + begin + lane);
-    w0v = __ldg(val + begin + lane);
+  float4* const slots = sp_ring + (threadIdx.x / G) * ((R + 1) * ROW4) + lane * V;   // this lane's 32 bytes of slot 0
+  const uint32_t slots_s = uint32_t(__cvta_generic_to_shared(slots));
+  uint64_t pol_cold, pol_hot;
+  if constexpr (HOT) {
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_cold));
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_hot));
+  } else {
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_cold));
+    pol_hot = pol_cold;
   }
-  while (true) {
-    const int64_t nitem = item + n_groups;
-    const bool more = nitem < n_items;
-    int4 nxt = make_int4(0, 0, 0, 0);
-    if (more) nxt = __ldg(work + nitem);                 // descriptor of the next item: in flight during the gather
-    float4 acc[V];
+  const int4 wd = __ldg(work + item);
+  const int32_t len = wd.z;
+  {
+    const int64_t begin = (int64_t(wd.y) << 32) | uint32_t(wd.x);
+    idx += begin + lane;
+    val += begin + lane;
+  }
+  // column ids / values of the current batch (c, w) and of the next one (c_nxt, w_nxt), one per lane
+  int32_t c = 0, c_nxt = 0;
+  float w = 0.f, w_nxt = 0.f;
+  if (lane < len) {
+    c = ld_idx<HOT>(idx);
+    w = ld_val<HOT>(val);
+  }
+  if (G + lane < len) {
+    c_nxt = ld_idx<HOT>(idx + G);
+    w_nxt = ld_val<HOT>(val + G);
+  }
+  idx += 2 * G;
+  val += 2 * G;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // epilogue operand first: by the time the gathers are done it has long arrived
+  const bool plain = item >= uint32_t(sc.n_chunks);
+  const bool have_acc = plain && ACC_OUT != nullptr && ACC_IN != nullptr && (acc_nz == nullptr || __ldg(acc_nz + wd.w) != 0);
+  if (have_acc) {
+    const float4* a = ACC_IN + int64_t(wd.w) * ROW4 + lane * V;
+    cp_async16(slots_s + R * ROW4 * 16, a, pol_cold);
+    cp_async16(slots_s + R * ROW4 * 16 + 16, a + 1, pol_cold);
+  }
+  cp_async_commit();
+  auto issue = [&](int32_t cj, int slot) {   // this lane's 32 bytes of row cj -> ring slot
+    const float4* p = X + int64_t(HOT ? (cj & 0x7fffffff) : cj) * ROW4 + lane * V;
+    const uint64_t pol = (HOT && cj < 0) ? pol_hot : pol_cold;
+    cp_async16(slots_s + slot * (ROW4 * 16), p, pol);
+    cp_async16(slots_s + slot * (ROW4 * 16) + 16, p + 1, pol);
+  };
 #pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    gather_batches<G, V, UNR, HINT>(idx, val, begin, begin + cur.z, X, lane, mask, c0v, w0v, acc);
-    const int64_t nbegin = (int64_t(nxt.y) << 32) | uint32_t(nxt.x);
-    c0v = 0;
-    w0v = 0.f;
-    if (more && lane < nxt.z) {                          // first batch of the next item: in flight during the epilogue
-      c0v = __ldg(idx + nbegin + lane);
-      w0v = __ldg(val + nbegin + lane);
-    }
-    if (item < sc.n_chunks) {
-      const int32_t k = cur.w;
+  for (int t = 0; t < R; ++t) {   // fill the ring: rows 0 .. R-1 (all inside the first batch, R <= G)
+    const int32_t cj = __shfl_sync(mask, c, t, G);
+    if (t < len) issue(cj, t);
+    cp_async_commit();
+  }
+  float4 acc[V];
 #pragma unroll
-      for (int v = 0; v < V; ++v) __stcg(partial + item * ROW4 + v * G + lane, acc[v]);
-      if (k >= sc.n_huge) {                              // rows above CGX_HUGE_ROW are combined by k_spmm_finish
-        const int32_t ch0 = __ldg(sc.chunk_ptr + k), ch1 = __ldg(sc.chunk_ptr + k + 1);
-        __threadfence();                                 // release: this group's partial is visible device-wide
-        __syncwarp(mask);
-        int prev = 0;
-        if (lane == 0) prev = atomicAdd(sc.arrive + k, 1);
-        prev = __shfl_sync(mask, prev, 0, G);
-        if (prev == ch1 - ch0 - 1) {                     // last chunk of the row: add the partials in chunk order
-          __threadfence();
-#pragma unroll
-          for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int c = ch0; c < ch1; ++c) {
-#pragma unroll
-            for (int v = 0; v < V; ++v) acc[v] = add4(acc[v], __ldcg(partial + int64_t(c) * ROW4 + v * G + lane));
-          }
-          epilogue<G, V>(int64_t(__ldg(sc.perm + k)), lane, acc, Y, ACC_IN, ACC_OUT, acc_scale);
-          if (lane == 0) sc.arrive[k] = 0;               // self-resetting for the next launch
-        }
+  for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int32_t bq = 0;   // first row of the current batch
+  for (int32_t q = 0; q < len; ++q) {
+    if (q - bq == G) {   // the consumer enters the next batch: shift, prefetch the one after
+      bq += G;
+      c = c_nxt;
+      w = w_nxt;
+      if (bq + G + lane < len) {
+        c_nxt = ld_idx<HOT>(idx);
+        w_nxt = ld_val<HOT>(val);
       }
-    } else {
-      epilogue<G, V>(int64_t(cur.w), lane, acc, Y, ACC_IN, ACC_OUT, acc_scale);
+      idx += G;
+      val += G;
     }
-    if (!more) break;
-    item = nitem;
-    cur = nxt;
-    begin = nbegin;
+    cp_async_wait<R - 1>();   // everything but the R - 1 youngest groups has landed: row q (and ACC_IN) are here
+    const float wq = __shfl_sync(mask, w, q - bq, G);
+    const float4 x0 = slots[(q & (R - 1)) * ROW4], x1 = slots[(q & (R - 1)) * ROW4 + 1];
+    fma4(acc[0], wq, x0);
+    fma4(acc[1], wq, x1);
+    // refill the slot just consumed with row q + R (it may belong to the next batch)
+    const int32_t il = q + R - bq;   // in [R, G + R)
+    const int32_t cj = __shfl_sync(mask, il < G ? c : c_nxt, il & (G - 1), G);
+    if (q + R < len) issue(cj, q & (R - 1));
+    cp_async_commit();
   }
+  if (plain) {
+    cp_async_wait<0>();   // (only matters for len == 0: ACC_IN may still be in flight)
+    // epilogue with ACC_IN taken from its slot
+    const int64_t row = wd.w;
+    const int64_t o = row * ROW4 + lane * V;
+    constexpr int POL = HOT ? POL_FIRST : POL_NORMAL;
+    if (ps.rows_per > 0) {
+      const int owner = int(row / ps.rows_per);
+      float4* ypush = reinterpret_cast<float4*>(c_push_base[owner] + ps.off) +
+                      (int64_t(ps.rank) * ps.rows_per + (row - int64_t(owner) * ps.rows_per)) * ROW4 + lane * V;
+      ypush[0] = acc[0];
+      ypush[1] = acc[1];
+    }
+    if (Y != nullptr) st256<POL>(Y + o, acc[0], acc[1]);
+    if (ACC_OUT != nullptr) {
+      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+      if (have_acc) {
+        a0 = slots[R * ROW4];
+        a1 = slots[R * ROW4 + 1];
+      }
+      st256<POL>(ACC_OUT + o, scale4(add4(a0, acc[0]), acc_scale), scale4(add4(a1, acc[1]), acc_scale));
+    }
+    return;
+  }
+  const int32_t k = wd.w;
+#pragma unroll
+  for (int v = 0; v < V; ++v) __stcg(partial + int64_t(item) * ROW4 + lane * V + v, acc[v]);
+  if (k < sc.n_huge) return;            // combined by k_spmm_finish
+  const int32_t c0 = __ldg(sc.chunk_ptr + k), c1 = __ldg(sc.chunk_ptr + k + 1);
+  __threadfence();                       // release: this group's partial is visible device-wide
+  __syncwarp(mask);
+  int prev = 0;
+  if (lane == 0) prev = atomicAdd(sc.arrive + k, 1);
+  prev = __shfl_sync(mask, prev, 0, G);
+  if (prev != c1 - c0 - 1) return;
+  __threadfence();                       // acquire: every other chunk's partial is visible
+#pragma unroll
+  for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int cc = c0; cc < c1; ++cc) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = add4(acc[v], __ldcg(partial + int64_t(cc) * ROW4 + lane * V + v));
+  }
+  epilogue<G, V, HOT>(int64_t(__ldg(sc.perm + k)), lane, acc, Y, ACC_IN, ACC_OUT, acc_scale, acc_nz, ps);
+  if (lane == 0) sc.arrive[k] = 0;       // self-resetting for the next launch
 }
 
 // one CTA per huge row: groups sum interleaved chunk partials, fixed-order reduction, epilogue
 template <int G, int V>
 __global__ void __launch_bounds__(SP_THREADS) k_spmm_finish(SpmmSched sc, const float4* __restrict__ partial,
                                                             float4* __restrict__ Y, const float4* ACC_IN,
-                                                            float4* ACC_OUT, float acc_scale, const SpmmPush ps) {
+                                                            float4* ACC_OUT, float acc_scale,
+                                                            const uint8_t* __restrict__ acc_nz, const SpmmPush ps) {
   constexpr int GROUPS = SP_THREADS / G;
   constexpr int ROW4 = G * V;
   __shared__ float4 red[GROUPS][ROW4];
@@ -384,19 +494,19 @@ __global__ void __launch_bounds__(SP_THREADS) k_spmm_finish(SpmmSched sc, const 
   for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int c = c0 + grp; c < c1; c += GROUPS) {
 #pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = add4(acc[v], __ldg(partial + int64_t(c) * ROW4 + v * G + lane));
+    for (int v = 0; v < V; ++v) acc[v] = add4(acc[v], __ldg(partial + int64_t(c) * ROW4 + lane * V + v));
   }
 #pragma unroll
-  for (int v = 0; v < V; ++v) red[grp][v * G + lane] = acc[v];
+  for (int v = 0; v < V; ++v) red[grp][lane * V + v] = acc[v];
   __syncthreads();
   if (grp == 0) {
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      float4 s = red[0][v * G + lane];
-      for (int g = 1; g < GROUPS; ++g) s = add4(s, red[g][v * G + lane]);
+      float4 s = red[0][lane * V + v];
+      for (int g = 1; g < GROUPS; ++g) s = add4(s, red[g][lane * V + v]);
       acc[v] = s;
     }
-    epilogue<G, V>(int64_t(__ldg(sc.perm + k)), lane, acc, Y, ACC_IN, ACC_OUT, acc_scale, ps);
+    epilogue<G, V, false>(int64_t(__ldg(sc.perm + k)), lane, acc, Y, ACC_IN, ACC_OUT, acc_scale, acc_nz, ps);
   }
 }
 
@@ -422,35 +532,10 @@ static int row_flags(const float* X, int64_t n_rows, int32_t d, uint8_t* flags, 
   return CGX_OK;
 }
 
-static int spmm_env(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
-// The persistent, software-pipelined kernel is kept as an experiment: measured SLOWER than one group per
-// item with hardware CTA scheduling (C2 d=64: 0.62 vs 0.43 ms fwd+bwd; 64M-edge d=128: 65.4 vs 61.2 ms;
-// profiles/r1_spmm_variants.txt), so it is off unless CGX_SPMM_PERSISTENT=1.
-// CGX_SPMM_WORK=0: k_spmm looks rows up through perm -> indptr instead of the flattened descriptors
-static bool spmm_use_work() {
-  static const bool on = spmm_env("CGX_SPMM_WORK", 1) != 0;
-  return on;
-}
-static bool spmm_persistent() {
-  static const bool v = spmm_env("CGX_SPMM_PERSISTENT", 0) != 0;
-  return v;
-}
-static bool spmm_pdl() {   // programmatic dependent launch of k_spmm (CGX_SPMM_PDL=0 disables)
-  static const bool v = spmm_env("CGX_SPMM_PDL", 1) != 0;
-  return v;
-}
-static int spmm_waves() {
-  static const int v = spmm_env("CGX_SPMM_WAVES", 1);
-  return v < 1 ? 1 : v;
-}
-
-template <int G, int V, int UNR, int HINT, int MINB, bool NZ = false, bool PUSH = false>
+template <int G, int V, int UNR, int MINB, bool NZ, bool PUSH, bool HOT>
 static int launch_spmm(const cgx_csr* m, const float* val, const float* X, float* Y, const float* ACC_IN,
                        float* ACC_OUT, float acc_scale, void* workspace, size_t workspace_bytes,
-                       cudaStream_t stream, const uint8_t* nz = nullptr, const SpmmPush ps = SpmmPush{0ull, 0, 0}) {
+                       cudaStream_t stream, const uint8_t* nz, const uint8_t* acc_nz, const SpmmPush ps) {
   constexpr int GROUPS = SP_THREADS / G;
   float4* partial = nullptr;
   if (m->n_long > 0) {
@@ -459,155 +544,163 @@ static int launch_spmm(const cgx_csr* m, const float* val, const float* X, float
                 "spmm: workspace too small for %d long-row chunks", m->n_chunks);
     partial = static_cast<float4*>(workspace);
   }
-  SpmmSched sc{m->perm, m->chunk_ptr, m->chunk_row, m->arrive, m->n_long, m->n_chunks, m->n_huge};
+  SpmmSched sc{m->perm, m->chunk_ptr, m->arrive, m->n_chunks, m->n_huge};
   const int64_t items = int64_t(m->n_chunks) + (m->n_rows - m->n_long);
-  if (!NZ && ps.rows_per == 0 && m->work != nullptr && spmm_persistent()) {
-    int64_t blocks = ceil_div(items, GROUPS);
-    const int64_t resident = int64_t(148) * MINB * spmm_waves();     // CTAs that fit the chip at once (x waves)
-    if (blocks > resident) blocks = resident;
-    k_spmm_p<G, V, UNR, HINT, MINB><<<(unsigned)blocks, SP_THREADS, 0, stream>>>(
-        static_cast<const int4*>(m->work), items, m->idx, val, sc, reinterpret_cast<const float4*>(X),
-        reinterpret_cast<float4*>(Y), reinterpret_cast<const float4*>(ACC_IN), reinterpret_cast<float4*>(ACC_OUT),
-        acc_scale, partial);
-  } else {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)ceil_div(items, GROUPS));
-    cfg.blockDim = dim3(SP_THREADS);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = spmm_pdl() ? 1 : 0;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    CGX_CUDA(cudaLaunchKernelEx(&cfg, k_spmm<G, V, UNR, HINT, MINB, NZ, PUSH>, m->indptr, m->idx, val, m->n_rows, sc,
-                                reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(Y),
-                                reinterpret_cast<const float4*>(ACC_IN), reinterpret_cast<float4*>(ACC_OUT), acc_scale,
-                                partial, nz, spmm_use_work() ? static_cast<const int4*>(m->work) : nullptr, ps));
-  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)ceil_div(items, GROUPS));
+  cfg.blockDim = dim3(SP_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = option(CGX_OPT_PDL) != 0 ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CGX_CUDA(cudaLaunchKernelEx(&cfg, k_spmm<G, V, UNR, MINB, NZ, PUSH, HOT>, HOT ? m->idx_hint : m->idx, val, items, sc,
+                              reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(Y),
+                              reinterpret_cast<const float4*>(ACC_IN), reinterpret_cast<float4*>(ACC_OUT), acc_scale,
+                              partial, nz, acc_nz, static_cast<const int4*>(m->work), ps));
   CGX_LAUNCH_CHECK();
   if (m->n_huge > 0) {
     k_spmm_finish<G, V><<<(unsigned)m->n_huge, SP_THREADS, 0, stream>>>(
         sc, partial, reinterpret_cast<float4*>(Y), reinterpret_cast<const float4*>(ACC_IN),
-        reinterpret_cast<float4*>(ACC_OUT), acc_scale, ps);
+        reinterpret_cast<float4*>(ACC_OUT), acc_scale, acc_nz, ps);
     CGX_LAUNCH_CHECK();
   }
   return CGX_OK;
 }
 
-// gathered tables above this many bytes count as "beyond L2" (cgx_spmm_set_l2_table_bytes; default 96 MiB of 126)
-static int64_t g_l2_table_bytes = int64_t(96) << 20;
+constexpr int RING_ROWS = 4;    // row slots per group (plus one for ACC_IN): 5 x 4d bytes of shared memory per group
+constexpr int RING_MINB = 5;    // CTAs per SM the register allocation must allow (48 registers)
 
-static int spmm_variant() {
-  static int v = [] {
-    const char* e = getenv("CGX_SPMM_VARIANT");
-    return e ? atoi(e) : 0;
-  }();
-  return v;
+template <int G, int V, bool PUSH, bool HOT>
+static int launch_spmm_ring(const cgx_csr* m, const float* val, const float* X, float* Y, const float* ACC_IN,
+                            float* ACC_OUT, float acc_scale, void* workspace, size_t workspace_bytes,
+                            cudaStream_t stream, const uint8_t* acc_nz, const SpmmPush ps) {
+  constexpr int GROUPS = SP_THREADS / G;
+  constexpr size_t SMEM = size_t(GROUPS) * (RING_ROWS + 1) * G * V * sizeof(float4);
+  float4* partial = nullptr;
+  if (m->n_long > 0) {
+    size_t need = size_t(m->n_chunks) * G * V * sizeof(float4);
+    CGX_REQUIRE(workspace != nullptr && workspace_bytes >= need, CGX_ERR_WORKSPACE,
+                "spmm: workspace too small for %d long-row chunks", m->n_chunks);
+    partial = static_cast<float4*>(workspace);
+  }
+  auto kern = k_spmm_ring<G, V, RING_ROWS, RING_MINB, PUSH, HOT>;
+  if (SMEM > 48 * 1024) {   // opt-in above 48 KB, once per device (a bit per ordinal; also keeps it out of graph captures)
+    static std::atomic<unsigned long long> attr_set{0};
+    int dev = 0;
+    CGX_CUDA(cudaGetDevice(&dev));
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(attr_set.load(std::memory_order_acquire) & bit)) {
+      CGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+      attr_set.fetch_or(bit, std::memory_order_release);
+    }
+  }
+  SpmmSched sc{m->perm, m->chunk_ptr, m->arrive, m->n_chunks, m->n_huge};
+  const int64_t items = int64_t(m->n_chunks) + (m->n_rows - m->n_long);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)ceil_div(items, GROUPS));
+  cfg.blockDim = dim3(SP_THREADS);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = option(CGX_OPT_PDL) != 0 ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CGX_CUDA(cudaLaunchKernelEx(&cfg, kern, HOT ? m->idx_hint : m->idx, val, items, sc,
+                              reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(Y),
+                              reinterpret_cast<const float4*>(ACC_IN), reinterpret_cast<float4*>(ACC_OUT), acc_scale,
+                              partial, acc_nz, static_cast<const int4*>(m->work), ps));
+  CGX_LAUNCH_CHECK();
+  if (m->n_huge > 0) {
+    k_spmm_finish<G, V><<<(unsigned)m->n_huge, SP_THREADS, 0, stream>>>(
+        sc, partial, reinterpret_cast<float4*>(Y), reinterpret_cast<const float4*>(ACC_IN),
+        reinterpret_cast<float4*>(ACC_OUT), acc_scale, acc_nz, ps);
+    CGX_LAUNCH_CHECK();
+  }
+  return CGX_OK;
 }
 
-#define CGX_SPMM_ARGS m, val, X, Y, ACC_IN, ACC_OUT, acc_scale, ws, ws_bytes, stream, nz, ps
+#define CGX_SPMM_ARGS m, val, X, Y, ACC_IN, ACC_OUT, acc_scale, ws, ws_bytes, stream, nz, acc_nz, ps
+
+// Group geometry by regime (profiles/r1_spmm_variants.txt; the sweep itself lives in the round-1 history).
+// Gathered table in L2 (C2/C3: latency-bound): d/4 lanes per row, one float4 per lane, 8 gathers in flight.
+// Gathered table beyond L2 (HBM-bound): d/8 lanes per row, 32 contiguous bytes (one 256-bit access) per lane, four
+// gathers in flight -- twice the rows in flight per SM at the same bytes in flight per lane (d = 64: 27.3 vs 30.1 ms,
+// d = 128: 53.8 vs 58.6 ms on the 64M-edge shape; on C2 the same split LOSES, 0.65 vs 0.43 ms at d = 64) -- and,
+// when the graph carries hot-row hints (cgx_hot_hints), per-row L2 eviction priorities.
+template <int G, int V, int UNR>
+static int spmm_flavour(const cgx_csr* m, const float* val, const float* X, float* Y, const float* ACC_IN,
+                        float* ACC_OUT, float acc_scale, void* ws, size_t ws_bytes, cudaStream_t stream,
+                        const uint8_t* nz, const uint8_t* acc_nz, const SpmmPush ps, bool hot) {
+  const bool push = ps.rows_per > 0;
+  if constexpr (V == 2) {
+#define CGX_RING_ARGS m, val, X, Y, ACC_IN, ACC_OUT, acc_scale, ws, ws_bytes, stream, acc_nz, ps
+    if (nz == nullptr && option(CGX_OPT_SPMM_RING) != 0) {   // HBM-resident table: gathers staged through shared memory
+      if (hot) {
+        if (push) return launch_spmm_ring<G, V, true, true>(CGX_RING_ARGS);
+        return launch_spmm_ring<G, V, false, true>(CGX_RING_ARGS);
+      }
+      if (push) return launch_spmm_ring<G, V, true, false>(CGX_RING_ARGS);
+      return launch_spmm_ring<G, V, false, false>(CGX_RING_ARGS);
+    }
+#undef CGX_RING_ARGS
+    if (hot && nz == nullptr) {
+      if (push) return launch_spmm<G, V, UNR, 4, false, true, true>(CGX_SPMM_ARGS);
+      return launch_spmm<G, V, UNR, 4, false, false, true>(CGX_SPMM_ARGS);
+    }
+  }
+  if (push) {
+    if (nz) return launch_spmm<G, V, UNR, 4, true, true, false>(CGX_SPMM_ARGS);
+    return launch_spmm<G, V, UNR, 4, false, true, false>(CGX_SPMM_ARGS);
+  }
+  if (nz) return launch_spmm<G, V, UNR, 4, true, false, false>(CGX_SPMM_ARGS);
+  return launch_spmm<G, V, UNR, 4, false, false, false>(CGX_SPMM_ARGS);
+}
+
+#define CGX_FLAVOUR_ARGS m, val, X, Y, ACC_IN, ACC_OUT, acc_scale, ws, ws_bytes, stream, nz, acc_nz, ps, hot
 
 static int spmm_dispatch(const cgx_csr* m, int use_bwd, int32_t d, const float* X, float* Y, const float* ACC_IN,
                          float* ACC_OUT, float acc_scale, void* ws, size_t ws_bytes, cudaStream_t stream,
-                         const uint8_t* nz = nullptr, const SpmmPush ps = SpmmPush{0ull, 0, 0}) {
-  CGX_REQUIRE(m && m->indptr && m->perm && (m->nnz == 0 || (m->idx && m->val_fwd && m->val_bwd)) && X, CGX_ERR_ARG,
-              "spmm: NULL pointer");
-  CGX_REQUIRE(m->n_long == 0 || (m->chunk_ptr && m->chunk_row && m->arrive), CGX_ERR_ARG,
-              "spmm: chunk tables missing");
+                         const uint8_t* nz = nullptr, const SpmmPush ps = SpmmPush{0ull, 0, 0},
+                         const uint8_t* acc_nz = nullptr) {
+  CGX_REQUIRE(m && m->perm && m->work && (m->nnz == 0 || (m->idx && m->val_fwd && m->val_bwd)) && X, CGX_ERR_ARG,
+              "spmm: NULL pointer (cgx_csr needs idx, both value arrays and the cgx_row_schedule* outputs)");
+  CGX_REQUIRE(m->n_long == 0 || (m->chunk_ptr && m->arrive), CGX_ERR_ARG, "spmm: chunk tables missing");
   CGX_REQUIRE(Y || ACC_OUT || ps.rows_per > 0, CGX_ERR_ARG, "spmm: no output requested");
   const float* val = use_bwd ? m->val_bwd : m->val_fwd;
   if (m->n_rows == 0) return CGX_OK;
-  // Group geometry by regime (profiles/r1_spmm_variants.txt).  Gathered table in L2 (C2/C3: latency-bound): d/4 lanes
-  // per row, one float4 per lane, 8 gathers in flight.  Gathered table beyond L2 (HBM-bound): d/8 lanes per row, two
-  // float4 per lane, 4 gathers in flight -- twice the rows in flight per SM at the same bytes in flight per lane
-  // (d = 64: 27.3 vs 30.1 ms, d = 128: 53.8 vs 58.6 ms on the 64M-edge shape; on C2 the same split LOSES, 0.65 vs
-  // 0.43 ms at d = 64 and 0.71 vs 0.61 ms at d = 128).
-  const bool beyond_l2 = int64_t(m->n_cols) * int64_t(d) * 4 > g_l2_table_bytes;
-  if (ps.rows_per > 0) {   // push mode (user-sharded item products): default geometries, with or without row flags
-#define CGX_PUSH_CASE(GG, VV, UU)                                                              \
-    return nz ? launch_spmm<GG, VV, UU, HINT_NC, 4, true, true>(CGX_SPMM_ARGS)                \
-              : launch_spmm<GG, VV, UU, HINT_NC, 4, false, true>(CGX_SPMM_ARGS)
-    switch (d) {
-      case 16: CGX_PUSH_CASE(4, 1, 4);
-      case 32: CGX_PUSH_CASE(8, 1, 8);
-      case 64:
-        if (beyond_l2) { CGX_PUSH_CASE(8, 2, 4); }
-        CGX_PUSH_CASE(16, 1, 8);
-      case 128:
-        if (beyond_l2) { CGX_PUSH_CASE(16, 2, 4); }
-        CGX_PUSH_CASE(32, 1, 8);
-      case 256: CGX_PUSH_CASE(32, 2, 4);
-      default:
-        set_error("spmm: emb_dim %d unsupported (16, 32, 64, 128, 256)", d);
-        return CGX_ERR_UNSUPPORTED;
-    }
-#undef CGX_PUSH_CASE
-  }
-  if (nz != nullptr) {   // sparse input rows: the default geometry of every width, row loads predicated on nz
-    switch (d) {
-      case 16: return launch_spmm<4, 1, 4, HINT_NC, 4, true>(CGX_SPMM_ARGS);
-      case 32: return launch_spmm<8, 1, 8, HINT_NC, 4, true>(CGX_SPMM_ARGS);
-      case 64:
-        if (beyond_l2) return launch_spmm<8, 2, 4, HINT_NC, 4, true>(CGX_SPMM_ARGS);
-        return launch_spmm<16, 1, 8, HINT_NC, 4, true>(CGX_SPMM_ARGS);
-      case 128:
-        if (beyond_l2) return launch_spmm<16, 2, 4, HINT_NC, 4, true>(CGX_SPMM_ARGS);
-        return launch_spmm<32, 1, 8, HINT_NC, 4, true>(CGX_SPMM_ARGS);
-      case 256: return launch_spmm<32, 2, 4, HINT_NC, 4, true>(CGX_SPMM_ARGS);
-      default: break;
-    }
-  }
-  const int variant = spmm_variant();
+  const bool beyond_l2 = int64_t(m->n_cols) * int64_t(d) * 4 > option(CGX_OPT_L2_TABLE_BYTES);
+  const bool hot = beyond_l2 && m->idx_hint != nullptr && option(CGX_OPT_HOT_ROWS) != 0;
   switch (d) {
-    case 16: return launch_spmm<4, 1, 4, HINT_NC, 4>(CGX_SPMM_ARGS);
-    case 32: return launch_spmm<8, 1, 8, HINT_NC, 4>(CGX_SPMM_ARGS);
-  // The gather-loop / geometry variants measured in profiles/r1_spmm_variants.txt (CGX_SPMM_VARIANT=<id>) are only
-  // compiled with `make EXTRA=-DCGX_SPMM_TUNING` (profiles/tune_spmm.py): 40 extra instantiations of k_spmm.
-#ifndef CGX_SPMM_TUNING
-#define CGX_VARIANTS(GG) return launch_spmm<GG, 1, 8, HINT_NC, 4>(CGX_SPMM_ARGS);
-#else
-#define CGX_VARIANTS(GG)                                                                   \
-      switch (variant) {                                                                   \
-        case 1: return launch_spmm<GG, 1, 16, HINT_NC, 1>(CGX_SPMM_ARGS);                  \
-        case 2: return launch_spmm<GG, 1, 8, HINT_CG, 1>(CGX_SPMM_ARGS);                   \
-        case 3: return launch_spmm<GG, 1, 8, HINT_NC_NOALLOC, 1>(CGX_SPMM_ARGS);           \
-        case 4: return launch_spmm<GG, 1, 4, HINT_NC, 6>(CGX_SPMM_ARGS);                   \
-        case 5: return launch_spmm<GG, 1, 8, HINT_NC, 5>(CGX_SPMM_ARGS);                   \
-        case 6: return launch_spmm<GG, 1, 16, HINT_NC_NOALLOC, 1>(CGX_SPMM_ARGS);          \
-        case 7: return launch_spmm<GG, 1, 4, HINT_NC, 8>(CGX_SPMM_ARGS);                   \
-        case 8: return launch_spmm<GG, 1, 2, HINT_NC, 8>(CGX_SPMM_ARGS);                   \
-        case 9: return launch_spmm<GG, 1, 4, HINT_NC_NOALLOC, 6>(CGX_SPMM_ARGS);           \
-        case 10: return launch_spmm<GG, 1, 4, HINT_CG, 6>(CGX_SPMM_ARGS);                  \
-        case 11: return launch_spmm<GG, 1, 2, HINT_NC, 6>(CGX_SPMM_ARGS);                  \
-        case 12: return launch_spmm<GG, 1, 8, HINT_NC, 3>(CGX_SPMM_ARGS);                  \
-        case 13: return launch_spmm<GG, 1, 16, HINT_NC, 2>(CGX_SPMM_ARGS);                 \
-        case 14: return launch_spmm<GG, 1, 4, HINT_NC, 4>(CGX_SPMM_ARGS);                  \
-        case 15: return launch_spmm<GG, 1, 8, HINT_NC, 4>(CGX_SPMM_ARGS);                  \
-        case 16: return launch_spmm<GG, 1, 8, HINT_NC, 1>(CGX_SPMM_ARGS);                  \
-        case 17: return launch_spmm<GG / 2, 2, 4, HINT_NC, 4>(CGX_SPMM_ARGS);              \
-        case 18: return launch_spmm<GG / 2, 2, 8, HINT_NC, 2>(CGX_SPMM_ARGS);              \
-        case 19: return launch_spmm<GG / 4, 4, 2, HINT_NC, 4>(CGX_SPMM_ARGS);              \
-        case 20: return launch_spmm<GG / 2, 2, 2, HINT_NC, 6>(CGX_SPMM_ARGS);              \
-        case 21: return launch_spmm<GG / 2, 2, 4, HINT_NC, 3>(CGX_SPMM_ARGS);              \
-        default: return launch_spmm<GG, 1, 8, HINT_NC, 4>(CGX_SPMM_ARGS);                  \
-      }
-#endif
+    case 16: return spmm_flavour<4, 1, 4>(CGX_FLAVOUR_ARGS);
+    case 32: return spmm_flavour<8, 1, 8>(CGX_FLAVOUR_ARGS);
     case 64:
-      if (variant == 0 && beyond_l2) return launch_spmm<8, 2, 4, HINT_NC, 4>(CGX_SPMM_ARGS);
-      CGX_VARIANTS(16)
+      if (beyond_l2) return spmm_flavour<8, 2, 4>(CGX_FLAVOUR_ARGS);
+      return spmm_flavour<16, 1, 8>(CGX_FLAVOUR_ARGS);
     case 128:
-      if (variant == 0 && beyond_l2) return launch_spmm<16, 2, 4, HINT_NC, 4>(CGX_SPMM_ARGS);
-      CGX_VARIANTS(32)
-    case 256:
-#ifdef CGX_SPMM_TUNING
-      if (variant == 17) return launch_spmm<16, 4, 2, HINT_NC, 4>(CGX_SPMM_ARGS);
-#endif
-      return launch_spmm<32, 2, 4, HINT_NC, 4>(CGX_SPMM_ARGS);
+      if (beyond_l2) return spmm_flavour<16, 2, 4>(CGX_FLAVOUR_ARGS);
+      return spmm_flavour<32, 1, 8>(CGX_FLAVOUR_ARGS);
+    case 256: return spmm_flavour<32, 2, 4>(CGX_FLAVOUR_ARGS);
     default:
       set_error("spmm: emb_dim %d unsupported (16, 32, 64, 128, 256)", d);
       return CGX_ERR_UNSUPPORTED;
   }
+}
+
+// hot[c] = 1 for the first n_hot entries of col_by_degree (the OTHER row order's perm: columns in descending degree)
+__global__ void k_hot_flags(const int32_t* __restrict__ col_by_degree, int32_t n_hot, uint8_t* __restrict__ hot) {
+  const int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n_hot) hot[__ldg(col_by_degree + k)] = 1;
+}
+__global__ void k_hot_hint(const int32_t* __restrict__ idx, int64_t nnz, const uint8_t* __restrict__ hot,
+                           int32_t* __restrict__ out) {
+  const int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= nnz) return;
+  const int32_t c = idx[p];
+  out[p] = __ldg(hot + c) ? (c | int32_t(0x80000000u)) : c;
 }
 
 static size_t spmm_ws(const cgx_csr* m, int32_t d) { return align_up(size_t(m ? m->n_chunks : 0) * d * 4); }
@@ -634,9 +727,33 @@ extern "C" int cgx_spmm_sparse_rows(const cgx_csr* m, int use_bwd_values, int32_
 }
 
 extern "C" int64_t cgx_spmm_set_l2_table_bytes(int64_t bytes) {
-  const int64_t old = g_l2_table_bytes;
-  g_l2_table_bytes = bytes < 0 ? (int64_t(96) << 20) : bytes;
+  int64_t old = 0;
+  cgx_set_option(CGX_OPT_L2_TABLE_BYTES, bytes, &old);
   return old;
+}
+
+extern "C" size_t cgx_hot_hints_workspace_bytes(int32_t n_cols) { return align_up(size_t(n_cols > 0 ? n_cols : 0)) + 256; }
+
+extern "C" int cgx_hot_hints(const int32_t* idx, int64_t nnz, int32_t n_cols, const int32_t* col_by_degree,
+                             int32_t n_hot, int32_t* idx_hint, void* workspace, size_t workspace_bytes,
+                             void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CGX_REQUIRE(nnz >= 0 && n_cols > 0 && col_by_degree && idx_hint && (nnz == 0 || idx) && n_hot >= 0 &&
+                  n_hot <= n_cols,
+              CGX_ERR_ARG, "hot_hints: bad argument");
+  CGX_REQUIRE(workspace != nullptr && workspace_bytes >= cgx_hot_hints_workspace_bytes(n_cols), CGX_ERR_WORKSPACE,
+              "hot_hints: workspace too small");
+  uint8_t* hot = static_cast<uint8_t*>(workspace);
+  CGX_CUDA(cudaMemsetAsync(hot, 0, size_t(n_cols), stream));
+  if (n_hot > 0) {
+    k_hot_flags<<<(unsigned)ceil_div(n_hot, 256), 256, 0, stream>>>(col_by_degree, n_hot, hot);
+    CGX_LAUNCH_CHECK();
+  }
+  if (nnz > 0) {
+    k_hot_hint<<<(unsigned)ceil_div(nnz, 256), 256, 0, stream>>>(idx, nnz, hot, idx_hint);
+    CGX_LAUNCH_CHECK();
+  }
+  return CGX_OK;
 }
 
 extern "C" int cgx_spmm_set_push_peers(void* const* peer_bases, int world) {
@@ -729,8 +846,9 @@ extern "C" int cgx_propagate_bwd(const cgx_csr* by_user, const cgx_csr* by_item,
   const float s = 1.0f / float(K + 1);
   // The incoming gradient has non-zero rows only where the batch touched the tables (<= batch users,
   // <= 2 * batch items): the products that gather g_u / g_i directly skip the zero rows (row flags, 1 byte per
-  // row).  After one product the adjoint is dense.  CGX_SPARSE_BWD=0 switches this off.
-  static const bool sparse = spmm_env("CGX_SPARSE_BWD", 1) != 0;
+  // row), and every product's ACC_IN -- the gradient seed again -- is only read where its flag is set.  After one
+  // product the adjoint itself is dense.  CGX_OPT_SPARSE_FIRST_ADJOINT = 0 switches both off.
+  const bool sparse = option(CGX_OPT_SPARSE_FIRST_ADJOINT) != 0;
   uint8_t* nz_u = ws.take<uint8_t>(U);
   uint8_t* nz_i = ws.take<uint8_t>(I);
   CGX_REQUIRE(ws.ok, CGX_ERR_WORKSPACE, "propagate_bwd: workspace too small");
@@ -750,21 +868,29 @@ extern "C" int cgx_propagate_bwd(const cgx_csr* by_user, const cgx_csr* by_item,
       float* ni = last ? d_e0_i : ib[k & 1];
       const float sc = last ? s : 1.0f;
       const bool sp = sparse && k == 0;
-      CGX_TRY(spmm_dispatch(by_user, 1, d, bi, nullptr, g_u, nu, sc, lw, lws, stream, sp ? nz_i : nullptr));  // g_u + C^T bi
-      CGX_TRY(spmm_dispatch(by_item, 1, d, bu, nullptr, g_i, ni, sc, lw, lws, stream, sp ? nz_u : nullptr));  // g_i + A^T bu
+      const SpmmPush nops{0ull, 0, 0};
+      CGX_TRY(spmm_dispatch(by_user, 1, d, bi, nullptr, g_u, nu, sc, lw, lws, stream, sp ? nz_i : nullptr, nops,
+                            sparse ? nz_u : nullptr));                                             // g_u + C^T bi
+      CGX_TRY(spmm_dispatch(by_item, 1, d, bu, nullptr, g_i, ni, sc, lw, lws, stream, sp ? nz_u : nullptr, nops,
+                            sparse ? nz_i : nullptr));                                             // g_i + A^T bu
       bu = nu;
       bi = ni;
     }
   } else {
     const float* bu = g_u;
-    if (sparse) CGX_TRY(row_flags(g_u, U, d, nz_u, stream));
+    if (sparse) {
+      CGX_TRY(row_flags(g_u, U, d, nz_u, stream));
+      CGX_TRY(row_flags(g_i, I, d, nz_i, stream));
+    }
+    const SpmmPush nops{0ull, 0, 0};
     for (int k = 0; k < K; ++k) {
       const bool last = k == K - 1;
       float* ni = ib[0];
       float* nu = last ? d_e0_u : ub[k & 1];
       CGX_TRY(spmm_dispatch(by_item, 1, d, bu, nullptr, g_i, ni, 1.0f, lw, lws, stream,
-                            sparse && k == 0 ? nz_u : nullptr));                                      // bi'
-      CGX_TRY(spmm_dispatch(by_user, 1, d, ni, nullptr, g_u, nu, last ? s : 1.0f, lw, lws, stream));  // bu'
+                            sparse && k == 0 ? nz_u : nullptr, nops, sparse ? nz_i : nullptr));       // bi'
+      CGX_TRY(spmm_dispatch(by_user, 1, d, ni, nullptr, g_u, nu, last ? s : 1.0f, lw, lws, stream, nullptr, nops,
+                            sparse ? nz_u : nullptr));                                                // bu'
       bu = nu;
     }
     const int64_t n4 = I * d / 4;

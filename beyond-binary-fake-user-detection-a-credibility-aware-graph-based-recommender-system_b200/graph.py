@@ -69,6 +69,8 @@ class Csr:
     n_huge: int = 0
     arrive: torch.Tensor | None = None
     work: torch.Tensor | None = None
+    idx_hint: torch.Tensor | None = None       # idx | hot << 31 (cgx_hot_hints); None = no hints
+    n_hot: int = 0
     _struct: CsrStruct | None = field(default=None, repr=False)
 
     def struct(self) -> CsrStruct:
@@ -84,6 +86,7 @@ class Csr:
             s.n_huge = self.n_huge
             s.arrive = self.arrive.data_ptr() if self.n_long else None
             s.work = self.work.data_ptr() if self.work is not None else None
+            s.idx_hint = self.idx_hint.data_ptr() if self.idx_hint is not None else None
             self._struct = s
         return self._struct
 
@@ -111,6 +114,25 @@ class Csr:
             check(lib().cgx_row_schedule_work(ptr(self.indptr), ptr(self.perm), self.n_rows, self.n_long,
                                               self.n_chunks, ptr(self.chunk_ptr), ptr(self.chunk_row),
                                               ptr(self.work), stream_ptr(dev)))
+        self._struct = None
+
+    def set_hot_columns(self, col_by_degree: torch.Tensor, n_hot: int):
+        """Mark the n_hot highest-degree columns as hot rows of the gathered table (cgx_hot_hints).  The hint array
+        keeps its address when it is rebuilt (a captured CUDA graph stays valid); n_hot = 0 removes the hints."""
+        n_hot = max(0, min(int(n_hot), self.n_cols))
+        if n_hot == self.n_hot:
+            return
+        self.n_hot = n_hot
+        if n_hot == 0 or self.nnz == 0:
+            self.idx_hint, self.n_hot = None, 0
+        else:
+            dev = self.indptr.device
+            if self.idx_hint is None:
+                self.idx_hint = torch.empty_like(self.idx)
+            ws = workspace(lib().cgx_hot_hints_workspace_bytes(self.n_cols), dev)
+            with torch.cuda.device(dev):
+                check(lib().cgx_hot_hints(ptr(self.idx), self.nnz, self.n_cols, ptr(col_by_degree), n_hot,
+                                          ptr(self.idx_hint), ptr(ws), ws.numel(), stream_ptr(dev)))
         self._struct = None
 
     def row_ids(self) -> torch.Tensor:
@@ -142,9 +164,24 @@ class CredGraph:
     def user_csr_numpy(self):
         return self.samp_indptr.cpu().numpy(), self.samp_idx.cpu().numpy().astype(np.int64)
 
+    # Hot rows (north_star 2: "staging of hot (high-degree) rows"): when a gathered table is larger than L2, the rows of
+    # its highest-degree columns -- HOT_BYTES worth of them -- are loaded with the L2 evict_last priority by the SpMM
+    # and everything else streams through evict_first.  Half of the 126 MB L2 by default: the two L2 partitions each
+    # keep their own copy of a line that SMs of both dies read.
+    HOT_BYTES = 48 << 20
+
+    def set_emb_dim(self, d: int, hot_bytes: int | None = None):
+        """(Re)build the hot-row hints for embedding width d.  No hints when the table fits L2 anyway."""
+        hot_bytes = self.HOT_BYTES if hot_bytes is None else int(hot_bytes)
+        l2 = _lib.get_option("L2_TABLE_BYTES")
+        for csr, other in ((self.by_user, self.by_item), (self.by_item, self.by_user)):
+            beyond = csr.n_cols * d * 4 > l2
+            csr.set_hot_columns(other.perm, hot_bytes // (4 * d) if beyond else 0)
+
     def propagate_workspace(self, d: int) -> torch.Tensor:
         key = ("prop", d)
         if key not in self._ws_cache:
+            self.set_emb_dim(d)
             n = lib().cgx_propagate_workspace_bytes(self.by_user.ref(), self.by_item.ref(), d)
             self._ws_cache[key] = workspace(n, self.device)
         return self._ws_cache[key]

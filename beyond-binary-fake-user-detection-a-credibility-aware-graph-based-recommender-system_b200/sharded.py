@@ -89,6 +89,9 @@ class P2PExchange:
     REGION_ALIGN = 1 << 16
 
     def __init__(self, max_floats: int, device, group=None):
+        """Collective over `group`: EVERY rank issues the same sequence of torch.distributed calls whether or not
+        its own CUDA calls succeed (a failure is agreed on after each phase and raised on all ranks together), so a
+        rank without peer access can never leave the others waiting inside a mismatched collective."""
         import ctypes as C
         self.group, self.device = group, torch.device(device)
         self.world = _world(group)
@@ -96,29 +99,77 @@ class P2PExchange:
         self.region = (4 * int(max_floats) + self.REGION_ALIGN - 1) // self.REGION_ALIGN * self.REGION_ALIGN
         self.flag_off = 4 * self.region
         total = self.flag_off + 4096
-        base = C.c_void_p()
-        with torch.cuda.device(self.device):
-            check(lib().cgx_comm_alloc(total, C.byref(base)))
-            handle = (C.c_char * 64)()
-            check(lib().cgx_comm_ipc_handle(base, handle))
-            handles = [None] * self.world
+        self.base = C.c_void_p()
+        self.bases = (C.c_void_p * self.world)()
+        self._opened = []
+        handle = (C.c_char * 64)()
+        err = None
+
+        def agree(phase):
+            """All ranks learn whether ANY rank failed `phase`; all raise together."""
+            nonlocal err
+            bad = torch.tensor([0.0 if err is None else 1.0], device=self.device)
             if self.world > 1:
+                dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=group)
+            if bad.item() != 0:
+                self.close()
+                raise _lib.CgxError(f"P2PExchange: {phase} failed on " +
+                                    (f"this rank: {err}" if err is not None else "another rank"))
+
+        with torch.cuda.device(self.device):
+            try:                                    # phase 1: allocate + export
+                check(lib().cgx_comm_alloc(total, C.byref(self.base)))
+                check(lib().cgx_comm_ipc_handle(self.base, handle))
+            except Exception as e:                  # noqa: BLE001
+                err = f"{type(e).__name__}: {e}"
+            agree("allocating the communication buffer")
+            handles = [None] * self.world
+            if self.world > 1:                      # outside any try: every rank takes part
                 dist.all_gather_object(handles, bytes(handle.raw), group=group)
-            self.bases = (C.c_void_p * self.world)()
-            for p in range(self.world):
-                if p == self.rank:
-                    self.bases[p] = base.value
-                else:
-                    peer = C.c_void_p()
-                    check(lib().cgx_comm_ipc_open(C.c_char_p(handles[p]), C.byref(peer)))
-                    self.bases[p] = peer.value
-            check(lib().cgx_spmm_set_push_peers(self.bases, self.world))   # targets of the fused product + exchange
-        self.base = base
-        self.bytes = torch.as_tensor(_RawCuda(base.value, total), device=self.device)
+            try:                                    # phase 2: map the peers
+                for p in range(self.world):
+                    if p == self.rank:
+                        self.bases[p] = self.base.value
+                    else:
+                        peer = C.c_void_p()
+                        check(lib().cgx_comm_ipc_open(C.c_char_p(handles[p]), C.byref(peer)))
+                        self._opened.append(peer)
+                        self.bases[p] = peer.value
+                check(lib().cgx_spmm_set_push_peers(self.bases, self.world))   # targets of the fused product + exchange
+            except Exception as e:                  # noqa: BLE001
+                err = f"{type(e).__name__}: {e}"
+            agree("mapping the peers' buffers (no NVLink / IPC peer access?)")
+        self.bytes = torch.as_tensor(_RawCuda(self.base.value, total), device=self.device)
         self.epoch_dev = torch.zeros(1, dtype=torch.int64, device=self.device)   # exchanges done so far
         self.slot = 0                                                          # region of the next exchange
         if self.world > 1:
-            dist.barrier(group=group)          # every rank has mapped every buffer before the first collective
+            dist.barrier(group=group)          # every rank has mapped every buffer before the first exchange
+
+    def check(self):
+        """Raise if a cross-GPU barrier of an exchange timed out (a peer died or lost step): the kernels then gave up
+        instead of hanging the job, and every table exchanged since is unusable.  Synchronises the device."""
+        import ctypes as C
+        if self.base is None or not self.base.value:
+            return
+        code = C.c_uint32(0)
+        with torch.cuda.device(self.device):
+            check(lib().cgx_comm_status(self.base, self.flag_off, self.world, C.byref(code)))
+        if code.value:
+            raise _lib.CgxError(f"P2PExchange: rank {self.rank} gave up waiting for rank {(code.value & 0xff) - 1} at "
+                                f"barrier {'AB'[(code.value >> 8) - 1]} of an exchange "
+                                f"(time-out {_lib.get_option('P2P_TIMEOUT_MS')} ms)")
+
+    def close(self):
+        """Unmap the peers' buffers and free the own one (after all ranks are done with the exchange)."""
+        self.bytes = None
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            for peer in self._opened:
+                lib().cgx_comm_ipc_close(peer)
+            self._opened = []
+            if self.base is not None and self.base.value:
+                lib().cgx_comm_free(self.base)
+            self.base = None
 
     def _view(self, offset, shape):
         n = int(np.prod(shape))
@@ -138,8 +189,12 @@ class P2PExchange:
         """Fused SpMM -> owner push + local reduce (cgx_spmm_push / cgx_comm_allreduce_pushed): the default above
         2 ranks (4 ranks: 0.896 vs 0.975 ms/step).  At 2 ranks the one-shot pull kernel has one barrier less and
         wins (0.793 vs 0.812 ms).  CGX_P2P_PUSH=1 / 0 forces it on / off."""
+        if self.force_push is not None:
+            return self.world > 1 and bool(self.force_push)
         env = os.environ.get("CGX_P2P_PUSH")
         return self.world > 1 and (env == "1" or (env is None and self.world > 2))
+
+    force_push = None       # True / False overrides the default choice (tests)
 
     def exchange_pushed(self, shape, push_product):
         """One item-table exchange in pushed form.  `push_product(stage_off, rank, world, rows_per)` must launch the
@@ -330,19 +385,15 @@ class ShardedTrainStep:
         n_red = 2 * self.ei.numel() + 4
         self.ex = None
         if exchange == "p2p" and _world(group) > 1:
-            # peer mapping can be unavailable (no NVLink/IPC between the ranks): all ranks must then agree to
-            # use the collective exchange, so the outcome itself is reduced
-            ok = torch.ones(1, device=self.ei.device)
+            # peer mapping can be unavailable (no NVLink/IPC between the ranks): P2PExchange agrees on the outcome
+            # over `group` and raises on ALL ranks together, which then all use the collective exchange
             try:
                 self.ex = P2PExchange(n_red, self.ei.device, group)
-            except Exception as e:      # noqa: BLE001 -- any failure means "no peer path"
-                ok.zero_()
-                self._p2p_error = f"{type(e).__name__}: {e}"
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-            if ok.item() == 0:
-                self.ex = None
+            except _lib.CgxError as e:
+                self._p2p_error = str(e)
         if self.ex is None:
             self.ex = CollectiveExchange(group)
+        graph.set_emb_dim(self.ei.shape[1])          # hot-row hints of the SpMMs for this width
         self.prop = ShardedPropagation(CudaBackend(graph), num_layers, order, group, self.ex)
         self.sampler = TripleSampler(graph, mix_pop, gamma, max_tries, seed)
         self.reg = float(reg_weight)
@@ -422,6 +473,16 @@ class ShardedTrainStep:
             return self._g_loss
         return self(torch.as_tensor(users).to(self.eu.device, non_blocking=True))
 
+    def check(self):
+        """Raise if an exchange gave up waiting for a peer (P2PExchange.check; synchronises)."""
+        if isinstance(self.ex, P2PExchange):
+            self.ex.check()
+
+    def close(self):
+        self._graph = None
+        if isinstance(self.ex, P2PExchange):
+            self.ex.close()
+
 
 @torch.no_grad()
 def evaluate_full_ranking_sharded(f_u_local, f_i, graph: CredGraph, test_edges_local, num_items, Ks=(10, 20),
@@ -489,20 +550,105 @@ def evaluate_full_ranking_sharded(f_u_local, f_i, graph: CredGraph, test_edges_l
 
 
 # ------------------------------------------------------------------------------------------
-# bench.py --gpus N (N > 1): weak scaling, one C2-shaped user shard per rank
+# parity of the sharded path against the single-GPU path (tests/test_gpu_multi.py, bench.py --gpus N)
+# ------------------------------------------------------------------------------------------
+@torch.no_grad()
+def parity_vs_single_gpu(rank: int, world: int, dev, variant="v2", order="gs", exchange=None, d=64, K=3,
+                         batch=2048, graph_kwargs=None):
+    """max relative error of the user-sharded forward / loss / gradients over `world` ranks against the single-GPU
+    path on the WHOLE graph (a C1-shaped graph split by partition_users), for one injected triple list.  Every rank
+    computes the single-GPU truth itself; the result is the maximum over ranks and quantities."""
+    from . import synth
+    from .graph import build_graph
+    from .model import CredLightGCN, LightGCN, TrainStep
+    sg = synth.make_graph("C1", **(graph_kwargs or dict(duplicate_edges=100)))
+    U, I = sg.num_users, sg.num_items
+    bounds = partition_users(np.bincount(sg.train_edges[0], minlength=U), world)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    users, pos, neg = synth.make_triples(sg, batch)
+    mine = (users >= lo) & (users < hi)
+    torch.manual_seed(0)
+    eu = torch.nn.init.xavier_uniform_(torch.empty(U, d))
+    ei = torch.nn.init.xavier_uniform_(torch.empty(I, d))
+    gl = build_local_graph(shard_edges(sg.train_edges, bounds, rank), hi - lo, I, sg.cred[lo:hi], variant, dev)
+    ex = exchange or CollectiveExchange()
+    prop = ShardedPropagation(CudaBackend(gl), K, order, exchange=ex)
+    if hasattr(ex, "begin_step"):
+        ex.begin_step()
+    eu_l, ei_d = eu[lo:hi].to(dev).contiguous(), ei.to(dev)
+    f_u, f_i = prop.forward(eu_l, ei_d)
+    f_u, f_i = f_u.clone(), f_i.clone()
+    g_u = torch.zeros_like(eu_l)
+    gi2 = ex.partial_buffer((2, I, d), dev).zero_()
+    ego_u = torch.zeros_like(eu_l)
+    ul = torch.as_tensor(users[mine] - lo, device=dev)
+    if ul.numel() == 0:            # bpr_fused needs >= 1 triple: contribute a zero-weight dummy via batch_total only
+        loss = torch.zeros(1, device=dev)
+    else:
+        loss, _, _, ego_rows, ego_coef = bpr_fused(gl, f_u, f_i, eu_l, ei_d, ul, torch.as_tensor(pos[mine], device=dev),
+                                                   torch.as_tensor(neg[mine], device=dev), 1e-4, 0.0, None, g_u, gi2[0],
+                                                   batch_total=len(users))
+        apply_ego(gl, ego_rows, ego_coef, eu_l, ei_d, ego_u, gi2[1])
+    gi2 = ex.reduce(gi2).clone()
+    loss = all_reduce_sum(loss.clone())
+    d_u, d_i = prop.backward(g_u, gi2[0])
+    d_u, d_i = d_u + ego_u, d_i + gi2[1]
+    # single-GPU truth
+    gr = build_graph(sg.train_edges, U, I, sg.cred, variant, dev)
+    Net = CredLightGCN if order == "jacobi" else LightGCN
+    ops = (gr.operator("C"), gr.operator("A")) if order == "jacobi" else (gr.operator("A"), gr.operator("C"))
+    net = Net(U, I, d, K, *ops)
+    net.load_state_dict({"user_emb.weight": eu, "item_emb.weight": ei})
+    net = net.to(dev)
+    st = TrainStep(net, reg_weight=1e-4)
+    want = st.forward_backward(users, pos, neg)
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    errs = dict(loss=abs(float(loss.item()) - float(want.item())) / abs(float(want.item())),
+                f_i=rel(f_i, st.f_i), d_i=rel(d_i, net.item_emb.weight.grad),
+                deg_i=float((gl.deg_i != gr.deg_i).sum().item()))
+    if hi > lo:
+        errs["f_u"] = rel(f_u, st.f_u[lo:hi])
+        errs["d_u"] = rel(d_u, net.user_emb.weight.grad[lo:hi])
+    worst = torch.tensor([max(errs.values())], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    return float(worst.item()), errs, (f_u, f_i, d_u, d_i)
+
+
+# ------------------------------------------------------------------------------------------
+# bench.py --gpus N (N > 1): weak scaling, one user shard of the workload per rank (C5: ONE graph split over the ranks)
 # ------------------------------------------------------------------------------------------
 def bench_main(args, rank: int, world: int, dev: torch.device):
+    import pathlib
+    import sys
     from . import synth
-    shp = synth.SHAPES[args.workload]
-    strong = args.workload == "C5"
+    root = pathlib.Path(__file__).resolve().parents[1]
+    name = args.workload or "C4"
+    shp = synth.SHAPES[name]
+    strong = name == "C5"
+    ex_kind = os.environ.get("CGX_EXCHANGE", "p2p")
+
+    # ---- parity of this very exchange against the single-GPU path, before anything is timed ----
+    par_ex = None
+    if ex_kind == "p2p":
+        try:
+            par_ex = P2PExchange(2 * synth.SHAPES["C1"]["num_items"] * 64 + 4, dev)
+        except _lib.CgxError:
+            par_ex = None
+    parity, parity_detail, _ = parity_vs_single_gpu(rank, world, dev, "v2", "gs", exchange=par_ex)
+    if par_ex is not None:
+        par_ex.check()
+        dist.barrier()
+        par_ex.close()
+
     if strong:      # BASELINE configs[4]: THE 50M x 10M x 1B-edge graph, its users split over the ranks
         sg = synth.make_graph_device("C5", dev, num_users=shp["num_users"] // world,
                                      num_edges=shp["num_edges"] // world, seed=20240 + 1000 * (rank + 1),
                                      item_seed=20242)
-    elif args.workload == "C4":
-        sg = synth.make_graph_device(args.workload, dev, seed=20240 + 1000 * (rank + 1), item_seed=20242)
+    elif name == "C4":
+        sg = synth.make_graph_device(name, dev, seed=20240 + 1000 * (rank + 1), item_seed=20242)
     else:
-        sg = synth.make_graph(args.workload, seed=20240 + 1000 * (rank + 1), item_seed=20242)
+        sg = synth.make_graph(name, seed=20240 + 1000 * (rank + 1), item_seed=20242)
     U, I, d, K = sg.num_users, sg.num_items, shp["emb_dim"], shp["num_layers"]
     E_local = int(sg.train_edges.shape[1])
     gr = build_local_graph(sg.train_edges, U, I, sg.cred, shp["variant"], dev)
@@ -510,15 +656,16 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
     item_emb = torch.nn.init.xavier_uniform_(torch.empty(I, d, device=dev))      # identical on every rank
     torch.manual_seed(1000 + rank)
     user_emb = torch.nn.init.xavier_uniform_(torch.empty(U, d, device=dev))
-    n_eval = int(__import__("os").environ.get("CGX_BENCH_EVAL_USERS", "0"))   # per rank; 0 = no evaluation leg
+    n_eval = int(os.environ.get("CGX_BENCH_EVAL_USERS", "0"))   # per rank; 0 = no evaluation leg
     test_edges = None
     if n_eval:
         te = torch.as_tensor(sg.test_edges, device=dev)
         test_edges = te[:, te[0] < n_eval].contiguous()
         del te
     del sg
+    torch.cuda.empty_cache()
     step = ShardedTrainStep(gr, user_emb, item_emb, K, shp["order"], mix_pop=None if shp["variant"] == "cu" else 0.7,
-                            exchange=__import__("os").environ.get("CGX_EXCHANGE", "p2p"))
+                            exchange=ex_kind)
     train_users = torch.nonzero(gr.deg_u > 0).reshape(-1).cpu().numpy()
     np.random.default_rng(42 + rank).shuffle(train_users)
     nb = min(len(train_users) // args.batch, 64)
@@ -527,14 +674,14 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
     pinned = [torch.from_numpy(b).pin_memory() for b in host_batches]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    graphed = isinstance(step.ex, P2PExchange) and __import__("os").environ.get("CGX_SHARDED_GRAPH", "1") == "1"
+    graphed = isinstance(step.ex, P2PExchange) and os.environ.get("CGX_SHARDED_GRAPH", "1") == "1"
     if graphed:
         try:
             step.capture(args.batch)
         except Exception as e:          # noqa: BLE001
             graphed, step._graph = False, None
             print(f"[bench] rank {rank}: CUDA-graph capture failed ({type(e).__name__}: {e}); eager launches",
-                  file=__import__("sys").stderr)
+                  file=sys.stderr)
         flag = torch.tensor([1.0 if graphed else 0.0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if flag.item() == 0:            # every rank must take the same path
@@ -546,7 +693,6 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
         step.step(dev_batches[s % len(dev_batches)])
     torch.cuda.synchronize()
     dist.barrier()
-    launches0 = lib().cgx_launch_count()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     for s in range(args.steps):
@@ -556,9 +702,6 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
         ends[s].record()
     torch.cuda.synchronize()
     dist.barrier()
-    launches = lib().cgx_launch_count() - launches0
-    if graphed:                                  # replays do not pass through the host-side counter
-        launches = launches_per_step * args.steps
     total_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in zip(starts, ends))], device=dev)
     dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
 
@@ -571,30 +714,103 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
     torch.cuda.synchronize()
     e2e = torch.tensor([1e3 * (time.perf_counter() - t0)], device=dev)
     dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    step.check()                                 # no exchange gave up on a peer
+
+    # ---- where the step's time goes: the propagation alone (products + exchanges), and one exchange alone ----
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    prop_f, prop_b = [], []
+    g_u = torch.zeros_like(step.eu.data)
+    g_i = torch.zeros_like(step.ei.data)
+    g_u[:64] = 1e-3
+    for _ in range(3):
+        if hasattr(step.ex, "begin_step"):
+            step.ex.begin_step()
+        dist.barrier()
+        ev[0].record()
+        step.prop.forward(step.eu.data, step.ei.data)
+        ev[1].record()
+        step.prop.backward(g_u, g_i)
+        ev[2].record()
+        torch.cuda.synchronize()
+        prop_f.append(ev[0].elapsed_time(ev[1]))
+        prop_b.append(ev[1].elapsed_time(ev[2]))
+    del g_u
+    xs = []
+    buf = step.ex.partial_buffer(tuple(step.ei.shape), dev)
+    if hasattr(step.ex, "begin_step"):
+        step.ex.begin_step()
+    for _ in range(4):
+        dist.barrier()
+        buf = step.ex.partial_buffer(tuple(step.ei.shape), dev)
+        ev[0].record()
+        step.ex.reduce(buf)
+        ev[1].record()
+        torch.cuda.synchronize()
+        xs.append(ev[0].elapsed_time(ev[1]))
+    t3 = torch.tensor([min(prop_f), min(prop_b), min(xs[1:])], device=dev)
+    dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+    prop_f_ms, prop_b_ms, xchg_ms = (float(v) for v in t3.tolist())
     edges = torch.tensor([E_local], dtype=torch.int64, device=dev)
     dist.all_reduce(edges)
+    nnz_t = torch.tensor([gr.nnz], dtype=torch.int64, device=dev)
+    tu = torch.tensor([len(train_users)], dtype=torch.int64, device=dev)
+    dist.all_reduce(tu, op=dist.ReduceOp.MAX)
     if rank == 0:
+        sys.path.insert(0, str(root))
+        import bench as _bench
         ms = float(total_ms.item()) / args.steps
         e2e_ms = float(e2e.item()) / args.steps
         E = int(edges.item())
-        print(json.dumps({
+        hbm_peak, peak_src = _bench.peaks()
+        nvl_peak = 770.0          # GB/s per direction per GPU, measured peer copy (B200_PROFILING.md)
+        r = 4 * d
+        table_bytes = I * r
+        # per rank: what its own products move (gather model / compulsory) and what crosses NVLink
+        gather = _bench.gather_model_bytes(U, I, int(nnz_t.item()), d, K)
+        comp = _bench.compulsory_bytes(U, I, int(nnz_t.item()), d, K)
+        traffic, traffic_src = _bench.traffic_per_step(name)
+        prop_ms = prop_f_ms + prop_b_ms
+        n_x = 2 * K + 1
+        link_bytes = (world - 1) / world * table_bytes          # per direction, per rank, per exchange
+        steps_per_epoch = -(-int(tu.item()) // args.batch)
+        line = {
             "metric": "edges/sec (3-layer cred-weighted LightGCN fwd+bwd)", "value": E / (ms / 1e3), "unit": "edges/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": (f"C5 split over {world} GPUs: {U * world:,} users x {I:,} items, " if strong else
-                                    f"{args.workload} x {world}: ") +
-                                   f"one {U:,}-user shard per GPU ({E:,} train edges in "
-                                   f"total), {I:,} items replicated, user-sharded rows, item table all-reduced per layer",
-                       "emb_dim": d, "num_layers": K, "batch_users": args.batch * world,
-                       "step": "sample+fwd+loss+bwd+adam", "parallelism": f"user-shard x{world}",
-                       "l2": "flushed between timed steps (256 MiB write)"},
+            "config": _bench.workload_config(name, args.batch, world),
+            "train_edges": E, "users_per_rank": U, "items": I,
             "e2e": {"value": E / (e2e_ms / 1e3), "unit": "edges/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(host_batches[0].nbytes) * world, "d2h_bytes_per_step": 4 * world},
-            "gpu_launches": int(launches), "loss": loss_host,
-            "collectives_per_step": 2 * K + 1, "cuda_graph": graphed,
-            "exchange": type(step.ex).__name__,
-        }))
+                    "h2d_bytes_per_step": int(host_batches[0].nbytes) * world, "d2h_bytes_per_step": 4 * world,
+                    "api": "ShardedTrainStep.step(pinned_host_users) + loss.item() on every rank"},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "gpu_launches_note": f"{launches_per_step} kernels of libcredgcn.so per step and rank",
+            "loss": loss_host,
+            "collectives_per_step": n_x, "cuda_graph": graphed, "exchange": type(step.ex).__name__ +
+            (" (rows pushed from the SpMM epilogue + local reduce)" if getattr(step.ex, "push_enabled", lambda: False)()
+             else ""),
+            "parity_vs_1gpu": parity, "parity_vs_1gpu_detail": {k: float(v) for k, v in parity_detail.items()},
+            "roofline": {
+                "bound": "hbm + nvlink", "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
+                "propagate_ms": {"fwd": prop_f_ms, "bwd": prop_b_ms,
+                                 "note": "products + exchanges of one step, eager launches, max over ranks"},
+                "frac_dram_bytes": (traffic / (prop_ms / 1e3) / 1e9 / hbm_peak) if traffic else None,
+                "traffic_source": traffic_src,
+                "frac_gather_model": gather / (prop_ms / 1e3) / 1e9 / hbm_peak,
+                "frac_compulsory": comp / (prop_ms / 1e3) / 1e9 / hbm_peak,
+                "frac": (traffic if traffic else gather) / (prop_ms / 1e3) / 1e9 / hbm_peak,
+                "achieved": (traffic if traffic else gather) / (prop_ms / 1e3) / 1e9,
+                "nvlink": {"bytes_per_exchange_per_direction": link_bytes, "exchange_ms": xchg_ms,
+                           "achieved_gbs": link_bytes / (xchg_ms / 1e3) / 1e9, "peak_gbs": nvl_peak,
+                           "frac": link_bytes / (xchg_ms / 1e3) / 1e9 / nvl_peak,
+                           "exchanges_per_step": n_x, "exchange_share_of_step": n_x * xchg_ms / ms,
+                           "note": "one item-table exchange timed alone (reduce-scatter + all-gather over peer "
+                                   "memory), max over ranks"},
+            },
+            "steps_per_epoch": steps_per_epoch, "epoch_ms": ms * steps_per_epoch,
+            "epoch_ms_kind": f"extrapolated: {steps_per_epoch} steps x the timed mean step",
+        }
+        print(json.dumps(line))
     if n_eval:      # user-sharded full-rank evaluation of the first n_eval users of every shard (second JSON line)
         with torch.no_grad():
             f_u, f_i = step.prop.forward(step.eu.detach(), step.ei.detach())
@@ -619,4 +835,5 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
                               "recall@20": res[20]["recall"], "ndcg@20": res[20]["ndcg"],
                               "projected_seconds_all_users": sec * (U * world * 0.85) / max(n, 1)}))
     dist.barrier()
+    step.close()
     dist.destroy_process_group()

@@ -11,7 +11,8 @@
  *   - every function returns 0 on success, a negative cgx_status on failure; the message is
  *     available from cgx_last_error() (thread-local);
  *   - every pointer marked "device" is a CUDA device pointer owned by the caller; the library
- *     never frees caller memory and keeps no global mutable state (re-entrant per stream);
+ *     never frees caller memory and keeps no global mutable state besides the tuning options of
+ *     cgx_set_option (re-entrant per stream); it reads no environment variables;
  *   - scratch space is caller-provided: ask the matching *_workspace_bytes() first;
  *   - every op is asynchronous on the cudaStream_t passed as `stream` (a void* here so that the
  *     header needs no CUDA include); there are no hidden synchronisations except where a
@@ -55,6 +56,25 @@ uint64_t cgx_launch_count(void);
 /* Supported embedding widths: 16, 32, 64, 128, 256 (reference default emb_dim = 64, CU:53). */
 int cgx_emb_dim_supported(int32_t d);
 
+/* Process-wide tuning options (defaults in brackets).  None of them changes a result bit: tests force both sides.
+ * cgx_set_option stores `value` (negative = restore the default) and returns the previous one through
+ * `previous` (nullable); cgx_get_option returns -1 for an unknown option. */
+typedef enum {
+  CGX_OPT_L2_TABLE_BYTES = 0,        /* [96 MiB] gathered tables above this are treated as HBM-resident by cgx_spmm */
+  CGX_OPT_SPARSE_FIRST_ADJOINT = 1,  /* [1] cgx_propagate_bwd skips the zero rows of the loss gradient */
+  CGX_OPT_PDL = 2,                   /* [1] programmatic dependent launch between consecutive SpMMs */
+  CGX_OPT_P2P_ONESHOT_MAX = 3,       /* [2] cgx_comm_allreduce uses the one-shot form up to this many ranks */
+  CGX_OPT_P2P_TIMING = 4,            /* [0] accumulate in-kernel phase times for cgx_comm_timing */
+  CGX_OPT_P2P_TIMEOUT_MS = 5,        /* [20000] a cross-GPU barrier that waits longer gives up (cgx_comm_status) */
+  CGX_OPT_EVAL_DEBUG = 6,            /* [0] bit 0: cgx_eval_topk prints the redo-row count (synchronises) */
+  CGX_OPT_HOT_ROWS = 7,              /* [1] cgx_spmm uses the hot-row hints of cgx_csr.idx_hint when present */
+  CGX_OPT_SPMM_RING = 8,             /* [1] HBM-resident tables: gathered rows are staged through a shared-memory ring
+                                        (cp.async) instead of registers */
+  CGX_OPT_COUNT_ = 9
+} cgx_option;
+int cgx_set_option(int option, int64_t value, int64_t* previous);
+int64_t cgx_get_option(int option);
+
 /* ------------------------------------------------------------------------------------------
  * Graph build.  Replaces edges_to_user_csr (CU:259-276), build_cred_weighted_mats (CU:368-399),
  * build_message_passing_mats (V2:429-452, DA:349-403): degree vectors, the user-row CSR used by
@@ -87,6 +107,8 @@ typedef struct {
                                 mutable: at most one SpMM per cgx_csr may be in flight at a time */
   const void* work;          /* device, [n_chunks + n_rows - n_long] 16-byte work items in launch order
                                 {int64 begin; int32 len; int32 row (or perm position of a chunk's row)} */
+  const int32_t* idx_hint;   /* device, [nnz] or NULL: idx with bit 31 set where the column is a HOT row of the
+                                gathered table (cgx_hot_hints); used by cgx_spmm when that table exceeds L2 */
 } cgx_csr;
 
 #define CGX_LONG_ROW 256     /* rows above this many non-zeros are split */
@@ -141,6 +163,16 @@ int cgx_row_schedule_work(const int64_t* indptr, const int32_t* perm, int32_t n_
                           int32_t n_chunks, const int32_t* chunk_ptr, const int32_t* chunk_row, void* work,
                           void* stream);
 
+/* Hot-row hints of one row order (north_star: "staging of hot (high-degree) rows").  When the gathered table is
+ * larger than the L2 cache, cgx_spmm loads the rows of the n_hot highest-degree COLUMNS with the L2 evict_last
+ * priority and streams everything else (cold rows, ids / values, running sums, outputs) through evict_first, so
+ * that the rows most edges point at stay resident.  col_by_degree = the other row order's `perm` (columns in
+ * descending degree); n_hot is normally hot_bytes / (4 * emb_dim).  idx_hint int32[nnz] = idx | hot << 31.
+ * The hints change no result bit. */
+size_t cgx_hot_hints_workspace_bytes(int32_t n_cols);
+int cgx_hot_hints(const int32_t* idx, int64_t nnz, int32_t n_cols, const int32_t* col_by_degree, int32_t n_hot,
+                  int32_t* idx_hint, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Propagation.  Replaces torch.sparse.mm + stack().mean() (CU:420-448, V2:472-490) and their
  * autograd (CU:651, V2:862).  fp32, <= 1e-4 relative to the reference.
@@ -168,7 +200,8 @@ int cgx_row_flags(const float* X, int64_t n_rows, int32_t d, uint8_t* flags, voi
 
 /* cgx_spmm picks its thread geometry by regime: a gathered table X of more than this many bytes is treated as
  * HBM-resident (narrower groups, more rows in flight), a smaller one as L2-resident.  Default 96 MiB; a negative
- * value restores the default.  Returns the previous value.  Results do not depend on it (tests force both). */
+ * value restores the default.  Returns the previous value.  Results do not depend on it (tests force both).
+ * Same as cgx_set_option(CGX_OPT_L2_TABLE_BYTES, ...). */
 int64_t cgx_spmm_set_l2_table_bytes(int64_t bytes);
 
 size_t cgx_propagate_workspace_bytes(const cgx_csr* by_user, const cgx_csr* by_item, int32_t d);
@@ -265,7 +298,11 @@ int cgx_adam_step(float* p0, const float* g0, float* m0, float* v0, int64_t n0,
  * cgx_comm_ipc_handle -> 64-byte cudaIpcMemHandle_t to hand to the peers, cgx_comm_ipc_open on their
  * side.  cgx_comm_allreduce sums n_floats float32 at byte offset in_off of every rank's buffer, in rank
  * order (deterministic), into byte offset out_off of every rank's buffer: a two-shot pull kernel with
- * system-scope flag barriers at flag_off (>= 4 * (2 * world + 1) bytes, zero before first use).
+ * system-scope flag barriers at flag_off (>= 4 * (2 * world + 2) bytes, zero before first use).
+ * The barrier waits are bounded (CGX_OPT_P2P_TIMEOUT_MS): a rank that never arrives makes the waiting kernels
+ * give up, record an error word in the flag page and finish (with an unusable result) instead of hanging every
+ * GPU of the job; cgx_comm_status reads that word (synchronises the device; 0 = no time-out so far, else
+ * (barrier << 8 | peer rank + 1) of the first wait that expired, barrier 1 = A, 2 = B).
  * peer_bases: host array of `world` device pointers (own buffer at index rank).  epoch_dev: device counter
  * holding 1, 2, 3, ... for successive exchanges (cgx_tick it before each call), the same on all ranks.
  * ------------------------------------------------------------------------------------------ */
@@ -276,6 +313,7 @@ int cgx_comm_ipc_open(const void* handle_64, void** peer_base_out);
 int cgx_comm_ipc_close(void* peer_base);
 int cgx_comm_allreduce(int rank, int world, void* const* peer_bases, size_t in_off, size_t out_off,
                        size_t flag_off, int64_t n_floats, const uint64_t* epoch_dev, void* stream);
+int cgx_comm_status(const void* base, size_t flag_off, int world, uint32_t* error_out);
 
 /* Fused product + exchange of the user-sharded propagation.  cgx_spmm_push is cgx_spmm(Y only) whose output row r is
  * stored straight into the communication buffer of the rank that owns row r (rows_per consecutive rows per rank,
@@ -293,7 +331,7 @@ int cgx_comm_allreduce_pushed(int rank, int world, void* const* peer_bases, size
                               size_t flag_off, int64_t n_rows, int32_t d, int32_t rows_per,
                               const uint64_t* epoch_dev, void* stream);
 
-/* Diagnostics (CGX_P2P_TIMING=1 in the environment): nanoseconds accumulated inside cgx_comm_allreduce's kernel in
+/* Diagnostics (CGX_OPT_P2P_TIMING = 1): nanoseconds accumulated inside cgx_comm_allreduce's kernel in
  * {barrier A, reduce + delivery, barrier B} and the number of exchanges since the last call; out4 is a HOST array.
  * Synchronises the device.  All zeros when timing is off. */
 int cgx_comm_timing(uint64_t* out4);

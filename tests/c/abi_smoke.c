@@ -31,6 +31,17 @@ int main(void) {
       puts("l2 threshold"); ++failures;
     }
   }
+  /* tuning options: set returns the previous value, a negative value restores the default, unknown keys are errors */
+  {
+    int64_t prev = -7;
+    if (cgx_set_option(CGX_OPT_P2P_TIMEOUT_MS, 5, &prev) != CGX_OK || prev != 20000 ||
+        cgx_get_option(CGX_OPT_P2P_TIMEOUT_MS) != 5 || cgx_set_option(CGX_OPT_P2P_TIMEOUT_MS, -1, NULL) != CGX_OK ||
+        cgx_get_option(CGX_OPT_P2P_TIMEOUT_MS) != 20000 || cgx_set_option(CGX_OPT_COUNT_, 1, NULL) == CGX_OK ||
+        cgx_get_option(-1) != -1) {
+      puts("options"); ++failures;
+    }
+    if (sizeof(cgx_csr) != 112) { puts("cgx_csr layout"); ++failures; }
+  }
   printf("abi_smoke: %d failure(s)\n", failures);
   return failures;
 }

@@ -39,8 +39,10 @@ def test_version_and_dim_table():
 
 def test_struct_layout_matches_header():
     from credgcn._lib import CsrStruct
-    # int32,int32,int64, 5 pointers (indptr, idx, val_fwd, val_bwd, perm), int32,int32, 2 pointers
-    assert ctypes.sizeof(CsrStruct) == 4 + 4 + 8 + 5 * 8 + 4 + 4 + 2 * 8 + 4 + 4 + 8 + 8
+    # int32,int32,int64, 5 pointers (indptr, idx, val_fwd, val_bwd, perm), int32,int32, 2 pointers, int32,int32,
+    # 3 pointers (arrive, work, idx_hint)
+    assert ctypes.sizeof(CsrStruct) == 4 + 4 + 8 + 5 * 8 + 4 + 4 + 2 * 8 + 4 + 4 + 8 + 8 + 8
+    assert CsrStruct.work.offset == 96 and CsrStruct.idx_hint.offset == 104
     assert CsrStruct.n_huge.offset == 80 and CsrStruct.arrive.offset == 88
     assert CsrStruct.perm.offset == 48 and CsrStruct.n_long.offset == 56 and CsrStruct.chunk_ptr.offset == 64
 

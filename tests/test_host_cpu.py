@@ -11,8 +11,9 @@ ROOT = pathlib.Path(__file__).resolve().parents[1]
 
 
 def test_reference_arm_prints_the_contract_line():
-    """bench.py --impl reference runs the oracle port on the host cores and prints ONE JSON line with the keys the
-    driver reads (C1, the reference's own CPU-runnable configuration)."""
+    """bench.py --impl reference runs the reference's own scripts (oracle/_ref, staged by oracle/make_ref.py; the
+    oracle port when they did not travel) on the host cores and prints ONE JSON line with the keys the driver reads
+    (C1, the reference's own CPU-runnable configuration) -- and its `config` is the one our arm prints."""
     out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--workload", "C1", "--steps", "2",
                           "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
@@ -22,7 +23,13 @@ def test_reference_arm_prints_the_contract_line():
     assert o["impl"] == "reference" and o["unit"] == "edges/s" and o["higher_is_better"] is True
     assert o["steps"] == 2 and o["warmup"] == 1 and o["n_gpus"] == 1 and o["value"] > 0 and o["ms_per_step"] > 0
     assert o["metric"].startswith("edges/sec") and "workload" in o["config"] and o["config"]["workload"].startswith("C1")
-    assert o["cpu_baseline"]["kind"] == "port" and o["cpu_baseline"]["cores"] >= 1
+    have_ref = (ROOT / "oracle" / "_ref" / "lightgcn_cu.py").exists()
+    assert o["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and o["cpu_baseline"]["cores"] >= 1
+    sys.path.insert(0, str(ROOT))
+    import bench
+    assert o["config"] == bench.workload_config("C1", 4096, 1)          # same_config: both arms print this object
+    if have_ref:
+        assert o["cpu_baseline"]["reference_sampler_ms_per_batch"] > 0
     assert o["cpu_baseline"]["value"] == o["value"] == o["e2e"]["value"]
     assert o["e2e"]["h2d_bytes_per_step"] == 0 and o["e2e"]["d2h_bytes_per_step"] == 0
 
@@ -44,7 +51,7 @@ def test_algorithmic_bytes_reproduce_the_survey_figures():
              ((52_643, 91_599, 2_980_000, 64, 4), 13.47e9), ((10_000_000, 2_000_000, 200_000_000, 128, 3), 1358.6e9),
              ((50_000_000, 10_000_000, 1_000_000_000, 64, 3), 3444.5e9)]
     for args, want in cases:
-        assert abs(bench.algorithmic_bytes(*args) - want) / want < 2e-3, (args, bench.algorithmic_bytes(*args))
+        assert abs(bench.gather_model_bytes(*args) - want) / want < 2e-3, (args, bench.gather_model_bytes(*args))
 
 
 def test_synthetic_generator_is_seeded_and_shaped():
