@@ -246,6 +246,38 @@ __global__ void __launch_bounds__(P2P_THREADS) k_p2p_reduce_pushed(P2PPeers peer
   if (dbg && threadIdx.x == 0) dbg[2] += p2p_now() - t2;
 }
 
+// All-gather of one small block per rank (the compact loss gradient of the user-sharded step: <= 2 * batch item rows
+// per rank instead of two dense item tables).  Every rank stores its block into slot `rank` of the gather region of
+// EVERY rank (posted NVLink stores), the last CTA to finish signals the peers (the barrier-A flag slots: "rank p has
+// delivered epoch e") and waits for theirs, so the kernel completes only when all `world` blocks are local.
+__global__ void __launch_bounds__(P2P_THREADS) k_p2p_allgather(P2PPeers peers, int rank, int world,
+                                                               const float4* __restrict__ src, size_t dst_off,
+                                                               size_t flag_off, int64_t n4,
+                                                               const unsigned long long* __restrict__ epoch_dev,
+                                                               unsigned long long timeout_ns) {
+  const uint32_t epoch = uint32_t(*epoch_dev);
+  uint32_t* my_flags = reinterpret_cast<uint32_t*>(peers.base[rank] + flag_off);
+  const int64_t stride = int64_t(gridDim.x) * P2P_THREADS;
+  for (int64_t i = int64_t(blockIdx.x) * P2P_THREADS + threadIdx.x; i < n4; i += stride) {
+    const float4 v = src[i];
+    for (int p = 0; p < world; ++p)
+      reinterpret_cast<float4*>(peers.base[p] + dst_off)[int64_t(rank) * n4 + i] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(my_flags + 2 * world, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x == 0) my_flags[2 * world] = 0;   // self-resetting
+  if (threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<uint32_t*>(peers.base[threadIdx.x] + flag_off) + rank, epoch);
+    wait_flag(my_flags + threadIdx.x, epoch, timeout_ns, my_flags + 2 * world + 1, (3u << 8) | (threadIdx.x + 1));
+  }
+  __syncthreads();
+}
+
 }  // namespace cgx
 
 using namespace cgx;
@@ -332,6 +364,30 @@ extern "C" int cgx_comm_allreduce_pushed(int rank, int world, void* const* peer_
   k_p2p_reduce_pushed<<<(unsigned)blocks, P2P_THREADS, 0, stream>>>(
       peers, rank, world, stage_off, out_off, flag_off, n_rows, d / 4, rows_per,
       reinterpret_cast<const unsigned long long*>(epoch_dev), p2p_timeout_ns(), dbg);
+  CGX_LAUNCH_CHECK();
+  return CGX_OK;
+}
+
+extern "C" int cgx_comm_allgather(int rank, int world, void* const* peer_bases, const void* src, size_t dst_off,
+                                  size_t flag_off, int64_t bytes_per_rank, const uint64_t* epoch_dev, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CGX_REQUIRE(world >= 1 && world <= P2P_MAX_RANKS && rank >= 0 && rank < world && peer_bases && src, CGX_ERR_ARG,
+              "comm_allgather: bad rank/world");
+  CGX_REQUIRE(bytes_per_rank > 0 && bytes_per_rank % 16 == 0 && dst_off % 16 == 0 && flag_off % 16 == 0 &&
+                  (reinterpret_cast<uintptr_t>(src) & 15) == 0 && epoch_dev != nullptr,
+              CGX_ERR_ARG, "comm_allgather: bad sizes/offsets (16-byte granularity)");
+  P2PPeers peers;
+  for (int p = 0; p < world; ++p) {
+    CGX_REQUIRE(peer_bases[p] != nullptr, CGX_ERR_ARG, "comm_allgather: NULL peer buffer");
+    peers.base[p] = static_cast<char*>(peer_bases[p]);
+  }
+  const int64_t n4 = bytes_per_rank / 16;
+  int64_t blocks = ceil_div(n4, P2P_THREADS * 2);
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  if (blocks < 1) blocks = 1;
+  k_p2p_allgather<<<(unsigned)blocks, P2P_THREADS, 0, stream>>>(
+      peers, rank, world, static_cast<const float4*>(src), dst_off, flag_off, n4,
+      reinterpret_cast<const unsigned long long*>(epoch_dev), p2p_timeout_ns());
   CGX_LAUNCH_CHECK();
   return CGX_OK;
 }

@@ -74,6 +74,16 @@ class CollectiveExchange:
     def reduce(self, buf):
         return all_reduce_sum(buf, self.group)
 
+    def allgather(self, block: torch.Tensor) -> torch.Tensor:
+        """[n] float32 per rank -> [world, n], rank order."""
+        world = _world(self.group)
+        out = torch.empty(world, block.numel(), dtype=block.dtype, device=block.device)
+        if world > 1:
+            dist.all_gather_into_tensor(out, block.contiguous(), group=self.group)
+        else:
+            out[0] = block
+        return out
+
 
 class _RawCuda:
     def __init__(self, address, nbytes):
@@ -88,8 +98,9 @@ class P2PExchange:
 
     REGION_ALIGN = 1 << 16
 
-    def __init__(self, max_floats: int, device, group=None):
-        """Collective over `group`: EVERY rank issues the same sequence of torch.distributed calls whether or not
+    def __init__(self, max_floats: int, device, group=None, gather_floats: int = 0):
+        """max_floats: largest table exchanged; gather_floats: largest per-rank block of allgather().
+        Collective over `group`: EVERY rank issues the same sequence of torch.distributed calls whether or not
         its own CUDA calls succeed (a failure is agreed on after each phase and raised on all ranks together), so a
         rank without peer access can never leave the others waiting inside a mismatched collective."""
         import ctypes as C
@@ -98,7 +109,9 @@ class P2PExchange:
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         self.region = (4 * int(max_floats) + self.REGION_ALIGN - 1) // self.REGION_ALIGN * self.REGION_ALIGN
         self.flag_off = 4 * self.region
-        total = self.flag_off + 4096
+        self.gather_off = self.flag_off + 4096
+        self.gather_block = (4 * int(gather_floats) + 15) // 16 * 16
+        total = self.gather_off + self.world * self.gather_block + 256
         self.base = C.c_void_p()
         self.bases = (C.c_void_p * self.world)()
         self._opened = []
@@ -187,12 +200,13 @@ class P2PExchange:
 
     def push_enabled(self) -> bool:
         """Fused SpMM -> owner push + local reduce (cgx_spmm_push / cgx_comm_allreduce_pushed): the default above
-        2 ranks (4 ranks: 0.896 vs 0.975 ms/step).  At 2 ranks the one-shot pull kernel has one barrier less and
-        wins (0.793 vs 0.812 ms).  CGX_P2P_PUSH=1 / 0 forces it on / off."""
+        2 ranks (C2 shards, 4 ranks: 0.896 vs 0.975 ms/step) and for tables of 64 MB and more at any rank count (the
+        reduce-scatter half then hides under the product).  At 2 ranks and 10 MB tables the one-shot pull kernel has
+        one barrier less and wins (0.793 vs 0.812 ms).  force_push / CGX_P2P_PUSH=1 / 0 force it on / off."""
         if self.force_push is not None:
             return self.world > 1 and bool(self.force_push)
         env = os.environ.get("CGX_P2P_PUSH")
-        return self.world > 1 and (env == "1" or (env is None and self.world > 2))
+        return self.world > 1 and (env == "1" or (env is None and (self.world > 2 or self.region >= (64 << 20))))
 
     force_push = None       # True / False overrides the default choice (tests)
 
@@ -213,6 +227,20 @@ class P2PExchange:
                                                   (2 + par) * self.region, self.flag_off, n_rows, d, rows_per,
                                                   ptr(self.epoch_dev), st))
         return self._view((2 + par) * self.region, (n_rows, d))
+
+    def allgather(self, block: torch.Tensor) -> torch.Tensor:
+        """[n] float32 per rank -> [world, n] (a view of the gather region; valid until the next allgather)."""
+        nbytes = (4 * block.numel() + 15) // 16 * 16
+        if nbytes > self.gather_block:
+            raise _lib.CgxError("P2PExchange.allgather: block larger than the gather region (gather_floats)")
+        block = block.contiguous()
+        with torch.cuda.device(self.device):
+            st = stream_ptr(self.device)
+            check(lib().cgx_tick(ptr(self.epoch_dev), st))
+            check(lib().cgx_comm_allgather(self.rank, self.world, self.bases, ptr(block), self.gather_off,
+                                           self.flag_off, nbytes, ptr(self.epoch_dev), st))
+        out = self.bytes[self.gather_off: self.gather_off + self.world * nbytes].view(torch.float32)
+        return out.view(self.world, nbytes // 4)[:, : block.numel()]
 
     def reduce(self, buf):
         par = self.slot
@@ -347,21 +375,31 @@ class ShardedPropagation:
             u, i = u_new, i_new
         return acc_u, acc_i.mul_(s)
 
-    def backward(self, g_u: torch.Tensor, g_i_total: torch.Tensor):
+    def backward(self, g_u: torch.Tensor, g_i_total: torch.Tensor, seed_rows=None):
         """g_u: dL/d(final_u) rows of this shard; g_i_total: dL/d(final_i) already summed over ranks.
+        seed_rows: optional (rows int64[n], keep bool[n]) -- g_i_total is zero outside rows[keep] (distinct rows): the
+        seed is then added to each adjoint layer row by row instead of by a pass over the whole table, and in
+        Gauss-Seidel order the item result (s * g_i_total, just as sparse) is left to the caller (None).
         Returns (dL/dE0_u shard, dL/dE0_i replicated)."""
         s = 1.0 / (self.K + 1)
+
+        def add_seed(t):
+            if seed_rows is None:
+                return t.add_(g_i_total)
+            rows, keep = seed_rows
+            return t.index_add_(0, rows, g_i_total[rows] * keep[:, None])
+
         if self.order == "gs":
             bu = g_u
             for k in range(self.K):   # only the first product gathers the (row-sparse) loss gradient itself
-                bi = self._item_exchange(bu, True, tuple(g_i_total.shape), sparse=k == 0).add_(g_i_total)
+                bi = add_seed(self._item_exchange(bu, True, tuple(g_i_total.shape), sparse=k == 0))
                 _, bu = self.b.user_rows_acc(bi, True, g_u, s if k == self.K - 1 else 1.0, need_y=False)
-            return bu, g_i_total.mul(s)
+            return bu, (g_i_total.mul(s) if seed_rows is None else None)
         bu, bi = g_u, g_i_total
         for k in range(self.K):
             last = k == self.K - 1
             _, nu = self.b.user_rows_acc(bi, True, g_u, s if last else 1.0, need_y=False, **self._hint(k == 0))
-            ni = self._item_exchange(bu, True, tuple(g_i_total.shape), sparse=k == 0).add_(g_i_total)
+            ni = add_seed(self._item_exchange(bu, True, tuple(g_i_total.shape), sparse=k == 0))
             bu, bi = nu, (ni.mul_(s) if last else ni)
         return bu, bi
 
@@ -374,43 +412,61 @@ def build_local_graph(local_edges, num_local_users, num_items, cred_local, varia
 
 class ShardedTrainStep:
     """One training step over user shards: local sampling, sharded forward, fused loss on the local
-    triples (means over the GLOBAL batch), sharded backward, Adam on (local users, replicated items)."""
+    triples (means over the GLOBAL batch), sharded backward, Adam on (local users, replicated items).
+
+    Exchanges per step: K item tables forward, K backward, and ONE all-gather of the compact loss gradient -- the
+    loss touches <= 2 * batch item rows per rank, so the gradient seed dL/d(final_i), the item L2 gradient and the loss
+    value travel as (row id, coefficient, d floats) blocks of a few MB instead of two dense [I, d] tables, and every
+    rank adds the blocks in rank order (identical bits on every rank)."""
 
     def __init__(self, graph: CredGraph, user_emb: torch.Tensor, item_emb: torch.Tensor, num_layers, order,
                  lr=1e-3, reg_weight=1e-4, mix_pop=0.7, gamma=0.75, max_tries=50, seed=42, group=None,
-                 exchange: str = "p2p"):
+                 exchange: str = "p2p", max_batch: int = 4096):
         self.graph, self.group = graph, group
         self.eu = torch.nn.Parameter(user_emb.contiguous())
         self.ei = torch.nn.Parameter(item_emb.contiguous())
-        n_red = 2 * self.ei.numel() + 4
+        dev = self.ei.device
+        I, d = self.ei.shape
+        self.max_batch = int(max_batch)
         self.ex = None
         if exchange == "p2p" and _world(group) > 1:
             # peer mapping can be unavailable (no NVLink/IPC between the ranks): P2PExchange agrees on the outcome
             # over `group` and raises on ALL ranks together, which then all use the collective exchange
             try:
-                self.ex = P2PExchange(n_red, self.ei.device, group)
+                self.ex = P2PExchange((I + _world(group)) * d, dev, group,
+                                      gather_floats=self._block_floats(self.max_batch, d))
             except _lib.CgxError as e:
                 self._p2p_error = str(e)
         if self.ex is None:
             self.ex = CollectiveExchange(group)
-        graph.set_emb_dim(self.ei.shape[1])          # hot-row hints of the SpMMs for this width
+        graph.set_emb_dim(d)          # hot-row hints of the SpMMs for this width
         self.prop = ShardedPropagation(CudaBackend(graph), num_layers, order, group, self.ex)
         self.sampler = TripleSampler(graph, mix_pop, gamma, max_tries, seed)
         self.reg = float(reg_weight)
         self.eu.grad, self.ei.grad = torch.zeros_like(self.eu), torch.zeros_like(self.ei)
         self.opt = FusedAdam(self.eu, self.ei, lr=lr)
-        self.g_u = torch.empty_like(self.eu)
-        self.ego_u = torch.empty_like(self.eu)
-        self.tick = torch.zeros(1, dtype=torch.int64, device=self.ei.device)
+        self.g_u = torch.zeros_like(self.eu)
+        self.ego_u = torch.zeros_like(self.eu)
+        # dense item tables kept ZERO outside the rows of the current batch (cleared row by row after use)
+        self.gi_local = torch.empty_like(self.ei)            # bpr writes whole rows; only those rows are read back
+        self.g_i = torch.zeros_like(self.ei)                 # dL/d(final_i), summed over ranks
+        self.owner = torch.full((I + 1,), -1, dtype=torch.int64, device=dev)
+        self.tick = torch.zeros(1, dtype=torch.int64, device=dev)
         self._bufs = {}
         self._graph = None
+
+    @staticmethod
+    def _block_floats(B: int, d: int) -> int:
+        return 2 * B * (d + 2) + 4            # [2B, d] rows | 2B L2 coefficients | 2B row ids | loss (+ padding)
 
     @torch.no_grad()
     def __call__(self, users_local: torch.Tensor, batch_total: int | None = None):
         """batch_total: global batch size (default: every rank holds a batch of this size)."""
         g, dev = self.graph, self.eu.device
         B = users_local.numel()
-        B_total = int(batch_total) if batch_total is not None else B * _world(self.group)
+        world = _world(self.group)
+        B_total = int(batch_total) if batch_total is not None else B * world
+        U, (I, d) = g.num_users, self.ei.shape
         if B not in self._bufs:
             self._bufs[B] = (torch.empty(3 * B, dtype=torch.int64, device=dev), bpr_buffers(g, B, dev))
         plan, bufs = self._bufs[B]
@@ -421,25 +477,55 @@ class ShardedTrainStep:
         pos, neg = self.sampler.sample(users_local, offset=0, offset_dev=self.tick)
         bpr_plan(g, users_local, pos, neg, plan)
         f_u, f_i = self.prop.forward(self.eu.data, self.ei.data)
-        n = self.ei.numel()
-        red = self.ex.partial_buffer((2 * n + 4,), dev)        # [item seed ; item L2 gradient ; loss]
-        gi2 = red[: 2 * n].view(2, *self.ei.shape)
         self.g_u.zero_()
-        red.zero_()
         self.ego_u.zero_()
-        bufs = (red[2 * n: 2 * n + 1],) + tuple(bufs[1:])
         loss, _, _, ego_rows, ego_coef = bpr_fused(g, f_u, f_i, self.eu.data, self.ei.data, users_local, pos, neg,
-                                                   self.reg, 0.0, None, self.g_u, gi2[0], plan, bufs, B_total)
-        apply_ego(g, ego_rows, ego_coef, self.eu.data, self.ei.data, self.ego_u, gi2[1])
-        # item seed, item L2 gradient and the loss in ONE exchange; cloned because the exchange's output region is
-        # recycled two exchanges later while the seed is needed by every backward layer
-        red = self.ex.reduce(red).clone()
-        gi2 = red[: 2 * n].view(2, *self.ei.shape)
-        d_u, d_i = self.prop.backward(self.g_u, gi2[0])
+                                                   self.reg, 0.0, None, self.g_u, self.gi_local, plan, bufs, B_total)
+        # user part of the L2 gradient stays local (item entries masked out: rows >= U)
+        ego_user = torch.where(ego_rows < U, ego_rows, torch.full_like(ego_rows, -1))
+        apply_ego(g, ego_user, ego_coef, self.eu.data, self.ei.data, self.ego_u, self.gi_local)
+        # ---- compact item part: the plan is sorted by row, users first, so item runs live in positions [B, 3B) ----
+        er = ego_rows[B:]
+        valid = er >= U
+        rows = torch.where(valid, er - U, torch.zeros_like(er)).to(torch.int64)
+        block = torch.empty(self._block_floats(B, d), dtype=torch.float32, device=dev)
+        block[: 2 * B * d].view(2 * B, d).copy_(self.gi_local[rows] * valid[:, None])
+        block[2 * B * d: 2 * B * (d + 1)] = ego_coef[B:] * valid
+        block[2 * B * (d + 1): 2 * B * (d + 2)] = torch.where(valid, rows, torch.full_like(rows, -1)).to(
+            torch.int32).view(torch.float32)
+        block[2 * B * (d + 2):] = 0.0
+        block[2 * B * (d + 2)] = loss[0]
+        blocks = self.ex.allgather(block)                                   # [world, n], rank order
+        vals = blocks[:, : 2 * B * d].reshape(world, 2 * B, d)
+        coef = blocks[:, 2 * B * d: 2 * B * (d + 1)]
+        rid = blocks[:, 2 * B * (d + 1): 2 * B * (d + 2)].contiguous().view(torch.int32).to(torch.int64)
+        ok = rid >= 0
+        rows_all = torch.where(ok, rid, torch.full_like(rid, I))            # invalid slots -> the dummy row I
+        total_loss = blocks[:, 2 * B * (d + 2)].sum().reshape(1)
+        for r in range(world):                                              # rank order: same bits on every rank
+            self.g_i.index_add_(0, rows_all[r].clamp(max=I - 1), vals[r] * ok[r][:, None])
+        flat = rows_all.reshape(-1)
+        ar = torch.arange(flat.numel(), device=dev)
+        self.owner.scatter_(0, flat, ar)                                    # one representative per distinct row
+        keep = (self.owner[flat] == ar) & ok.reshape(-1)
+        flat_c = flat.clamp(max=I - 1)
+        d_u, d_i = self.prop.backward(self.g_u, self.g_i, seed_rows=(flat_c, keep))
         self.eu.grad.copy_(d_u.add_(self.ego_u))
-        self.ei.grad.copy_(d_i.add_(gi2[1]))
+        # item gradient: in Gauss-Seidel order it is s * seed + L2 term, non-zero on the batch's rows only
+        if d_i is None:
+            s = 1.0 / (self.prop.K + 1)
+            self.ei.grad.index_add_(0, flat_c, self.g_i[flat_c] * (keep[:, None] * s))
+        else:
+            self.ei.grad.copy_(d_i)
+        for r in range(world):
+            rr = rows_all[r].clamp(max=I - 1)
+            self.ei.grad.index_add_(0, rr, self.ei.data[rr] * (coef[r] * ok[r])[:, None])
         self.opt.step()
-        return red[2 * n: 2 * n + 1]
+        # restore the all-zero invariant of the dense item tables, row by row
+        self.g_i[flat_c] = 0.0
+        if d_i is None:
+            self.ei.grad[flat_c] = 0.0
+        return total_loss
 
     def capture(self, batch: int):
         """Record the whole sharded step as one CUDA graph.  Only with the peer-memory exchange: every launch

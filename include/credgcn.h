@@ -314,6 +314,12 @@ int cgx_comm_ipc_close(void* peer_base);
 int cgx_comm_allreduce(int rank, int world, void* const* peer_bases, size_t in_off, size_t out_off,
                        size_t flag_off, int64_t n_floats, const uint64_t* epoch_dev, void* stream);
 int cgx_comm_status(const void* base, size_t flag_off, int world, uint32_t* error_out);
+/* All-gather of one block of bytes_per_rank bytes (16-byte granularity) per rank: block `rank` is read from the
+ * local device pointer src and lands at byte offset dst_off + rank * bytes_per_rank of EVERY rank's buffer; returns
+ * when all `world` blocks are local.  One epoch tick like the all-reduces.  Used for the compact loss gradient of the
+ * user-sharded step (<= 2 * batch item rows per rank instead of two dense item tables). */
+int cgx_comm_allgather(int rank, int world, void* const* peer_bases, const void* src, size_t dst_off,
+                       size_t flag_off, int64_t bytes_per_rank, const uint64_t* epoch_dev, void* stream);
 
 /* Fused product + exchange of the user-sharded propagation.  cgx_spmm_push is cgx_spmm(Y only) whose output row r is
  * stored straight into the communication buffer of the rank that owns row r (rows_per consecutive rows per rank,
