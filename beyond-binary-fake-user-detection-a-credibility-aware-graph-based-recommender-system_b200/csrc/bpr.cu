@@ -385,6 +385,28 @@ __global__ void __launch_bounds__(BP_THREADS) k_bpr_combine(BprArgs a, int entry
   }
 }
 
+// Row bookkeeping of the dense gradient tables g_u / g_i, driven by ego_rows (the head of every distinct row of the
+// batch): MARK sets the row flags the adjoint propagation reads (instead of scanning 4 (U + I) d bytes for
+// non-zero rows), CLEAR zeroes the rows -- and their flags -- after use, so that the tables are all-zero again
+// without a fill of the whole allocation.
+template <bool CLEAR>
+__global__ void __launch_bounds__(BP_THREADS) k_bpr_rows(const int32_t* __restrict__ ego_rows, int64_t n, int32_t U,
+                                                         int32_t row4, float4* __restrict__ g_u,
+                                                         float4* __restrict__ g_i, uint8_t* __restrict__ nz_u,
+                                                         uint8_t* __restrict__ nz_i) {
+  const int64_t k = blockIdx.x;                       // one CTA per plan entry
+  if (k >= n) return;
+  const int32_t row = ego_rows[k];
+  if (row < 0) return;
+  const bool user = row < U;
+  const int64_t r = user ? row : row - U;
+  if (threadIdx.x == 0) (user ? nz_u : nz_i)[r] = CLEAR ? 0 : 1;
+  if (CLEAR) {
+    float4* dst = (user ? g_u : g_i) + r * row4;
+    for (int p = threadIdx.x; p < row4; p += blockDim.x) dst[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
 // deterministic sum of B terms by one CTA (fixed tree); NaN if any index was out of range
 __global__ void __launch_bounds__(1024) k_sum_terms(const float* __restrict__ terms, int64_t n,
                                                     const unsigned long long* __restrict__ bad,
@@ -539,6 +561,27 @@ extern "C" int cgx_bpr_fwd_bwd(const int64_t* users, const int64_t* pos, const i
       set_error("bpr: emb_dim %d unsupported (16, 32, 64, 128, 256)", d);
       return CGX_ERR_UNSUPPORTED;
   }
+}
+
+extern "C" int cgx_bpr_mark_rows(const int32_t* ego_rows, int64_t n_entries, int32_t U, uint8_t* nz_u, uint8_t* nz_i,
+                                 void* stream_) {
+  CGX_REQUIRE(ego_rows && nz_u && nz_i && n_entries > 0 && n_entries < (int64_t(1) << 31), CGX_ERR_ARG,
+              "bpr_mark_rows: bad argument");
+  k_bpr_rows<false><<<(unsigned)n_entries, 32, 0, static_cast<cudaStream_t>(stream_)>>>(ego_rows, n_entries, U, 0,
+                                                                                        nullptr, nullptr, nz_u, nz_i);
+  CGX_LAUNCH_CHECK();
+  return CGX_OK;
+}
+
+extern "C" int cgx_bpr_clear_rows(const int32_t* ego_rows, int64_t n_entries, int32_t U, int32_t d, float* g_u,
+                                  float* g_i, uint8_t* nz_u, uint8_t* nz_i, void* stream_) {
+  CGX_REQUIRE(ego_rows && g_u && g_i && nz_u && nz_i && n_entries > 0 && n_entries < (int64_t(1) << 31) && d > 0 &&
+                  d % 4 == 0,
+              CGX_ERR_ARG, "bpr_clear_rows: bad argument");
+  k_bpr_rows<true><<<(unsigned)n_entries, 64, 0, static_cast<cudaStream_t>(stream_)>>>(
+      ego_rows, n_entries, U, d / 4, reinterpret_cast<float4*>(g_u), reinterpret_cast<float4*>(g_i), nz_u, nz_i);
+  CGX_LAUNCH_CHECK();
+  return CGX_OK;
 }
 
 extern "C" int cgx_bpr_apply_ego(const int32_t* ego_rows, const float* ego_coef, int64_t n_entries, int32_t U,

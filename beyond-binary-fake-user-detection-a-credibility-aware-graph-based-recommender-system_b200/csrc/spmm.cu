@@ -840,10 +840,28 @@ extern "C" int cgx_propagate_fwd(const cgx_csr* by_user, const cgx_csr* by_item,
   return CGX_OK;
 }
 
+// d_e0_i = s * g_i where only flagged rows of g_i are non-zero: zero fill + the flagged rows
+__global__ void k_scale_rows(const float4* __restrict__ in, const uint8_t* __restrict__ nz, float4* __restrict__ out,
+                             int64_t n_rows, int32_t row4, float s) {
+  const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) / 32;
+  if (r >= n_rows || __ldg(nz + r) == 0) return;
+  for (int p = threadIdx.x & 31; p < row4; p += 32) out[r * row4 + p] = scale4(in[r * row4 + p], s);
+}
+
 extern "C" int cgx_propagate_bwd(const cgx_csr* by_user, const cgx_csr* by_item, int order, int32_t K, int32_t d,
                                  const float* g_u, const float* g_i, float* d_e0_u, float* d_e0_i,
                                  void* workspace, size_t workspace_bytes, void* stream_) {
+  return cgx_propagate_bwd_flagged(by_user, by_item, order, K, d, g_u, g_i, nullptr, nullptr, d_e0_u, d_e0_i, workspace,
+                                   workspace_bytes, stream_);
+}
+
+extern "C" int cgx_propagate_bwd_flagged(const cgx_csr* by_user, const cgx_csr* by_item, int order, int32_t K,
+                                         int32_t d, const float* g_u, const float* g_i, const uint8_t* g_u_rows,
+                                         const uint8_t* g_i_rows, float* d_e0_u, float* d_e0_i, void* workspace,
+                                         size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CGX_REQUIRE((g_u_rows == nullptr) == (g_i_rows == nullptr), CGX_ERR_ARG,
+              "propagate_bwd_flagged: pass both row-flag arrays or neither");
   CGX_REQUIRE(by_user && by_item && g_u && g_i && d_e0_u && d_e0_i, CGX_ERR_ARG, "propagate_bwd: NULL pointer");
   CGX_REQUIRE(K >= 1, CGX_ERR_ARG, "propagate_bwd: num_layers must be >= 1");
   CGX_REQUIRE(order == CGX_ORDER_JACOBI || order == CGX_ORDER_GS, CGX_ERR_ARG, "propagate_bwd: bad order");
@@ -861,9 +879,10 @@ extern "C" int cgx_propagate_bwd(const cgx_csr* by_user, const cgx_csr* by_item,
   // <= 2 * batch items): the products that gather g_u / g_i directly skip the zero rows (row flags, 1 byte per
   // row), and every product's ACC_IN -- the gradient seed again -- is only read where its flag is set.  After one
   // product the adjoint itself is dense.  CGX_OPT_SPARSE_FIRST_ADJOINT = 0 switches both off.
-  const bool sparse = option(CGX_OPT_SPARSE_FIRST_ADJOINT) != 0;
-  uint8_t* nz_u = ws.take<uint8_t>(U);
-  uint8_t* nz_i = ws.take<uint8_t>(I);
+  const bool given = g_u_rows != nullptr;                 // the caller already knows the non-zero rows
+  const bool sparse = given || option(CGX_OPT_SPARSE_FIRST_ADJOINT) != 0;
+  uint8_t* nz_u = given ? const_cast<uint8_t*>(g_u_rows) : ws.take<uint8_t>(U);
+  uint8_t* nz_i = given ? const_cast<uint8_t*>(g_i_rows) : ws.take<uint8_t>(I);
   CGX_REQUIRE(ws.ok, CGX_ERR_WORKSPACE, "propagate_bwd: workspace too small");
   // Work with the unscaled adjoints bu' = bu / s, bi' = bi / s (the recurrences are linear):
   //   Jacobi: (bu', bi') <- (g_u + C^T bi', g_i + A^T bu');  Gauss-Seidel: bi' = g_i + A^T bu'; bu' = g_u + C^T bi'
@@ -871,7 +890,7 @@ extern "C" int cgx_propagate_bwd(const cgx_csr* by_user, const cgx_csr* by_item,
   if (order == CGX_ORDER_JACOBI) {
     const float* bu = g_u;
     const float* bi = g_i;
-    if (sparse) {
+    if (sparse && !given) {
       CGX_TRY(row_flags(g_u, U, d, nz_u, stream));
       CGX_TRY(row_flags(g_i, I, d, nz_i, stream));
     }
@@ -891,7 +910,7 @@ extern "C" int cgx_propagate_bwd(const cgx_csr* by_user, const cgx_csr* by_item,
     }
   } else {
     const float* bu = g_u;
-    if (sparse) {
+    if (sparse && !given) {
       CGX_TRY(row_flags(g_u, U, d, nz_u, stream));
       CGX_TRY(row_flags(g_i, I, d, nz_i, stream));
     }
@@ -907,9 +926,18 @@ extern "C" int cgx_propagate_bwd(const cgx_csr* by_user, const cgx_csr* by_item,
       bu = nu;
     }
     const int64_t n4 = I * d / 4;
-    k_scale<<<(unsigned)ceil_div(n4, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(g_i),
-                                                             reinterpret_cast<float4*>(d_e0_i), n4, s);
-    CGX_LAUNCH_CHECK();
+    if (given) {   // d_e0_i = s * g_i is as row-sparse as g_i: zero fill + the flagged rows (half the traffic)
+      CGX_CUDA(cudaMemsetAsync(d_e0_i, 0, size_t(I) * d * 4, stream));
+      if (I > 0) {
+        k_scale_rows<<<(unsigned)ceil_div(I * 32, 256), 256, 0, stream>>>(
+            reinterpret_cast<const float4*>(g_i), nz_i, reinterpret_cast<float4*>(d_e0_i), I, d / 4, s);
+        CGX_LAUNCH_CHECK();
+      }
+    } else {
+      k_scale<<<(unsigned)ceil_div(n4, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(g_i),
+                                                               reinterpret_cast<float4*>(d_e0_i), n4, s);
+      CGX_LAUNCH_CHECK();
+    }
   }
   return CGX_OK;
 }

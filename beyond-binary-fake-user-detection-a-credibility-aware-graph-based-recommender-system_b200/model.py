@@ -357,7 +357,12 @@ class TrainStep:
         self.pop = None if pop is None else torch.as_tensor(pop, dtype=torch.float32, device=dev).contiguous()
         eu, ei = model.user_emb.weight, model.item_emb.weight
         self.f_u, self.f_i = torch.empty_like(eu), torch.empty_like(ei)
-        self.g_u, self.g_i = torch.empty_like(eu), torch.empty_like(ei)
+        # dL/d(final tables): dense, but kept ALL-ZERO between steps -- the loss writes <= 3 * batch rows, flags them
+        # for the adjoint (cgx_bpr_mark_rows) and the rows are zeroed again after use (cgx_bpr_clear_rows): no fill of
+        # (U + I) d floats and no scan for non-zero rows per step
+        self.g_u, self.g_i = torch.zeros_like(eu), torch.zeros_like(ei)
+        self.nz_u = torch.zeros(eu.shape[0], dtype=torch.uint8, device=dev)
+        self.nz_i = torch.zeros(ei.shape[0], dtype=torch.uint8, device=dev)
         eu.grad, ei.grad = torch.empty_like(eu), torch.empty_like(ei)
         self.opt = optimizer or FusedAdam(eu, ei, lr=lr)
         self.sampler = sampler
@@ -391,11 +396,9 @@ class TrainStep:
         with torch.cuda.device(dev):
             main = torch.cuda.current_stream(dev)
             self._mark(marks)
-            self.side.wait_stream(main)                 # indices (and last step's use of g_u/g_i) are ready
+            self.side.wait_stream(main)                 # the indices are ready
             with torch.cuda.stream(self.side):
-                bpr_plan(g, users, pos, neg, plan)
-                self.g_u.zero_()
-                self.g_i.zero_()
+                bpr_plan(g, users, pos, neg, plan)      # scatter plan: beside the forward
             st = stream_ptr(dev)
             check(lib().cgx_propagate_fwd(g.by_user.ref(), g.by_item.ref(), order, K, d, ptr(eu), ptr(ei),
                                           ptr(self.f_u), ptr(self.f_i), ptr(ws), ws.numel(), st))
@@ -403,11 +406,16 @@ class TrainStep:
             main.wait_stream(self.side)
             loss, _, _, ego_rows, ego_coef = bpr_fused(g, self.f_u, self.f_i, eu, ei, users, pos, neg, self.reg,
                                                        self.fair, self.pop, self.g_u, self.g_i, plan, bufs)
+            n_ent = ego_rows.numel()
+            check(lib().cgx_bpr_mark_rows(ptr(ego_rows), n_ent, g.num_users, ptr(self.nz_u), ptr(self.nz_i), st))
             self._mark(marks)
-            check(lib().cgx_propagate_bwd(g.by_user.ref(), g.by_item.ref(), order, K, d, ptr(self.g_u),
-                                          ptr(self.g_i), ptr(eu.grad), ptr(ei.grad), ptr(ws), ws.numel(), st))
+            check(lib().cgx_propagate_bwd_flagged(g.by_user.ref(), g.by_item.ref(), order, K, d, ptr(self.g_u),
+                                                  ptr(self.g_i), ptr(self.nz_u), ptr(self.nz_i), ptr(eu.grad),
+                                                  ptr(ei.grad), ptr(ws), ws.numel(), st))
             self._mark(marks)
             apply_ego(g, ego_rows, ego_coef, eu, ei, eu.grad, ei.grad)
+            check(lib().cgx_bpr_clear_rows(ptr(ego_rows), n_ent, g.num_users, d, ptr(self.g_u), ptr(self.g_i),
+                                           ptr(self.nz_u), ptr(self.nz_i), st))
         if self.phase_events is not None:
             self.phase_events.append(marks)
         return loss

@@ -68,8 +68,8 @@ typedef enum {
   CGX_OPT_P2P_TIMEOUT_MS = 5,        /* [20000] a cross-GPU barrier that waits longer gives up (cgx_comm_status) */
   CGX_OPT_EVAL_DEBUG = 6,            /* [0] bit 0: cgx_eval_topk prints the redo-row count (synchronises) */
   CGX_OPT_HOT_ROWS = 7,              /* [1] cgx_spmm uses the hot-row hints of cgx_csr.idx_hint when present */
-  CGX_OPT_SPMM_RING = 8,             /* [1] HBM-resident tables: gathered rows are staged through a shared-memory ring
-                                        (cp.async) instead of registers */
+  CGX_OPT_SPMM_RING = 8,             /* [0] HBM-resident tables: stage the gathered rows through a shared-memory ring
+                                        (cp.async) instead of registers -- same bits; measured equal on C4 */
   CGX_OPT_COUNT_ = 9
 } cgx_option;
 int cgx_set_option(int option, int64_t value, int64_t* previous);
@@ -217,6 +217,13 @@ int cgx_propagate_fwd(const cgx_csr* by_user, const cgx_csr* by_item, int order,
 int cgx_propagate_bwd(const cgx_csr* by_user, const cgx_csr* by_item, int order, int32_t num_layers,
                       int32_t d, const float* g_u, const float* g_i, float* d_e0_u, float* d_e0_i,
                       void* workspace, size_t workspace_bytes, void* stream);
+/* The same when the caller already knows which rows of g_u / g_i are non-zero (uint8 flags as cgx_row_flags writes
+ * them; every unflagged row MUST be all zero): saves the scan of both tables.  cgx_bpr_mark_rows provides the flags
+ * for the gradient of cgx_bpr_fwd_bwd.  Pass both arrays or neither (NULL, NULL = cgx_propagate_bwd). */
+int cgx_propagate_bwd_flagged(const cgx_csr* by_user, const cgx_csr* by_item, int order, int32_t num_layers,
+                              int32_t d, const float* g_u, const float* g_i, const uint8_t* g_u_rows,
+                              const uint8_t* g_i_rows, float* d_e0_u, float* d_e0_i, void* workspace,
+                              size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * BPR + L2 (+ fairness) on a batch of (user, pos, neg) triples.  Replaces score / l2_reg / the loss
@@ -252,6 +259,15 @@ int cgx_bpr_fwd_bwd(const int64_t* users, const int64_t* pos, const int64_t* neg
 int cgx_bpr_apply_ego(const int32_t* ego_rows, const float* ego_coef, int64_t n_entries,
                       int32_t num_users, int32_t d, const float* e0_u, const float* e0_i,
                       float* d_e0_u, float* d_e0_i, void* stream);
+/* Row bookkeeping for callers that keep g_u / g_i all-zero between steps instead of zero-filling (U + I) d floats
+ * per step: ego_rows (output of cgx_bpr_fwd_bwd) names every distinct row the batch wrote.
+ *   cgx_bpr_mark_rows   nz_u[row] = 1 / nz_i[row] = 1 for those rows (flags for cgx_propagate_bwd_flagged;
+ *                       uint8[U] / uint8[I], zero before the first step)
+ *   cgx_bpr_clear_rows  zeroes those rows of g_u / g_i and their flags again (call after the backward) */
+int cgx_bpr_mark_rows(const int32_t* ego_rows, int64_t n_entries, int32_t num_users, uint8_t* nz_u, uint8_t* nz_i,
+                      void* stream);
+int cgx_bpr_clear_rows(const int32_t* ego_rows, int64_t n_entries, int32_t num_users, int32_t d, float* g_u,
+                       float* g_i, uint8_t* nz_u, uint8_t* nz_i, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Samplers.  Replace sample_pos_item / sample_neg_item (CU:288-299) and
