@@ -739,6 +739,13 @@ extern "C" int cgx_spmm_sparse_rows(const cgx_csr* m, int use_bwd_values, int32_
                        static_cast<cudaStream_t>(stream), x_row_nonzero);
 }
 
+extern "C" int cgx_spmm_ex(const cgx_csr* m, int use_bwd_values, int32_t d, const float* X, const uint8_t* x_row_nonzero,
+                           float* Y, const float* ACC_IN, const uint8_t* acc_row_nonzero, float* ACC_OUT,
+                           float acc_scale, void* workspace, size_t workspace_bytes, void* stream) {
+  return spmm_dispatch(m, use_bwd_values, d, X, Y, ACC_IN, ACC_OUT, acc_scale, workspace, workspace_bytes,
+                       static_cast<cudaStream_t>(stream), x_row_nonzero, SpmmPush{0ull, 0, 0}, acc_row_nonzero);
+}
+
 extern "C" int64_t cgx_spmm_set_l2_table_bytes(int64_t bytes) {
   int64_t old = 0;
   cgx_set_option(CGX_OPT_L2_TABLE_BYTES, bytes, &old);

@@ -267,13 +267,25 @@ class BackendBase:
 class CudaBackend(BackendBase):
     """The two products of one shard, on libcredgcn.so."""
     supports_sparse_rows = True
+    supports_row_flags = True
 
     def __init__(self, graph: CredGraph):
         self.graph = graph
         self._ws = {}
 
-    def _spmm(self, csr, x, bwd, y=None, acc_in=None, acc_out=None, scale=1.0, sparse=False):
-        """sparse=True: x is a loss gradient (rows mostly zero) -- flag its rows and skip the zero ones."""
+    def _flags_of(self, x):
+        """Row flags of x computed on device (a scan of the whole table)."""
+        fkey = ("flags", x.shape[0])
+        if fkey not in self._ws:
+            self._ws[fkey] = torch.empty(x.shape[0], dtype=torch.uint8, device=x.device)
+        flags = self._ws[fkey]
+        check(lib().cgx_row_flags(ptr(x), x.shape[0], x.shape[1], ptr(flags), stream_ptr(x.device)))
+        return flags
+
+    def _spmm(self, csr, x, bwd, y=None, acc_in=None, acc_out=None, scale=1.0, sparse=False, x_flags=None,
+              acc_flags=None):
+        """sparse=True: x is a loss gradient (rows mostly zero) -- skip its zero rows, using x_flags (uint8 per row)
+        when the caller has them, else flags scanned from x.  acc_flags: the same promise for acc_in."""
         x = x.contiguous()
         d = x.shape[1]
         if y is None and acc_out is None:
@@ -283,25 +295,18 @@ class CudaBackend(BackendBase):
             self._ws[key] = workspace(lib().cgx_spmm_workspace_bytes(csr.ref(), d), x.device)
         ws = self._ws[key]
         with torch.cuda.device(x.device):
+            flags = None
             if sparse:
-                fkey = ("flags", x.shape[0])
-                if fkey not in self._ws:
-                    self._ws[fkey] = torch.empty(x.shape[0], dtype=torch.uint8, device=x.device)
-                flags = self._ws[fkey]
-                check(lib().cgx_row_flags(ptr(x), x.shape[0], d, ptr(flags), stream_ptr(x.device)))
-                check(lib().cgx_spmm_sparse_rows(csr.ref(), int(bwd), d, ptr(x), ptr(flags), ptr(y), ptr(acc_in),
-                                                 ptr(acc_out), float(scale), ptr(ws), ws.numel(),
-                                                 stream_ptr(x.device)))
-            else:
-                check(lib().cgx_spmm(csr.ref(), int(bwd), d, ptr(x), ptr(y), ptr(acc_in), ptr(acc_out), float(scale),
-                                     ptr(ws), ws.numel(), stream_ptr(x.device)))
+                flags = x_flags if x_flags is not None else self._flags_of(x)
+            check(lib().cgx_spmm_ex(csr.ref(), int(bwd), d, ptr(x), ptr(flags), ptr(y), ptr(acc_in), ptr(acc_flags),
+                                    ptr(acc_out), float(scale), ptr(ws), ws.numel(), stream_ptr(x.device)))
         return y if y is not None else acc_out
 
-    def item_rows(self, x_u, bwd=False, out=None, sparse=False):
+    def item_rows(self, x_u, bwd=False, out=None, sparse=False, x_flags=None):
         """Partial [I, d]: C x_u (bwd: A^T x_u) summed over THIS shard's users (written into `out` if given)."""
-        return self._spmm(self.graph.by_item, x_u, bwd, y=out, sparse=sparse)
+        return self._spmm(self.graph.by_item, x_u, bwd, y=out, sparse=sparse, x_flags=x_flags)
 
-    def item_rows_push(self, x_u, bwd, stage_off, rank, world, rows_per, sparse=False):
+    def item_rows_push(self, x_u, bwd, stage_off, rank, world, rows_per, sparse=False, x_flags=None):
         """item_rows whose output rows go straight to their owner rank's staging area (cgx_spmm_push)."""
         csr = self.graph.by_item
         x = x_u.contiguous()
@@ -313,11 +318,7 @@ class CudaBackend(BackendBase):
         with torch.cuda.device(x.device):
             flags = None
             if sparse:
-                fkey = ("flags", x.shape[0])
-                if fkey not in self._ws:
-                    self._ws[fkey] = torch.empty(x.shape[0], dtype=torch.uint8, device=x.device)
-                flags = self._ws[fkey]
-                check(lib().cgx_row_flags(ptr(x), x.shape[0], d, ptr(flags), stream_ptr(x.device)))
+                flags = x_flags if x_flags is not None else self._flags_of(x)
             check(lib().cgx_spmm_push(csr.ref(), int(bwd), d, ptr(x), None if flags is None else ptr(flags), stage_off,
                                       rank, world, rows_per, ptr(ws), ws.numel(), stream_ptr(x.device)))
 
@@ -325,12 +326,15 @@ class CudaBackend(BackendBase):
         """[U_local, d]: A x_i (bwd: C^T x_i) for this shard's users."""
         return self._spmm(self.graph.by_user, x_i, bwd)
 
-    def user_rows_acc(self, x_i, bwd, acc_in, scale, need_y=True, sparse=False):
-        """Same product with the running sum / gradient seed fused into the SpMM epilogue."""
+    def user_rows_acc(self, x_i, bwd, acc_in, scale, need_y=True, sparse=False, acc_flags=None, acc_out=None):
+        """Same product with the running sum / gradient seed fused into the SpMM epilogue (acc_out: where to write
+        the sum; acc_flags: row flags of acc_in, whose unflagged rows are then not read)."""
         csr = self.graph.by_user
         y = torch.empty(csr.n_rows, x_i.shape[1], dtype=torch.float32, device=x_i.device) if need_y else None
-        acc = torch.empty(csr.n_rows, x_i.shape[1], dtype=torch.float32, device=x_i.device)
-        self._spmm(csr, x_i, bwd, y=y, acc_in=acc_in.contiguous(), acc_out=acc, scale=scale, sparse=sparse)
+        acc = acc_out if acc_out is not None else torch.empty(csr.n_rows, x_i.shape[1], dtype=torch.float32,
+                                                              device=x_i.device)
+        self._spmm(csr, x_i, bwd, y=y, acc_in=acc_in.contiguous(), acc_out=acc, scale=scale, sparse=sparse,
+                   acc_flags=acc_flags)
         return y, acc
 
 
@@ -344,19 +348,23 @@ class ShardedPropagation:
         self.b, self.K, self.order, self.group = backend, int(num_layers), order, group
         self.ex = exchange or CollectiveExchange(group)
 
+    def _flags_ok(self):
+        return getattr(self.b, "supports_row_flags", False)
+
     def _hint(self, sparse):
         """`sparse=True` keyword for backends that can skip zero rows of the input (an optimisation hint)."""
         return {"sparse": True} if sparse and getattr(self.b, "supports_sparse_rows", False) else {}
 
-    def _item_exchange(self, x_u, bwd, shape, sparse=False):
+    def _item_exchange(self, x_u, bwd, shape, sparse=False, x_flags=None):
         """Partial item table of this shard -> whole item table (one exchange).  sparse: x_u is the loss
-        gradient itself (rows mostly zero)."""
+        gradient itself (rows mostly zero; x_flags = its row flags when the caller has them)."""
+        fl = {"x_flags": x_flags} if (sparse and x_flags is not None and self._flags_ok()) else {}
         if hasattr(self.b, "item_rows_push") and getattr(self.ex, "push_enabled", lambda: False)():
             return self.ex.exchange_pushed(
                 shape, lambda off, rank, world, rows_per: self.b.item_rows_push(x_u, bwd, off, rank, world, rows_per,
-                                                                              sparse))
+                                                                              sparse, **fl))
         buf = self.ex.partial_buffer(shape, x_u.device)
-        res = self.b.item_rows(x_u, bwd, out=buf, **self._hint(sparse))
+        res = self.b.item_rows(x_u, bwd, out=buf, **self._hint(sparse), **fl)
         if res is not buf:                      # backends without an `out` argument return a fresh tensor
             buf.copy_(res)
         return self.ex.reduce(buf)
@@ -375,13 +383,19 @@ class ShardedPropagation:
             u, i = u_new, i_new
         return acc_u, acc_i.mul_(s)
 
-    def backward(self, g_u: torch.Tensor, g_i_total: torch.Tensor, seed_rows=None):
+    def backward(self, g_u: torch.Tensor, g_i_total: torch.Tensor, seed_rows=None, g_u_flags=None, out_u=None):
         """g_u: dL/d(final_u) rows of this shard; g_i_total: dL/d(final_i) already summed over ranks.
         seed_rows: optional (rows int64[n], keep bool[n]) -- g_i_total is zero outside rows[keep] (distinct rows): the
         seed is then added to each adjoint layer row by row instead of by a pass over the whole table, and in
         Gauss-Seidel order the item result (s * g_i_total, just as sparse) is left to the caller (None).
+        g_u_flags: optional uint8 row flags of g_u (unflagged rows are all zero and are then never read);
+        out_u: optional buffer for dL/dE0_u.
         Returns (dL/dE0_u shard, dL/dE0_i replicated)."""
         s = 1.0 / (self.K + 1)
+        fl = {"acc_flags": g_u_flags} if (g_u_flags is not None and self._flags_ok()) else {}
+
+        def last_out(last):
+            return {"acc_out": out_u} if (last and out_u is not None and self._flags_ok()) else {}
 
         def add_seed(t):
             if seed_rows is None:
@@ -392,14 +406,17 @@ class ShardedPropagation:
         if self.order == "gs":
             bu = g_u
             for k in range(self.K):   # only the first product gathers the (row-sparse) loss gradient itself
-                bi = add_seed(self._item_exchange(bu, True, tuple(g_i_total.shape), sparse=k == 0))
-                _, bu = self.b.user_rows_acc(bi, True, g_u, s if k == self.K - 1 else 1.0, need_y=False)
+                bi = add_seed(self._item_exchange(bu, True, tuple(g_i_total.shape), sparse=k == 0,
+                                                  x_flags=g_u_flags))
+                _, bu = self.b.user_rows_acc(bi, True, g_u, s if k == self.K - 1 else 1.0, need_y=False, **fl,
+                                             **last_out(k == self.K - 1))
             return bu, (g_i_total.mul(s) if seed_rows is None else None)
         bu, bi = g_u, g_i_total
         for k in range(self.K):
             last = k == self.K - 1
-            _, nu = self.b.user_rows_acc(bi, True, g_u, s if last else 1.0, need_y=False, **self._hint(k == 0))
-            ni = add_seed(self._item_exchange(bu, True, tuple(g_i_total.shape), sparse=k == 0))
+            _, nu = self.b.user_rows_acc(bi, True, g_u, s if last else 1.0, need_y=False, **self._hint(k == 0), **fl,
+                                         **last_out(last))
+            ni = add_seed(self._item_exchange(bu, True, tuple(g_i_total.shape), sparse=k == 0, x_flags=g_u_flags))
             bu, bi = nu, (ni.mul_(s) if last else ni)
         return bu, bi
 
@@ -429,7 +446,9 @@ class ShardedTrainStep:
         I, d = self.ei.shape
         self.max_batch = int(max_batch)
         self.ex = None
-        if exchange == "p2p" and _world(group) > 1:
+        if not isinstance(exchange, str):          # an exchange object made by the caller (tests share one)
+            self.ex = exchange
+        elif exchange == "p2p" and _world(group) > 1:
             # peer mapping can be unavailable (no NVLink/IPC between the ranks): P2PExchange agrees on the outcome
             # over `group` and raises on ALL ranks together, which then all use the collective exchange
             try:
@@ -445,10 +464,12 @@ class ShardedTrainStep:
         self.reg = float(reg_weight)
         self.eu.grad, self.ei.grad = torch.zeros_like(self.eu), torch.zeros_like(self.ei)
         self.opt = FusedAdam(self.eu, self.ei, lr=lr)
+        # dense gradient tables kept ZERO outside the rows of the current batch (flagged for the adjoint by
+        # cgx_bpr_mark_rows, cleared row by row after use): no per-step fill or scan of whole tables
         self.g_u = torch.zeros_like(self.eu)
-        self.ego_u = torch.zeros_like(self.eu)
-        # dense item tables kept ZERO outside the rows of the current batch (cleared row by row after use)
-        self.gi_local = torch.empty_like(self.ei)            # bpr writes whole rows; only those rows are read back
+        self.nz_u = torch.zeros(self.eu.shape[0], dtype=torch.uint8, device=dev)
+        self.nz_i_local = torch.zeros(I, dtype=torch.uint8, device=dev)
+        self.gi_local = torch.zeros_like(self.ei)            # bpr writes whole rows; only those rows are read back
         self.g_i = torch.zeros_like(self.ei)                 # dL/d(final_i), summed over ranks
         self.owner = torch.full((I + 1,), -1, dtype=torch.int64, device=dev)
         self.tick = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -460,8 +481,9 @@ class ShardedTrainStep:
         return 2 * B * (d + 2) + 4            # [2B, d] rows | 2B L2 coefficients | 2B row ids | loss (+ padding)
 
     @torch.no_grad()
-    def __call__(self, users_local: torch.Tensor, batch_total: int | None = None):
-        """batch_total: global batch size (default: every rank holds a batch of this size)."""
+    def __call__(self, users_local: torch.Tensor, batch_total: int | None = None, triples=None):
+        """batch_total: global batch size (default: every rank holds a batch of this size).
+        triples: optional injected (pos, neg) for users_local instead of sampling (parity tests)."""
         g, dev = self.graph, self.eu.device
         B = users_local.numel()
         world = _world(self.group)
@@ -474,16 +496,17 @@ class ShardedTrainStep:
             self.ex.begin_step()
         with torch.cuda.device(dev):
             check(lib().cgx_tick(ptr(self.tick), stream_ptr(dev)))
-        pos, neg = self.sampler.sample(users_local, offset=0, offset_dev=self.tick)
+        if triples is None:
+            pos, neg = self.sampler.sample(users_local, offset=0, offset_dev=self.tick)
+        else:
+            pos, neg = (torch.as_tensor(t, device=dev).to(torch.int64) for t in triples)
         bpr_plan(g, users_local, pos, neg, plan)
         f_u, f_i = self.prop.forward(self.eu.data, self.ei.data)
-        self.g_u.zero_()
-        self.ego_u.zero_()
         loss, _, _, ego_rows, ego_coef = bpr_fused(g, f_u, f_i, self.eu.data, self.ei.data, users_local, pos, neg,
                                                    self.reg, 0.0, None, self.g_u, self.gi_local, plan, bufs, B_total)
-        # user part of the L2 gradient stays local (item entries masked out: rows >= U)
-        ego_user = torch.where(ego_rows < U, ego_rows, torch.full_like(ego_rows, -1))
-        apply_ego(g, ego_user, ego_coef, self.eu.data, self.ei.data, self.ego_u, self.gi_local)
+        with torch.cuda.device(dev):
+            check(lib().cgx_bpr_mark_rows(ptr(ego_rows), ego_rows.numel(), U, ptr(self.nz_u), ptr(self.nz_i_local),
+                                          stream_ptr(dev)))
         # ---- compact item part: the plan is sorted by row, users first, so item runs live in positions [B, 3B) ----
         er = ego_rows[B:]
         valid = er >= U
@@ -509,8 +532,13 @@ class ShardedTrainStep:
         self.owner.scatter_(0, flat, ar)                                    # one representative per distinct row
         keep = (self.owner[flat] == ar) & ok.reshape(-1)
         flat_c = flat.clamp(max=I - 1)
-        d_u, d_i = self.prop.backward(self.g_u, self.g_i, seed_rows=(flat_c, keep))
-        self.eu.grad.copy_(d_u.add_(self.ego_u))
+        d_u, d_i = self.prop.backward(self.g_u, self.g_i, seed_rows=(flat_c, keep), g_u_flags=self.nz_u,
+                                      out_u=self.eu.grad)
+        if d_u is not self.eu.grad:
+            self.eu.grad.copy_(d_u)
+        # user part of the L2 gradient stays local (item entries masked out: rows >= U); added after the adjoint
+        ego_user = torch.where(ego_rows < U, ego_rows, torch.full_like(ego_rows, -1))
+        apply_ego(g, ego_user, ego_coef, self.eu.data, self.ei.data, self.eu.grad, self.gi_local)
         # item gradient: in Gauss-Seidel order it is s * seed + L2 term, non-zero on the batch's rows only
         if d_i is None:
             s = 1.0 / (self.prop.K + 1)
@@ -521,7 +549,10 @@ class ShardedTrainStep:
             rr = rows_all[r].clamp(max=I - 1)
             self.ei.grad.index_add_(0, rr, self.ei.data[rr] * (coef[r] * ok[r])[:, None])
         self.opt.step()
-        # restore the all-zero invariant of the dense item tables, row by row
+        # restore the all-zero invariant of the dense gradient tables, row by row
+        with torch.cuda.device(dev):
+            check(lib().cgx_bpr_clear_rows(ptr(ego_rows), ego_rows.numel(), U, d, ptr(self.g_u), ptr(self.gi_local),
+                                           ptr(self.nz_u), ptr(self.nz_i_local), stream_ptr(dev)))
         self.g_i[flat_c] = 0.0
         if d_i is None:
             self.ei.grad[flat_c] = 0.0
@@ -695,6 +726,19 @@ def parity_vs_single_gpu(rank: int, world: int, dev, variant="v2", order="gs", e
     if hi > lo:
         errs["f_u"] = rel(f_u, st.f_u[lo:hi])
         errs["d_u"] = rel(d_u, net.user_emb.weight.grad[lo:hi])
+    # the whole sharded training step (compact loss-gradient all-gather, row bookkeeping, Adam) on the same triples:
+    # Adam's first-moment buffers after one step are 0.1 x the gradients the step used
+    if hasattr(ex, "allgather"):         # (every rank of the C1 split owns users and triples; all ranks must take part)
+        assert hi > lo and int(mine.sum()) > 0, "parity graph too small for this many ranks"
+        sh = ShardedTrainStep(gl, eu[lo:hi].to(dev), ei.to(dev), K, order, reg_weight=1e-4,
+                              mix_pop=None if variant == "cu" else 0.7, exchange=ex, max_batch=batch)
+        loss2 = sh(ul, batch_total=len(users), triples=(pos[mine], neg[mine]))
+        st.opt.step()
+        errs["step_loss"] = abs(float(loss2.item()) - float(want.item())) / abs(float(want.item()))
+        errs["step_m_u"] = rel(sh.opt.m[0], st.opt.m[0][lo:hi])
+        errs["step_m_i"] = rel(sh.opt.m[1], st.opt.m[1])
+        errs["step_g_u_clean"] = float(sh.g_u.abs().max().item() + sh.g_i.abs().max().item()
+                                       + sh.gi_local.abs().max().item() + sh.nz_u.sum().item())
     worst = torch.tensor([max(errs.values())], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(worst, op=dist.ReduceOp.MAX)
@@ -718,7 +762,8 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
     par_ex = None
     if ex_kind == "p2p":
         try:
-            par_ex = P2PExchange(2 * synth.SHAPES["C1"]["num_items"] * 64 + 4, dev)
+            par_ex = P2PExchange(2 * synth.SHAPES["C1"]["num_items"] * 64 + 4, dev,
+                                 gather_floats=ShardedTrainStep._block_floats(2048, 64))
         except _lib.CgxError:
             par_ex = None
     parity, parity_detail, _ = parity_vs_single_gpu(rank, world, dev, "v2", "gs", exchange=par_ex)
@@ -751,7 +796,7 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
     del sg
     torch.cuda.empty_cache()
     step = ShardedTrainStep(gr, user_emb, item_emb, K, shp["order"], mix_pop=None if shp["variant"] == "cu" else 0.7,
-                            exchange=ex_kind)
+                            exchange=ex_kind, max_batch=args.batch)
     train_users = torch.nonzero(gr.deg_u > 0).reshape(-1).cpu().numpy()
     np.random.default_rng(42 + rank).shuffle(train_users)
     nb = min(len(train_users) // args.batch, 64)

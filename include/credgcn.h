@@ -197,6 +197,11 @@ int cgx_spmm_sparse_rows(const cgx_csr* m, int use_bwd_values, int32_t d, const 
                          const uint8_t* x_row_nonzero, float* Y, const float* ACC_IN, float* ACC_OUT,
                          float acc_scale, void* workspace, size_t workspace_bytes, void* stream);
 int cgx_row_flags(const float* X, int64_t n_rows, int32_t d, uint8_t* flags, void* stream);
+/* The general form: both flag arrays are optional.  acc_row_nonzero[r] == 0 promises that row r of ACC_IN is all
+ * zero, and it is then not read (the adjoint adds the row-sparse loss gradient to every layer). */
+int cgx_spmm_ex(const cgx_csr* m, int use_bwd_values, int32_t d, const float* X, const uint8_t* x_row_nonzero,
+                float* Y, const float* ACC_IN, const uint8_t* acc_row_nonzero, float* ACC_OUT, float acc_scale,
+                void* workspace, size_t workspace_bytes, void* stream);
 
 /* cgx_spmm picks its thread geometry by regime: a gathered table X of more than this many bytes is treated as
  * HBM-resident (narrower groups, more rows in flight), a smaller one as L2-resident.  Default 96 MiB; a negative

@@ -27,11 +27,12 @@ def _worker(rank, world, port, out):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         from credgcn import synth
-        from credgcn.sharded import (CollectiveExchange, P2PExchange, build_local_graph, parity_vs_single_gpu,
-                                     partition_users, shard_edges)
+        from credgcn.sharded import (CollectiveExchange, P2PExchange, ShardedTrainStep, build_local_graph,
+                                     parity_vs_single_gpu, partition_users, shard_edges)
         I, d = synth.SHAPES["C1"]["num_items"], 64
         res = {}
-        p2p = P2PExchange(2 * I * d + 4, dev)         # NVLink peer-memory exchange (csrc/comm.cu)
+        p2p = P2PExchange(2 * I * d + 4, dev,         # NVLink peer-memory exchange (csrc/comm.cu)
+                          gather_floats=ShardedTrainStep._block_floats(2048, d))
         for variant, order in (("v2", "gs"), ("cu", "jacobi"), ("da", "gs")):
             outs = {}
             for ex_name, ex, push in (("nccl", CollectiveExchange(), None), ("p2p", p2p, False), ("p2p_push", p2p, True)):
