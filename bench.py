@@ -344,7 +344,7 @@ def run_single(args, name, dev, steps, warmup, clocks, with_cpu, with_extras):
     B = int(host_batches[0].size)
 
     # ---- ONE code path for `value` and `e2e`: the public TrainStep.step() replaying the captured CUDA graph ----
-    step.capture(B)
+    step.capture(B, preserve_state=name != "C5")
     for s in range(max(warmup, 3)):
         step.step(dev_batches[s % n_batches])
     torch.cuda.synchronize()

@@ -68,6 +68,7 @@ _SIGNATURES = {
     "cgx_spmm_ex": (C.c_int, [_CSR, C.c_int, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_float, _P, C.c_size_t, _P]),
     "cgx_spmm_set_l2_table_bytes": (C.c_int64, [C.c_int64]),
     "cgx_propagate_workspace_bytes": (C.c_size_t, [_CSR, _CSR, C.c_int32]),
+    "cgx_propagate_workspace_bytes_for": (C.c_size_t, [_CSR, _CSR, C.c_int32, C.c_int]),
     "cgx_propagate_fwd": (C.c_int, [_CSR, _CSR, C.c_int, C.c_int32, C.c_int32, _P, _P, _P, _P, _P,
                                     C.c_size_t, _P]),
     "cgx_propagate_bwd": (C.c_int, [_CSR, _CSR, C.c_int, C.c_int32, C.c_int32, _P, _P, _P, _P, _P,

@@ -800,11 +800,24 @@ extern "C" int cgx_row_flags(const float* X, int64_t n_rows, int32_t d, uint8_t*
   return row_flags(X, n_rows, d, flags, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" size_t cgx_propagate_workspace_bytes(const cgx_csr* by_user, const cgx_csr* by_item, int32_t d) {
+// Layer buffers: the Jacobi order reads layer k of BOTH sides while it writes layer k + 1, so it needs two buffers
+// per side; in Gauss-Seidel order every buffer is dead by the time it is overwritten (the item product reads u_k
+// and writes i_{k+1}, the user product reads i_{k+1} and writes u_{k+1}), so one per side is enough -- 15 GB less
+// at the C5 shape.
+static size_t propagate_ws(const cgx_csr* by_user, const cgx_csr* by_item, int32_t d, int n_buf) {
   if (!by_user || !by_item) return 0;
   size_t long_ws = spmm_ws(by_user, d) > spmm_ws(by_item, d) ? spmm_ws(by_user, d) : spmm_ws(by_item, d);
-  return 2 * (align_up(size_t(by_user->n_rows) * d * 4) + align_up(size_t(by_item->n_rows) * d * 4)) + long_ws +
+  return n_buf * (align_up(size_t(by_user->n_rows) * d * 4) + align_up(size_t(by_item->n_rows) * d * 4)) + long_ws +
          align_up(size_t(by_user->n_rows)) + align_up(size_t(by_item->n_rows)) + 256;
+}
+
+extern "C" size_t cgx_propagate_workspace_bytes(const cgx_csr* by_user, const cgx_csr* by_item, int32_t d) {
+  return propagate_ws(by_user, by_item, d, 2);
+}
+
+extern "C" size_t cgx_propagate_workspace_bytes_for(const cgx_csr* by_user, const cgx_csr* by_item, int32_t d,
+                                                    int order) {
+  return propagate_ws(by_user, by_item, d, order == CGX_ORDER_GS ? 1 : 2);
 }
 
 extern "C" int cgx_propagate_fwd(const cgx_csr* by_user, const cgx_csr* by_item, int order, int32_t K, int32_t d,
@@ -816,12 +829,17 @@ extern "C" int cgx_propagate_fwd(const cgx_csr* by_user, const cgx_csr* by_item,
   CGX_REQUIRE(order == CGX_ORDER_JACOBI || order == CGX_ORDER_GS, CGX_ERR_ARG, "propagate_fwd: bad order");
   CGX_REQUIRE(by_user->n_rows == by_item->n_cols && by_user->n_cols == by_item->n_rows, CGX_ERR_ARG,
               "propagate_fwd: operator shapes disagree");
-  CGX_REQUIRE(workspace_bytes >= cgx_propagate_workspace_bytes(by_user, by_item, d), CGX_ERR_WORKSPACE,
+  CGX_REQUIRE(workspace_bytes >= cgx_propagate_workspace_bytes_for(by_user, by_item, d, order), CGX_ERR_WORKSPACE,
               "propagate_fwd: workspace too small");
   const int64_t U = by_user->n_rows, I = by_item->n_rows;
   Arena ws(workspace, workspace_bytes);
-  float* ub[2] = {ws.take<float>(U * d), ws.take<float>(U * d)};
-  float* ib[2] = {ws.take<float>(I * d), ws.take<float>(I * d)};
+  const bool one = order == CGX_ORDER_GS;   // one layer buffer per side is enough (see propagate_ws)
+  float* ub[2];
+  float* ib[2];
+  ub[0] = ws.take<float>(U * d);
+  ub[1] = one ? ub[0] : ws.take<float>(U * d);
+  ib[0] = ws.take<float>(I * d);
+  ib[1] = one ? ib[0] : ws.take<float>(I * d);
   size_t lws = spmm_ws(by_user, d) > spmm_ws(by_item, d) ? spmm_ws(by_user, d) : spmm_ws(by_item, d);
   void* lw = ws.take<char>(lws);
   CGX_REQUIRE(ws.ok, CGX_ERR_WORKSPACE, "propagate_fwd: workspace too small");
@@ -872,12 +890,17 @@ extern "C" int cgx_propagate_bwd_flagged(const cgx_csr* by_user, const cgx_csr* 
   CGX_REQUIRE(by_user && by_item && g_u && g_i && d_e0_u && d_e0_i, CGX_ERR_ARG, "propagate_bwd: NULL pointer");
   CGX_REQUIRE(K >= 1, CGX_ERR_ARG, "propagate_bwd: num_layers must be >= 1");
   CGX_REQUIRE(order == CGX_ORDER_JACOBI || order == CGX_ORDER_GS, CGX_ERR_ARG, "propagate_bwd: bad order");
-  CGX_REQUIRE(workspace_bytes >= cgx_propagate_workspace_bytes(by_user, by_item, d), CGX_ERR_WORKSPACE,
+  CGX_REQUIRE(workspace_bytes >= cgx_propagate_workspace_bytes_for(by_user, by_item, d, order), CGX_ERR_WORKSPACE,
               "propagate_bwd: workspace too small");
   const int64_t U = by_user->n_rows, I = by_item->n_rows;
   Arena ws(workspace, workspace_bytes);
-  float* ub[2] = {ws.take<float>(U * d), ws.take<float>(U * d)};
-  float* ib[2] = {ws.take<float>(I * d), ws.take<float>(I * d)};
+  const bool one = order == CGX_ORDER_GS;   // bi' and bu' are each dead when they are overwritten
+  float* ub[2];
+  float* ib[2];
+  ub[0] = ws.take<float>(U * d);
+  ub[1] = one ? ub[0] : ws.take<float>(U * d);
+  ib[0] = ws.take<float>(I * d);
+  ib[1] = one ? ib[0] : ws.take<float>(I * d);
   size_t lws = spmm_ws(by_user, d) > spmm_ws(by_item, d) ? spmm_ws(by_user, d) : spmm_ws(by_item, d);
   void* lw = ws.take<char>(lws);
   CGX_REQUIRE(ws.ok, CGX_ERR_WORKSPACE, "propagate_bwd: workspace too small");

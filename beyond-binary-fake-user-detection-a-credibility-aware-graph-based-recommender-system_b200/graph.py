@@ -178,11 +178,17 @@ class CredGraph:
             beyond = csr.n_cols * d * 4 > l2
             csr.set_hot_columns(other.perm, hot_bytes // (4 * d) if beyond else 0)
 
-    def propagate_workspace(self, d: int) -> torch.Tensor:
-        key = ("prop", d)
+    def propagate_workspace(self, d: int, order=None) -> torch.Tensor:
+        """Scratch of cgx_propagate_fwd / _bwd.  order ("gs" / "jacobi" or the C enum): the Gauss-Seidel order needs
+        half the layer buffers; None sizes it for either order."""
+        o = _lib.ORDERS.get(order, order)
+        key = ("prop", d, o)
         if key not in self._ws_cache:
             self.set_emb_dim(d)
-            n = lib().cgx_propagate_workspace_bytes(self.by_user.ref(), self.by_item.ref(), d)
+            if o is None:
+                n = lib().cgx_propagate_workspace_bytes(self.by_user.ref(), self.by_item.ref(), d)
+            else:
+                n = lib().cgx_propagate_workspace_bytes_for(self.by_user.ref(), self.by_item.ref(), d, int(o))
             self._ws_cache[key] = workspace(n, self.device)
         return self._ws_cache[key]
 

@@ -10,6 +10,7 @@ Host-side I/O only: nothing here touches the GPU.
 """
 from __future__ import annotations
 
+import array
 import hashlib
 import json
 import pickle
@@ -78,23 +79,28 @@ def build_graph_from_jsonl(cfg=None):
     src = Path(cfg.jsonl_path)
 
     user2idx, item2idx = {}, {}
-    rows = {"train": [], "val": [], "test": []}
-    for n, rec in iter_jsonl_records(src, cfg):          # one pass suffices: ids and buckets are per record
+    # One pass suffices (ids and buckets are per record).  Edges are appended to flat int32 arrays, 8 bytes per edge
+    # like the reference's preallocated [2, E] arrays (lightgcn_cu.py:211-237) -- a Python list of tuples would cost
+    # ~100 bytes per edge, many GB on the tens of millions of positives of the real dataset.
+    rows = {"train": array.array("i"), "val": array.array("i"), "test": array.array("i")}
+    for n, rec in iter_jsonl_records(src, cfg):
         if not is_positive_interaction(rec, cfg):
             continue
         uid, iid = rec[cfg.user_key], rec[cfg.item_key]
         u = user2idx.setdefault(uid, len(user2idx))
         i = item2idx.setdefault(iid, len(item2idx))
-        rows[split_bucket(uid, iid, cfg)].append((u, i))
+        b = rows[split_bucket(uid, iid, cfg)]
+        b.append(u)
+        b.append(i)
         if n % cfg.print_every == 0:
             print(f"PASS {n:,} | users={len(user2idx):,} items={len(item2idx):,} "
-                  + " ".join(f"{k}={len(v):,}" for k, v in rows.items()))
-    print("Users:", len(user2idx), "Items:", len(item2idx), "Positive edges:", sum(map(len, rows.values())))
-    print("Split counts:", {k: len(v) for k, v in rows.items()})
+                  + " ".join(f"{k}={len(v) // 2:,}" for k, v in rows.items()))
+    print("Users:", len(user2idx), "Items:", len(item2idx), "Positive edges:", sum(len(v) // 2 for v in rows.values()))
+    print("Split counts:", {k: len(v) // 2 for k, v in rows.items()})
     for name, obj in (("user2idx", user2idx), ("item2idx", item2idx)):
         with open(out / "model" / f"{name}.pkl", "wb") as f:
             pickle.dump(obj, f, protocol=pickle.HIGHEST_PROTOCOL)
     for k, v in rows.items():
-        arr = np.asarray(v, dtype=np.int32).reshape(-1, 2).T if v else np.empty((2, 0), dtype=np.int32)
+        arr = np.frombuffer(v, dtype=np.int32).reshape(-1, 2).T if len(v) else np.empty((2, 0), dtype=np.int32)
         np.save(out / "npy" / f"{k}_edges.npy", np.ascontiguousarray(arr))
     print("\n✅ Saved graph files to:", out)

@@ -34,7 +34,7 @@ def propagate_forward(graph: CredGraph, e0_u, e0_i, num_layers: int, order: str)
     e0_u, e0_i = _f32c(e0_u), _f32c(e0_i)
     d = e0_u.shape[1]
     out_u, out_i = torch.empty_like(e0_u), torch.empty_like(e0_i)
-    ws = graph.propagate_workspace(d)
+    ws = graph.propagate_workspace(d, order)
     with torch.cuda.device(graph.device):
         check(lib().cgx_propagate_fwd(graph.by_user.ref(), graph.by_item.ref(), _lib.ORDERS[order], num_layers, d,
                                       ptr(e0_u), ptr(e0_i), ptr(out_u), ptr(out_i), ptr(ws), ws.numel(),
@@ -46,7 +46,7 @@ def propagate_backward(graph: CredGraph, g_u, g_i, num_layers: int, order: str):
     g_u, g_i = _f32c(g_u), _f32c(g_i)
     d = g_u.shape[1]
     d_u, d_i = torch.empty_like(g_u), torch.empty_like(g_i)
-    ws = graph.propagate_workspace(d)
+    ws = graph.propagate_workspace(d, order)
     with torch.cuda.device(graph.device):
         check(lib().cgx_propagate_bwd(graph.by_user.ref(), graph.by_item.ref(), _lib.ORDERS[order], num_layers, d,
                                       ptr(g_u), ptr(g_i), ptr(d_u), ptr(d_i), ptr(ws), ws.numel(),
@@ -388,7 +388,7 @@ class TrainStep:
         m, g = self.model, self.graph
         eu, ei = m.user_emb.weight, m.item_emb.weight
         d, K, order = eu.shape[1], m.num_layers, _lib.ORDERS[m.ORDER]
-        ws = g.propagate_workspace(d)
+        ws = g.propagate_workspace(d, order)
         dev = eu.device
         users, pos, neg = _i64c(users, dev), _i64c(pos, dev), _i64c(neg, dev)
         plan, bufs = self._batch_bufs(users.numel(), dev)
@@ -435,8 +435,10 @@ class TrainStep:
         pos, neg = self.sampler.sample(users, offset=0, offset_dev=self.tick)
         return self.__call__(users, pos, neg)
 
-    def capture(self, batch: int):
-        """Record sample + forward + loss + backward + Adam for `batch` users as one CUDA graph."""
+    def capture(self, batch: int, preserve_state: bool = True):
+        """Record sample + forward + loss + backward + Adam for `batch` users as one CUDA graph.  The two warm-up
+        steps before the capture do not count: parameters, optimiser state and counters are restored afterwards --
+        unless preserve_state=False (three more copies of both tables do not fit next to the 1 B-edge shape)."""
         if self.sampler is None:
             raise _lib.CgxError("TrainStep.capture needs a TripleSampler (pass sampler=...)")
         dev = self.graph.device
@@ -446,14 +448,17 @@ class TrainStep:
         warm = torch.cuda.Stream(device=dev)
         warm.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(warm):                       # warm-up outside capture (allocations, attributes)
-            state = [p.detach().clone() for p in (self.model.user_emb.weight, self.model.item_emb.weight)]
-            opt_state = ([t.clone() for t in self.opt.m], [t.clone() for t in self.opt.v], self.opt.step_dev.clone(),
-                         self.tick.clone()) if isinstance(self.opt, FusedAdam) else None
+            state = opt_state = None
+            if preserve_state:
+                state = [p.detach().clone() for p in (self.model.user_emb.weight, self.model.item_emb.weight)]
+                opt_state = ([t.clone() for t in self.opt.m], [t.clone() for t in self.opt.v],
+                             self.opt.step_dev.clone(), self.tick.clone()) if isinstance(self.opt, FusedAdam) else None
             for _ in range(2):
                 self._sampled_step(self._g_users)
             # the warm-up steps must not count: restore parameters, optimiser state and counters
-            self.model.user_emb.weight.data.copy_(state[0])
-            self.model.item_emb.weight.data.copy_(state[1])
+            if state is not None:
+                self.model.user_emb.weight.data.copy_(state[0])
+                self.model.item_emb.weight.data.copy_(state[1])
             if opt_state is not None:
                 for dst, src in zip(self.opt.m, opt_state[0]):
                     dst.copy_(src)

@@ -507,26 +507,32 @@ class ShardedTrainStep:
         with torch.cuda.device(dev):
             check(lib().cgx_bpr_mark_rows(ptr(ego_rows), ego_rows.numel(), U, ptr(self.nz_u), ptr(self.nz_i_local),
                                           stream_ptr(dev)))
-        # ---- compact item part: the plan is sorted by row, users first, so item runs live in positions [B, 3B) ----
+        # ---- compact item part: the plan is sorted by row, users first, so item runs live in positions [B, 3B).
+        # Blocks have the size of max_batch on every rank (ranks may hold different batch sizes); unused slots carry
+        # row id -1. ----
+        Bm = self.max_batch
+        if B > Bm:
+            raise _lib.CgxError(f"ShardedTrainStep: batch of {B} users exceeds max_batch={Bm}")
         er = ego_rows[B:]
         valid = er >= U
         rows = torch.where(valid, er - U, torch.zeros_like(er)).to(torch.int64)
-        block = torch.empty(self._block_floats(B, d), dtype=torch.float32, device=dev)
-        block[: 2 * B * d].view(2 * B, d).copy_(self.gi_local[rows] * valid[:, None])
-        block[2 * B * d: 2 * B * (d + 1)] = ego_coef[B:] * valid
-        block[2 * B * (d + 1): 2 * B * (d + 2)] = torch.where(valid, rows, torch.full_like(rows, -1)).to(
-            torch.int32).view(torch.float32)
-        block[2 * B * (d + 2):] = 0.0
-        block[2 * B * (d + 2)] = loss[0]
+        block = torch.zeros(self._block_floats(Bm, d), dtype=torch.float32, device=dev)
+        block[: 2 * B * d].view(2 * B, d).copy_(torch.where(valid[:, None], self.gi_local[rows], 0.0))
+        o_coef, o_rows, o_loss = 2 * Bm * d, 2 * Bm * (d + 1), 2 * Bm * (d + 2)
+        block[o_coef: o_coef + 2 * B] = torch.where(valid, ego_coef[B:], 0.0)   # (non-head slots are uninitialised)
+        rid_local = torch.full((2 * Bm,), -1, dtype=torch.int32, device=dev)
+        rid_local[: 2 * B] = torch.where(valid, rows, torch.full_like(rows, -1)).to(torch.int32)
+        block[o_rows: o_rows + 2 * Bm] = rid_local.view(torch.float32)
+        block[o_loss] = loss[0]
         blocks = self.ex.allgather(block)                                   # [world, n], rank order
-        vals = blocks[:, : 2 * B * d].reshape(world, 2 * B, d)
-        coef = blocks[:, 2 * B * d: 2 * B * (d + 1)]
-        rid = blocks[:, 2 * B * (d + 1): 2 * B * (d + 2)].contiguous().view(torch.int32).to(torch.int64)
+        vals = blocks[:, : 2 * Bm * d].reshape(world, 2 * Bm, d)
+        coef = blocks[:, o_coef: o_coef + 2 * Bm]
+        rid = blocks[:, o_rows: o_rows + 2 * Bm].contiguous().view(torch.int32).to(torch.int64)
         ok = rid >= 0
         rows_all = torch.where(ok, rid, torch.full_like(rid, I))            # invalid slots -> the dummy row I
-        total_loss = blocks[:, 2 * B * (d + 2)].sum().reshape(1)
+        total_loss = blocks[:, o_loss].sum().reshape(1)
         for r in range(world):                                              # rank order: same bits on every rank
-            self.g_i.index_add_(0, rows_all[r].clamp(max=I - 1), vals[r] * ok[r][:, None])
+            self.g_i.index_add_(0, rows_all[r].clamp(max=I - 1), torch.where(ok[r][:, None], vals[r], 0.0))
         flat = rows_all.reshape(-1)
         ar = torch.arange(flat.numel(), device=dev)
         self.owner.scatter_(0, flat, ar)                                    # one representative per distinct row

@@ -210,6 +210,8 @@ int cgx_spmm_ex(const cgx_csr* m, int use_bwd_values, int32_t d, const float* X,
 int64_t cgx_spmm_set_l2_table_bytes(int64_t bytes);
 
 size_t cgx_propagate_workspace_bytes(const cgx_csr* by_user, const cgx_csr* by_item, int32_t d);
+/* The same for one layer order: Gauss-Seidel needs one layer buffer per side, Jacobi two (the size above). */
+size_t cgx_propagate_workspace_bytes_for(const cgx_csr* by_user, const cgx_csr* by_item, int32_t d, int order);
 
 /* Forward: final = mean over layers 0..K.  order JACOBI = CU:429-437, GS = V2:482-486.
  * e0_u [U,d], e0_i [I,d] -> out_u [U,d], out_i [I,d].  Nothing is saved for backward (the
