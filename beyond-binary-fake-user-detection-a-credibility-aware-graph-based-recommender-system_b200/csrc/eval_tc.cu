@@ -22,14 +22,17 @@
 //   warps 1-4 (and 5-8 when two epilogue groups are used: group g owns accumulator stage g)
 //               epilogue: tcgen05.ld 32x32b.x16 -> registers, predicated append of scores >= the row
 //               threshold, warp-uniform drain into the row's K' kept candidates (one thread per user)
-//   next 4      producers: cp.async (16 B, L2-only) the item operand into a ring of 3..8 shared-memory stages,
-//               one 64-column k-block (128 items x 128 B) per stage, in the canonical K-major SWIZZLE_128B
-//               UMMA layout (16-byte chunks XOR-ed with row%8 -- what TMA would write), so that a row's 8
-//               chunks are one coalesced 128-byte global read AND one conflict-free shared write; then fence
-//               to the async proxy and arrive on the stage's mbarrier.  The ring is k-block granular so that
-//               wide tables fit: d = 128 with BF16X3 needs 64 KB per item tile next to 64 KB of users.
+//   next 4      producer: ONE elected thread issues a TMA tile load (cp.async.bulk.tensor.2d, SWIZZLE_128B tensor
+//               map over the bf16 item operand [I, Kp]; rows past I are zero-filled by the unit) per ring stage:
+//               one 64-column k-block (128 items x 128 B) lands in the canonical K-major SWIZZLE_128B UMMA layout
+//               and completes the stage's mbarrier by transaction bytes -- no register staging, no per-thread
+//               address arithmetic, no proxy fence; the other producer lanes are idle and leave their issue slots
+//               to the epilogue.  The ring (3..8 stages) is k-block granular so that wide tables fit: d = 128 with
+//               BF16X3 needs 64 KB per item tile next to 64 KB of users.  (Round 1 staged the same layout with
+//               128 threads of 16-byte cp.async.)
 //   last 4      mask builders: per user row, 128 "is a train item" bits per item tile, a few tiles ahead
 // Two 128-column TMEM accumulators: the MMA of tile j+1 overlaps the epilogue of tile j.
+#include <cuda.h>        // CUtensorMap + the cuTensorMapEncodeTiled prototype (resolved at run time, no -lcuda)
 #include <cuda_bf16.h>
 #include <float.h>
 #include <stdlib.h>
@@ -85,10 +88,6 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return uint64_t((smem_addr & 0x3FFFF) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) |
          (uint64_t(1) << 46) | (uint64_t(2) << 61);
-}
-__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gmem_src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes)
-               : "memory");
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -158,8 +157,8 @@ __global__ void k_tc_convert(const float* __restrict__ src, const int64_t* __res
 // With NG = 2 group g drains accumulator stage g (tiles of parity g) into its own list, which doubles the
 // warps that scan scores -- the epilogue, not the MMA, bounds this kernel (d is only 64..128).
 template <int KC, int BC, int NG>
-__global__ void __launch_bounds__(32 * (9 + 4 * NG), 1) k_eval_umma(const __nv_bfloat16* __restrict__ Au,   // [n_users, Kp]
-                                                             const __nv_bfloat16* __restrict__ Bi,   // [I, Kp]
+__global__ void __launch_bounds__(32 * (9 + 4 * NG), 1) k_eval_umma(const __grid_constant__ CUtensorMap b_map,   // item operand [I, Kp] bf16
+                                                             const __nv_bfloat16* __restrict__ Au,   // [n_users, Kp]
                                                              const int64_t* __restrict__ users, int64_t n_users,
                                                              int32_t I, int32_t Kp, int32_t nkb, int32_t S,
                                                              const int64_t* __restrict__ tr_indptr,
@@ -201,7 +200,7 @@ __global__ void __launch_bounds__(32 * (9 + 4 * NG), 1) k_eval_umma(const __nv_b
   const int chunks = TC_M * n_units * 8;         // 16-byte chunks of the A operand
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(full_bar + s, 128); mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + a, 1); mbar_init(tempty_bar + a, 128); }
     for (int m = 0; m < TC_MASK_RING; ++m) { mbar_init(mfull_bar + m, 128); mbar_init(mempty_bar + m, 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -289,36 +288,27 @@ __global__ void __launch_bounds__(32 * (9 + 4 * NG), 1) k_eval_umma(const __nv_b
       mbar_arrive(mfull_bar + m);
     }
   } else if (warp >= 1 + 4 * NG) {
-    // ===== producers: stage item k-blocks with cp.async, one group per k-block, three groups in flight =====
-    const int pt = threadIdx.x - (1 + 4 * NG) * 32;   // 0..127
-    // thread pt owns chunk column c = pt % 8 of rows r0, r0+16, ... (128 threads cover 16 rows x 8 chunks)
-    const int c = pt & 7, r0 = pt >> 3;
-    int j = 0, u = 0;
-    int s = 0, s_done = 0;                            // ring positions of unit g and of unit g-2
-    uint32_t ph = 1;                                  // parity to wait for on empty_bar[s]: 1 on the first lap
-    for (int64_t g = 0; g < n_steps + 2; ++g) {
-      if (g < n_steps) {
+    // ===== producer: one thread, one TMA tile load per ring stage =====
+    if (threadIdx.x == (1 + 4 * NG) * 32) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&b_map)) : "memory");
+      int j = 0, u = 0, s = 0;
+      uint32_t ph = 1;                                // parity to wait for on empty_bar[s]: 1 on the first lap
+      for (int64_t g = 0; g < n_steps; ++g) {
         mbar_wait(empty_bar + s, ph);
-        const int64_t i0 = int64_t(j) * TC_N;
-        const __nv_bfloat16* src0 = Bi + (i0 + r0) * Kp + u * 64 + c * 8;
-        const uint32_t dst0 = smem_u32(smem_b + s * TC_KB_BYTES) + r0 * 128 + ((c ^ (r0 & 7)) << 4);   // (r0 + 16 t) % 8 == r0 % 8
-        const int rows_left = int((I - i0 - r0 + 15) / 16);                // rows r0 + 16 t that exist
+        const uint32_t bar = smem_u32(full_bar + s);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(uint32_t(TC_KB_BYTES))
+                     : "memory");
         if (!(dbg & 4)) {
-#pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const bool ok = t < rows_left;
-            cp_async16(dst0 + t * 2048, ok ? src0 + int64_t(t) * 16 * Kp : Bi, ok ? 16u : 0u);   // 0 -> zero fill
-          }
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+                  "r"(smem_u32(smem_b + s * TC_KB_BYTES)),
+              "l"(reinterpret_cast<uint64_t>(&b_map)), "r"(u * 64), "r"(j * TC_N), "r"(bar)
+              : "memory");
+        } else {
+          asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(uint32_t(TC_KB_BYTES)) : "memory");
         }
         if (++u == n_units) { u = 0; ++j; }
         if (++s == S) { s = 0; ph ^= 1u; }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      if (g >= 2) {   // unit g-2 has landed (the two newest groups may still be in flight; S >= 3)
-        asm volatile("cp.async.wait_group 2;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(full_bar + s_done);
-        if (++s_done == S) s_done = 0;
       }
     }
   } else {
@@ -643,6 +633,33 @@ static bool tc_supported(int32_t d, int32_t K, int precision) {
   return tc_stages(tc_config(K, precision), tc_parts(precision) * tc_dp(d)) > 0;
 }
 
+// Tensor map of the bf16 item operand [I rows, Kp columns], box = one ring stage (64 columns x 128 rows), 128-byte
+// swizzle (the UMMA K-major layout), out-of-bounds rows read as zero.  cuTensorMapEncodeTiled is a driver entry
+// point: resolved through the runtime, so the library does not link libcuda.
+static int make_b_map(const __nv_bfloat16* Bi, int32_t I, int Kp, CUtensorMap* map) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CGX_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    CGX_REQUIRE(fn != nullptr && q == cudaDriverEntryPointSuccess, CGX_ERR_CUDA,
+                "eval_topk: cuTensorMapEncodeTiled is not available from this driver");
+    encode = reinterpret_cast<encode_fn>(fn);
+  }
+  const cuuint64_t dims[2] = {cuuint64_t(Kp), cuuint64_t(I)};
+  const cuuint64_t strides[1] = {cuuint64_t(Kp) * 2};
+  const cuuint32_t box[2] = {64, cuuint32_t(TC_N)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(Bi), dims, strides, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CGX_REQUIRE(r == CUDA_SUCCESS, CGX_ERR_CUDA, "eval_topk: cuTensorMapEncodeTiled failed (%d)", int(r));
+  return CGX_OK;
+}
+
 template <int KC, int BC, int NG, int STRIDE>
 static int tc_launch(const __nv_bfloat16* Au, const __nv_bfloat16* Bi, const int64_t* users, int64_t n_users,
                      const float* f_u, const float* f_i, int32_t I, int32_t d, int Kp, int nkb, const int64_t* tr_indptr,
@@ -652,8 +669,10 @@ static int tc_launch(const __nv_bfloat16* Au, const __nv_bfloat16* Bi, const int
   const int S = tc_stages(TcConfig{KC, BC, NG, STRIDE}, Kp);
   const size_t smem = tc_smem(TcConfig{KC, BC, NG, STRIDE}, Kp, S);
   CGX_CUDA(cudaFuncSetAttribute(k_eval_umma<KC, BC, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUtensorMap b_map;
+  CGX_TRY(make_b_map(Bi, I, Kp, &b_map));
   k_eval_umma<KC, BC, NG><<<(unsigned)ceil_div(n_users, TC_M), 32 * (9 + 4 * NG), smem, stream>>>(
-      Au, Bi, users, n_users, I, Kp, nkb, S, tr_indptr, tr_idx, cand, STRIDE, thr,
+      b_map, Au, users, n_users, I, Kp, nkb, S, tr_indptr, tr_idx, cand, STRIDE, thr,
       int(option(CGX_OPT_EVAL_DEBUG) >> 1));
   CGX_LAUNCH_CHECK();
   k_rescore<STRIDE><<<(unsigned)ceil_div(n_users, 8), 256, 0, stream>>>(users, n_users, f_u, f_i, d, tr_indptr, tr_idx,

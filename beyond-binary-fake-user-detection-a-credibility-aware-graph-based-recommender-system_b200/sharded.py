@@ -559,9 +559,9 @@ class ShardedTrainStep:
         with torch.cuda.device(dev):
             check(lib().cgx_bpr_clear_rows(ptr(ego_rows), ego_rows.numel(), U, d, ptr(self.g_u), ptr(self.gi_local),
                                            ptr(self.nz_u), ptr(self.nz_i_local), stream_ptr(dev)))
-        self.g_i[flat_c] = 0.0
-        if d_i is None:
-            self.ei.grad[flat_c] = 0.0
+        self.g_i.index_fill_(0, flat_c, 0.0)            # (index_fill_: `t[idx] = 0.0` would copy a host scalar, which a
+        if d_i is None:                                 #  CUDA-graph capture does not allow)
+            self.ei.grad.index_fill_(0, flat_c, 0.0)
         return total_loss
 
     def capture(self, batch: int):
@@ -907,7 +907,7 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
         comp = _bench.compulsory_bytes(U, I, int(nnz_t.item()), d, K)
         traffic, traffic_src = _bench.traffic_per_step(name)
         prop_ms = prop_f_ms + prop_b_ms
-        n_x = 2 * K + 1
+        n_x = 2 * K              # item-table exchanges (the loss gradient travels as one small all-gather)
         link_bytes = (world - 1) / world * table_bytes          # per direction, per rank, per exchange
         steps_per_epoch = -(-int(tu.item()) // args.batch)
         line = {
@@ -923,7 +923,8 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_note": f"{launches_per_step} kernels of libcredgcn.so per step and rank",
             "loss": loss_host,
-            "collectives_per_step": n_x, "cuda_graph": graphed, "exchange": type(step.ex).__name__ +
+            "collectives_per_step": f"{2 * K} item-table exchanges + 1 all-gather of the compact loss gradient",
+            "cuda_graph": graphed, "exchange": type(step.ex).__name__ +
             (" (rows pushed from the SpMM epilogue + local reduce)" if getattr(step.ex, "push_enabled", lambda: False)()
              else ""),
             "parity_vs_1gpu": parity, "parity_vs_1gpu_detail": {k: float(v) for k, v in parity_detail.items()},
