@@ -19,7 +19,7 @@ for n in (38048 * 64, 2 * 38048 * 64 + 4, 2_000_000 * 128):
             b = ex.partial_buffer((n,), dev); r = ex.reduce(b)
         e.record(); torch.cuda.synchronize()
         out[f"{name}_{n*4/1e6:.1f}MB_us"] = round(a.elapsed_time(e) * 50, 1)
-        if name == "p2p" and os.environ.get("CGX_P2P_TIMING"):
+        if name == "p2p" and os.environ.get("CGX_OPT_P2P_TIMING"):
             import ctypes
             from credgcn._lib import lib
             t = (ctypes.c_uint64 * 4)()

@@ -15,4 +15,4 @@ for prec in ("bf16x3", "bf16"):
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); evaluate.topk_device(fu, fi, users, csr, 20, prec); b.record(); torch.cuda.synchronize()
-    print(os.environ.get("CGX_EVAL_DBG", "0"), prec, round(a.elapsed_time(b), 3), "ms")
+    print(os.environ.get("CGX_OPT_EVAL_DEBUG", "0"), prec, round(a.elapsed_time(b), 3), "ms")
