@@ -433,7 +433,7 @@ def run_single(args, name, dev, steps, warmup, clocks, with_cpu, with_extras):
         alg, alg_kind = comp, "compulsory bytes (SURVEY 8d i): tables are L2-resident, the kernel is latency-bound"
     achieved = alg / (prop_ms / 1e3) / 1e9
     roof = {
-        "bound": "hbm", "kernel": "k_spmm_ring / k_spmm (+ k_spmm_finish for rows > 16384 nnz), 4K launches per step",
+        "bound": "hbm", "kernel": "k_spmm (+ k_spmm_finish for rows > 16384 nnz), 4K launches per step",
         "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": peak_src,
         "bytes": alg_kind, "traffic": (traffic / n_spmm) if traffic else None, "traffic_source": traffic_src,
         "avg_launch_ms": prop_ms / n_spmm, "launches_per_step": n_spmm,
@@ -442,8 +442,7 @@ def run_single(args, name, dev, steps, warmup, clocks, with_cpu, with_extras):
         "frac_compulsory": comp / (prop_ms / 1e3) / 1e9 / hbm_peak,
         "gather_model_bytes_per_step": gather, "compulsory_bytes_per_step": comp,
         "sparse_first_adjoint": _lib.get_option("SPARSE_FIRST_ADJOINT") != 0,
-        "hot_rows": {"bytes": graph.CredGraph.HOT_BYTES, "items": gr.by_user.n_hot, "users": gr.by_item.n_hot,
-                     "ring_form": bool(hbm_bound and _lib.get_option("SPMM_RING") != 0)},
+        "hot_rows": {"bytes": graph.CredGraph.HOT_BYTES, "items": gr.by_user.n_hot, "users": gr.by_item.n_hot},
     }
     line = {
         "metric": METRIC, "value": E / (ms / 1e3), "unit": "edges/s", "n_gpus": 1, "steps": steps,

@@ -215,13 +215,38 @@ __global__ void __launch_bounds__(P2P_THREADS) k_p2p_reduce_pushed(P2PPeers peer
   const int64_t slot4 = int64_t(rows_per) * row4;
   const float4* stage = reinterpret_cast<const float4*>(peers.base[rank] + stage_off);
   const int64_t stride = int64_t(gridDim.x) * P2P_THREADS;
-  for (int64_t i = int64_t(blockIdx.x) * P2P_THREADS + threadIdx.x; i < n4; i += stride) {
-    float4 acc = ld_peer(stage + i);                       // written by rank 0's SpMM (maybe a remote GPU): no L1
-    for (int p = 1; p < world; ++p) {
-      const float4 v = ld_peer(stage + int64_t(p) * slot4 + i);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  // PU float4 per thread and pass: all PU x world staged values are requested before the first add, and the PU x world
+  // posted NVLink stores of a pass leave back to back
+  constexpr int PU = 4;
+  for (int64_t i0 = int64_t(blockIdx.x) * P2P_THREADS + threadIdx.x; i0 < n4; i0 += stride * PU) {
+    float4 acc[PU];
+#pragma unroll
+    for (int t = 0; t < PU; ++t) {
+      const int64_t i = i0 + t * stride;
+      acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < n4) acc[t] = ld_peer(stage + i);             // written by rank 0's SpMM (maybe a remote GPU): no L1
     }
-    for (int p = 0; p < world; ++p) reinterpret_cast<float4*>(peers.base[p] + out_off)[lo_row * row4 + i] = acc;
+    for (int p = 1; p < world; ++p) {
+      float4 v[PU];
+#pragma unroll
+      for (int t = 0; t < PU; ++t) {
+        const int64_t i = i0 + t * stride;
+        v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n4) v[t] = ld_peer(stage + int64_t(p) * slot4 + i);
+      }
+#pragma unroll
+      for (int t = 0; t < PU; ++t) {
+        acc[t].x += v[t].x; acc[t].y += v[t].y; acc[t].z += v[t].z; acc[t].w += v[t].w;
+      }
+    }
+    for (int p = 0; p < world; ++p) {
+      float4* dst = reinterpret_cast<float4*>(peers.base[p] + out_off) + lo_row * row4;
+#pragma unroll
+      for (int t = 0; t < PU; ++t) {
+        const int64_t i = i0 + t * stride;
+        if (i < n4) dst[i] = acc[t];
+      }
+    }
   }
   // ---- barrier B: every slice delivered ----
   __threadfence_system();

@@ -21,8 +21,6 @@
 // Tuning (profiles/r1_spmm_variants.txt): 8 gathers in flight per lane with the register budget
 // capped for 4 CTAs/SM is within 3 % of the best variant on both the L2-resident C2 shape and the
 // HBM-bound 64M-edge shape; higher unrolls lose occupancy (d=128: 86 registers -> 2 CTAs/SM).
-#include <atomic>
-
 #include "common.cuh"
 
 namespace cgx {
@@ -215,8 +213,14 @@ __device__ __forceinline__ void epilogue(int64_t row, int lane, const float4 (&y
     const int owner = int(row / ps.rows_per);
     float4* ypush = reinterpret_cast<float4*>(c_push_base[owner] + ps.off) +
                     (int64_t(ps.rank) * ps.rows_per + (row - int64_t(owner) * ps.rows_per)) * ROW4 + lane * V;
+    // one 32-byte store per lane: the G lanes of the instruction write the row's 32 G contiguous bytes as whole
+    // sectors (two strided 16-byte stores per lane leave every sector half-written per instruction, and NVLink
+    // carries partial-sector writes at a fraction of its rate)
+    if constexpr (V == 2) st256<POL_NORMAL>(ypush, y[0], y[1]);
+    else {
 #pragma unroll
-    for (int v = 0; v < V; ++v) ypush[v] = y[v];
+      for (int v = 0; v < V; ++v) ypush[v] = y[v];
+    }
   }
   if (Y != nullptr) {
     if constexpr (V == 2) st256<POL>(Y + o, y[0], y[1]);
@@ -308,184 +312,6 @@ __global__ void __launch_bounds__(SP_THREADS, MINB) k_spmm(const int32_t* __rest
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[v] = add4(acc[v], __ldcg(partial + int64_t(c) * ROW4 + lane * V + v));
   }
-  epilogue<G, V, HOT>(int64_t(__ldg(sc.perm + k)), lane, acc, Y, ACC_IN, ACC_OUT, acc_scale, acc_nz, ps);
-  if (lane == 0) sc.arrive[k] = 0;       // self-resetting for the next launch
-}
-
-// ---- ring form of k_spmm: gathered rows staged through shared memory by cp.async -------------------------------
-// The register form above keeps UNR rows in flight per group and drains them before it issues the next UNR: a row of
-// 16 non-zeros is a chain of ~7 dependent memory latencies (descriptor, ids, 4 x gathers, ACC_IN) of which only the
-// gathers carry payload, and 64 registers per thread cap the SM at 64 groups.  When the gathered table lives in HBM
-// that chain, not the DRAM pipe, sets the pace of the short-row (user-row) products (ncu: 68 % of DRAM peak, long
-// scoreboard stalls, 45 % of the warp slots filled).  Here a lane moves its 32 bytes of every gathered row with two
-// 16-byte cp.async (LDGSTS: global -> shared memory without passing through registers) into a ring of R row slots
-// per group and reads them back itself -- shared memory is a per-lane staging area, so no barrier is needed, only
-// cp.async.wait_group.  The ring never drains inside a work item: row q + R is issued the moment row q has been
-// consumed, ACC_IN of the epilogue is fetched into a slot of its own before the first gather, and without the
-// x[UNR][V] registers the kernel fits 48 registers: 5 CTAs = 80 groups per SM, each with R = 4 rows in flight.
-// cp.async takes the L2 eviction priority of the hot-row hints as a cache-policy operand.
-// Same sums in the same order as the register form: bit-identical results.
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint64_t policy) {
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(policy)
-               : "memory");
-}
-__device__ __forceinline__ void st128_hint(float4* p, const float4& a, uint64_t policy) {
-  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z),
-               "f"(a.w), "l"(policy)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-template <int G, int V, int R, int MINB, bool PUSH, bool HOT>
-__global__ void __launch_bounds__(SP_THREADS, MINB) k_spmm_ring(const int32_t* __restrict__ idx,
-                                                                const float* __restrict__ val, int64_t n_items,
-                                                                SpmmSched sc, const float4* __restrict__ X,
-                                                                float4* __restrict__ Y, const float4* ACC_IN,
-                                                                float4* ACC_OUT, float acc_scale, float4* partial,
-                                                                const uint8_t* __restrict__ acc_nz,
-                                                                const int4* __restrict__ work, const SpmmPush ps_in) {
-  static_assert(V == 2 && R <= G && (R & (R - 1)) == 0, "ring form: 32 bytes per lane, power-of-two ring within a batch");
-  extern __shared__ __align__(16) float4 sp_ring[];   // [groups per CTA][R + 1][ROW4]; slot R holds ACC_IN
-  const SpmmPush ps = PUSH ? ps_in : SpmmPush{0ull, 0, 0};
-  constexpr int ROW4 = G * V;
-  asm volatile("griddepcontrol.launch_dependents;");
-  const int lane = threadIdx.x & (G - 1);
-  const uint32_t item = (blockIdx.x * uint32_t(SP_THREADS) + threadIdx.x) / G;   // < 2^32 / G items
-  const unsigned mask = group_mask<G>();
-  if (item >= n_items) return;
-  // A lane owns float4 slots `lane` and `G + lane` of every row here (not 2 lane, 2 lane + 1 as in the register
-  // form): the G lanes of ONE cp.async instruction then cover 16 G contiguous bytes = whole 32-byte sectors.  With
-  // 32 contiguous bytes per lane each of the two instructions would touch every sector of the row half-used, and
-  // the L2 -> SM traffic would double (measured: 149 vs 130 ms per C4 step).
-  float4* const slots = sp_ring + (threadIdx.x / G) * ((R + 1) * ROW4) + lane;   // this lane's first float4 of slot 0
-  const uint32_t slots_s = uint32_t(__cvta_generic_to_shared(slots));
-  uint64_t pol_cold, pol_hot;
-  if constexpr (HOT) {
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_cold));
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_hot));
-  } else {
-    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_cold));
-    pol_hot = pol_cold;
-  }
-  const int4 wd = __ldg(work + item);
-  const int32_t len = wd.z;
-  {
-    const int64_t begin = (int64_t(wd.y) << 32) | uint32_t(wd.x);
-    idx += begin + lane;
-    val += begin + lane;
-  }
-  // column ids / values of the current batch (c, w) and of the next one (c_nxt, w_nxt), one per lane
-  int32_t c = 0, c_nxt = 0;
-  float w = 0.f, w_nxt = 0.f;
-  if (lane < len) {
-    c = ld_idx<HOT>(idx);
-    w = ld_val<HOT>(val);
-  }
-  if (G + lane < len) {
-    c_nxt = ld_idx<HOT>(idx + G);
-    w_nxt = ld_val<HOT>(val + G);
-  }
-  idx += 2 * G;
-  val += 2 * G;
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  // epilogue operand first: by the time the gathers are done it has long arrived
-  const bool plain = item >= uint32_t(sc.n_chunks);
-  const bool have_acc = plain && ACC_OUT != nullptr && ACC_IN != nullptr && (acc_nz == nullptr || __ldg(acc_nz + wd.w) != 0);
-  if (have_acc) {
-    const float4* a = ACC_IN + int64_t(wd.w) * ROW4 + lane;
-    cp_async16(slots_s + R * ROW4 * 16, a, pol_cold);
-    cp_async16(slots_s + R * ROW4 * 16 + G * 16, a + G, pol_cold);
-  }
-  cp_async_commit();
-  auto issue = [&](int32_t cj, int slot) {   // this lane's 32 bytes of row cj -> ring slot
-    const float4* p = X + int64_t(HOT ? (cj & 0x7fffffff) : cj) * ROW4 + lane;
-    const uint64_t pol = (HOT && cj < 0) ? pol_hot : pol_cold;
-    cp_async16(slots_s + slot * (ROW4 * 16), p, pol);
-    cp_async16(slots_s + slot * (ROW4 * 16) + G * 16, p + G, pol);
-  };
-#pragma unroll
-  for (int t = 0; t < R; ++t) {   // fill the ring: rows 0 .. R-1 (all inside the first batch, R <= G)
-    const int32_t cj = __shfl_sync(mask, c, t, G);
-    if (t < len) issue(cj, t);
-    cp_async_commit();
-  }
-  float4 acc[V];
-#pragma unroll
-  for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-  int32_t bq = 0;   // first row of the current batch
-  for (int32_t q = 0; q < len; ++q) {
-    if (q - bq == G) {   // the consumer enters the next batch: shift, prefetch the one after
-      bq += G;
-      c = c_nxt;
-      w = w_nxt;
-      if (bq + G + lane < len) {
-        c_nxt = ld_idx<HOT>(idx);
-        w_nxt = ld_val<HOT>(val);
-      }
-      idx += G;
-      val += G;
-    }
-    cp_async_wait<R - 1>();   // everything but the R - 1 youngest groups has landed: row q (and ACC_IN) are here
-    const float wq = __shfl_sync(mask, w, q - bq, G);
-    const float4 x0 = slots[(q & (R - 1)) * ROW4], x1 = slots[(q & (R - 1)) * ROW4 + G];
-    fma4(acc[0], wq, x0);
-    fma4(acc[1], wq, x1);
-    // refill the slot just consumed with row q + R (it may belong to the next batch)
-    const int32_t il = q + R - bq;   // in [R, G + R)
-    const int32_t cj = __shfl_sync(mask, il < G ? c : c_nxt, il & (G - 1), G);
-    if (q + R < len) issue(cj, q & (R - 1));
-    cp_async_commit();
-  }
-  if (plain) {
-    cp_async_wait<0>();   // (only matters for len == 0: ACC_IN may still be in flight)
-    // epilogue with ACC_IN taken from its slot
-    const int64_t row = wd.w;
-    const int64_t o = row * ROW4 + lane;
-    if (ps.rows_per > 0) {
-      const int owner = int(row / ps.rows_per);
-      float4* ypush = reinterpret_cast<float4*>(c_push_base[owner] + ps.off) +
-                      (int64_t(ps.rank) * ps.rows_per + (row - int64_t(owner) * ps.rows_per)) * ROW4 + lane;
-      ypush[0] = acc[0];
-      ypush[G] = acc[1];
-    }
-    if (Y != nullptr) {
-      st128_hint(Y + o, acc[0], pol_cold);
-      st128_hint(Y + o + G, acc[1], pol_cold);
-    }
-    if (ACC_OUT != nullptr) {
-      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-      if (have_acc) {
-        a0 = slots[R * ROW4];
-        a1 = slots[R * ROW4 + G];
-      }
-      st128_hint(ACC_OUT + o, scale4(add4(a0, acc[0]), acc_scale), pol_cold);
-      st128_hint(ACC_OUT + o + G, scale4(add4(a1, acc[1]), acc_scale), pol_cold);
-    }
-    return;
-  }
-  const int32_t k = wd.w;
-#pragma unroll
-  for (int v = 0; v < V; ++v) __stcg(partial + int64_t(item) * ROW4 + v * G + lane, acc[v]);
-  if (k < sc.n_huge) return;            // combined by k_spmm_finish
-  const int32_t c0 = __ldg(sc.chunk_ptr + k), c1 = __ldg(sc.chunk_ptr + k + 1);
-  __threadfence();                       // release: this group's partial is visible device-wide
-  __syncwarp(mask);
-  int prev = 0;
-  if (lane == 0) prev = atomicAdd(sc.arrive + k, 1);
-  prev = __shfl_sync(mask, prev, 0, G);
-  if (prev != c1 - c0 - 1) return;
-  __threadfence();                       // acquire: every other chunk's partial is visible
-#pragma unroll
-  for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int cc = c0; cc < c1; ++cc) {
-#pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = add4(acc[v], __ldcg(partial + int64_t(cc) * ROW4 + lane * V + v));
-  }
-  // (the sum of the partials is re-read in the register form's layout: 2 lane, 2 lane + 1)
   epilogue<G, V, HOT>(int64_t(__ldg(sc.perm + k)), lane, acc, Y, ACC_IN, ACC_OUT, acc_scale, acc_nz, ps);
   if (lane == 0) sc.arrive[k] = 0;       // self-resetting for the next launch
 }
@@ -583,59 +409,6 @@ static int launch_spmm(const cgx_csr* m, const float* val, const float* X, float
   return CGX_OK;
 }
 
-constexpr int RING_ROWS = 4;    // row slots per group (plus one for ACC_IN): 5 x 4d bytes of shared memory per group
-constexpr int RING_MINB = 5;    // CTAs per SM the register allocation must allow (48 registers)
-
-template <int G, int V, bool PUSH, bool HOT>
-static int launch_spmm_ring(const cgx_csr* m, const float* val, const float* X, float* Y, const float* ACC_IN,
-                            float* ACC_OUT, float acc_scale, void* workspace, size_t workspace_bytes,
-                            cudaStream_t stream, const uint8_t* acc_nz, const SpmmPush ps) {
-  constexpr int GROUPS = SP_THREADS / G;
-  constexpr size_t SMEM = size_t(GROUPS) * (RING_ROWS + 1) * G * V * sizeof(float4);
-  float4* partial = nullptr;
-  if (m->n_long > 0) {
-    size_t need = size_t(m->n_chunks) * G * V * sizeof(float4);
-    CGX_REQUIRE(workspace != nullptr && workspace_bytes >= need, CGX_ERR_WORKSPACE,
-                "spmm: workspace too small for %d long-row chunks", m->n_chunks);
-    partial = static_cast<float4*>(workspace);
-  }
-  auto kern = k_spmm_ring<G, V, RING_ROWS, RING_MINB, PUSH, HOT>;
-  if (SMEM > 48 * 1024) {   // opt-in above 48 KB, once per device (a bit per ordinal; also keeps it out of graph captures)
-    static std::atomic<unsigned long long> attr_set{0};
-    int dev = 0;
-    CGX_CUDA(cudaGetDevice(&dev));
-    const unsigned long long bit = 1ull << (dev & 63);
-    if (!(attr_set.load(std::memory_order_acquire) & bit)) {
-      CGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-      attr_set.fetch_or(bit, std::memory_order_release);
-    }
-  }
-  SpmmSched sc{m->perm, m->chunk_ptr, m->arrive, m->n_chunks, m->n_huge};
-  const int64_t items = int64_t(m->n_chunks) + (m->n_rows - m->n_long);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)ceil_div(items, GROUPS));
-  cfg.blockDim = dim3(SP_THREADS);
-  cfg.dynamicSmemBytes = SMEM;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = option(CGX_OPT_PDL) != 0 ? 1 : 0;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  CGX_CUDA(cudaLaunchKernelEx(&cfg, kern, HOT ? m->idx_hint : m->idx, val, items, sc,
-                              reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(Y),
-                              reinterpret_cast<const float4*>(ACC_IN), reinterpret_cast<float4*>(ACC_OUT), acc_scale,
-                              partial, acc_nz, static_cast<const int4*>(m->work), ps));
-  CGX_LAUNCH_CHECK();
-  if (m->n_huge > 0) {
-    k_spmm_finish<G, V><<<(unsigned)m->n_huge, SP_THREADS, 0, stream>>>(
-        sc, partial, reinterpret_cast<float4*>(Y), reinterpret_cast<const float4*>(ACC_IN),
-        reinterpret_cast<float4*>(ACC_OUT), acc_scale, acc_nz, ps);
-    CGX_LAUNCH_CHECK();
-  }
-  return CGX_OK;
-}
-
 #define CGX_SPMM_ARGS m, val, X, Y, ACC_IN, ACC_OUT, acc_scale, ws, ws_bytes, stream, nz, acc_nz, ps
 
 // Group geometry by regime (profiles/r1_spmm_variants.txt; the sweep itself lives in the round-1 history).
@@ -650,16 +423,6 @@ static int spmm_flavour(const cgx_csr* m, const float* val, const float* X, floa
                         const uint8_t* nz, const uint8_t* acc_nz, const SpmmPush ps, bool hot) {
   const bool push = ps.rows_per > 0;
   if constexpr (V == 2) {
-#define CGX_RING_ARGS m, val, X, Y, ACC_IN, ACC_OUT, acc_scale, ws, ws_bytes, stream, acc_nz, ps
-    if (nz == nullptr && option(CGX_OPT_SPMM_RING) != 0) {   // HBM-resident table: gathers staged through shared memory
-      if (hot) {
-        if (push) return launch_spmm_ring<G, V, true, true>(CGX_RING_ARGS);
-        return launch_spmm_ring<G, V, false, true>(CGX_RING_ARGS);
-      }
-      if (push) return launch_spmm_ring<G, V, true, false>(CGX_RING_ARGS);
-      return launch_spmm_ring<G, V, false, false>(CGX_RING_ARGS);
-    }
-#undef CGX_RING_ARGS
     if (hot && nz == nullptr) {
       if (push) return launch_spmm<G, V, UNR, 4, false, true, true>(CGX_SPMM_ARGS);
       return launch_spmm<G, V, UNR, 4, false, false, true>(CGX_SPMM_ARGS);

@@ -884,9 +884,22 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
         ev[1].record()
         torch.cuda.synchronize()
         xs.append(ev[0].elapsed_time(ev[1]))
-    t3 = torch.tensor([min(prop_f), min(prop_b), min(xs[1:])], device=dev)
+    ps = [0.0]
+    if getattr(step.ex, "push_enabled", lambda: False)():
+        # the pushed form's own part (barrier, local reduce of the staged rows, delivery, barrier) without a product
+        ps = []
+        for _ in range(4):
+            step.ex.begin_step()
+            dist.barrier()
+            ev[0].record()
+            step.ex.exchange_pushed(tuple(step.ei.shape), lambda *a: None)
+            ev[1].record()
+            torch.cuda.synchronize()
+            ps.append(ev[0].elapsed_time(ev[1]))
+        ps = ps[1:]
+    t3 = torch.tensor([min(prop_f), min(prop_b), min(xs[1:]), min(ps)], device=dev)
     dist.all_reduce(t3, op=dist.ReduceOp.MAX)
-    prop_f_ms, prop_b_ms, xchg_ms = (float(v) for v in t3.tolist())
+    prop_f_ms, prop_b_ms, xchg_ms, push_ms = (float(v) for v in t3.tolist())
     edges = torch.tensor([E_local], dtype=torch.int64, device=dev)
     dist.all_reduce(edges)
     nnz_t = torch.tensor([gr.nnz], dtype=torch.int64, device=dev)
@@ -942,8 +955,10 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
                            "achieved_gbs": link_bytes / (xchg_ms / 1e3) / 1e9, "peak_gbs": nvl_peak,
                            "frac": link_bytes / (xchg_ms / 1e3) / 1e9 / nvl_peak,
                            "exchanges_per_step": n_x, "exchange_share_of_step": n_x * xchg_ms / ms,
-                           "note": "one item-table exchange timed alone (reduce-scatter + all-gather over peer "
-                                   "memory), max over ranks"},
+                           "pushed_form_reduce_deliver_ms": push_ms if push_ms > 0 else None,
+                           "note": "exchange_ms: one item-table exchange timed alone in its stand-alone (pull / "
+                                   "collective) form, max over ranks; pushed_form_reduce_deliver_ms: what the pushed "
+                                   "form adds after the product (its reduce-scatter half rides on the SpMM epilogue)"},
             },
             "steps_per_epoch": steps_per_epoch, "epoch_ms": ms * steps_per_epoch,
             "epoch_ms_kind": f"extrapolated: {steps_per_epoch} steps x the timed mean step",

@@ -2,8 +2,7 @@
 
 Builds the synthetic graph on the device (the C4/C5 generator law), then times the item-row product (C x_u), the
 user-row product (A x_i, with the running-sum epilogue) and a whole forward + adjoint propagation with CUDA events,
-for the register form and the shared-memory ring form of the SpMM (CGX_OPT_SPMM_RING) and with / without the hot-row
-hints.  Used for the C5-shard shape (6.25M x 10M x 125M, d = 64): the per-rank products of the 8-GPU run."""
+with / without the hot-row hints.  Used for the C5-shard shape (6.25M x 10M x 125M, d = 64): the per-rank products of the 8-GPU run."""
 import json
 import pathlib
 import sys
@@ -42,9 +41,8 @@ def timed(fn, n=5):
 
 for hot in (1, 0):
     gr.set_emb_dim(d, hot_bytes=None if hot else 0)
-    for ring in (0, 1):
-        _lib.set_option("SPMM_RING", ring)
-        key = f"{'hot' if hot else 'nohot'}/{'ring' if ring else 'regs'}"
+    for _ in (0,):
+        key = "hot" if hot else "nohot"
         out[key] = {
             "item_rows_ms": timed(lambda: model.spmm(gr.by_item, xu)),
             "user_rows_ms": timed(lambda: model.spmm(gr.by_user, xi)),
@@ -54,5 +52,4 @@ for hot in (1, 0):
         r = 4 * d
         out[key]["item_rows_gather_model_gbs"] = (nnz * (8 + r) + I * r) / out[key]["item_rows_ms"] / 1e6
         out[key]["user_rows_gather_model_gbs"] = (nnz * (8 + r) + U * r) / out[key]["user_rows_ms"] / 1e6
-_lib.set_option("SPMM_RING", -1)
 print(json.dumps(out))

@@ -4,7 +4,7 @@
     C3  52,643 x 91,599 x 2.98 M, degree-aware operator, 4 layers, d = 64 (Degree-Aware Message.py:349-403, 424-442)
     C4s a C4-shaped 1/16 subsample (625,000 x 250,000 x 12.5 M, d = 128): both gathered tables exceed the 96 MiB
         regime switch WITHOUT forcing it, the hottest item row has > 16,384 non-zeros (finishing kernel), the hot-row
-        hints and the shared-memory ring form of the SpMM are the kernels that run.
+        hints are active in the kernels that run.
 
 Bars: graph arrays bit-exact; forward / loss / gradients of one injected 4096-triple batch <= 1e-4 relative;
 top-20 ids of 1,000 users identical except where the oracle's own fp32 scores tie to 1e-6."""
@@ -138,9 +138,9 @@ def test_c4_shaped_subsample_crosses_the_regime_switch_against_the_oracle(cg):
 
 @pytest.mark.parametrize("d", [64, 128, 256])
 def test_spmm_forms_give_identical_bits(cg, d):
-    """Register form / shared-memory ring form, with and without hot-row hints, and the L2-resident geometry all
-    add the same terms in the same order: every combination must reproduce the same bits -- plain and adjoint
-    products, zero-degree rows, chunked and huge rows, both propagation orders."""
+    """The HBM-resident geometry (32 bytes per lane, 256-bit accesses) with and without hot-row hints and the
+    L2-resident geometry all add the same terms in the same order: every combination must reproduce the same bits --
+    plain and adjoint products, zero-degree rows, chunked and huge rows, both propagation orders."""
     lib, m = cg["lib"], cg["model"]
     sg = cg["synth"].make_graph("C1", num_users=6000, num_items=900, num_edges=400_000, duplicate_edges=500)
     gr = cg["graph"].build_graph(sg.train_edges, sg.num_users, sg.num_items, sg.cred, "v2", DEV)
@@ -158,16 +158,16 @@ def test_spmm_forms_give_identical_bits(cg, d):
                 *m.propagate_backward(gr, gs, xi, 2, "jacobi"))
 
     want = run()                                  # L2-resident geometry, no hints
-    keep = {k: lib.get_option(k) for k in ("L2_TABLE_BYTES", "SPMM_RING", "HOT_ROWS")}
+    keep = {k: lib.get_option(k) for k in ("L2_TABLE_BYTES", "HOT_ROWS")}
     try:
         lib.set_option("L2_TABLE_BYTES", 0)       # every table counts as HBM-resident
-        for ring in (0, 1):
+        for use_hints in (1, 0):
             for n_hot in (0, 64):
-                lib.set_option("SPMM_RING", ring)
+                lib.set_option("HOT_ROWS", use_hints)
                 gr.by_user.set_hot_columns(gr.by_item.perm, n_hot)
                 gr.by_item.set_hot_columns(gr.by_user.perm, 8 * n_hot)
                 for a, b in zip(run(), want):
-                    assert torch.equal(a.view(torch.int32), b.view(torch.int32)), (ring, n_hot)
+                    assert torch.equal(a.view(torch.int32), b.view(torch.int32)), (use_hints, n_hot)
     finally:
         for k, v in keep.items():
             lib.set_option(k, v)
