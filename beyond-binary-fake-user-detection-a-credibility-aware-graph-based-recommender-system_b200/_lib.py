@@ -100,6 +100,8 @@ _SIGNATURES = {
                                      C.c_int64, _P, _P]),
     "cgx_comm_allgather": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p), _P, C.c_size_t, C.c_size_t, C.c_int64,
                                      _P, _P]),
+    "cgx_comm_allreduce_nvls": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p), _P, C.c_size_t, C.c_size_t,
+                                          C.c_size_t, C.c_int64, _P, _P]),
     "cgx_comm_timing": (C.c_int, [_P]),
     "cgx_spmm_set_push_peers": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     "cgx_spmm_push": (C.c_int, [_CSR, C.c_int, C.c_int32, _P, _P, C.c_size_t, C.c_int, C.c_int, C.c_int32, _P,

@@ -271,6 +271,79 @@ __global__ void __launch_bounds__(P2P_THREADS) k_p2p_reduce_pushed(P2PPeers peer
   if (dbg && threadIdx.x == 0) dbg[2] += p2p_now() - t2;
 }
 
+// NVLS form of the exchange: when the communication buffers are bound to one NVSwitch multicast object (mc_base;
+// torch symmetric memory sets that up), rank r reduces slice r with multimem.ld_reduce -- ONE load whose value is the
+// sum over all ranks' `in` regions, added inside the switch -- and delivers it with multimem.st -- ONE store the switch
+// replicates into every rank's `out` region.  Per exchange and direction a rank then moves ~S bytes over NVLink
+// (its partial out, the reduced table in) instead of 2 (R-1)/R S with peer loads + peer stores.  The order of the
+// in-switch sum is the switch's, not rank order: every rank receives the same bits, but they can differ in the last
+// place from the pull / pushed forms (tests compare this form by tolerance).
+__device__ __forceinline__ float4 multimem_ld_reduce(const float4* p) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st(float4* p, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(P2P_THREADS) k_nvls_allreduce(P2PPeers peers, char* mc_base, int rank, int world,
+                                                                size_t in_off, size_t out_off, size_t flag_off,
+                                                                int64_t n4,
+                                                                const unsigned long long* __restrict__ epoch_dev,
+                                                                unsigned long long timeout_ns) {
+  const uint32_t epoch = uint32_t(*epoch_dev);
+  uint32_t* my_flags = reinterpret_cast<uint32_t*>(peers.base[rank] + flag_off);
+  // ---- barrier A: all partials complete and visible ----
+  if (blockIdx.x == 0 && threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<uint32_t*>(peers.base[threadIdx.x] + flag_off) + rank, epoch);
+  }
+  if (threadIdx.x < world)
+    wait_flag(my_flags + threadIdx.x, epoch, timeout_ns, my_flags + 2 * world + 1, (1u << 8) | (threadIdx.x + 1));
+  __syncthreads();
+  const int64_t per = (n4 + world - 1) / world;
+  const int64_t lo = int64_t(rank) * per;
+  const int64_t hi = lo + per < n4 ? lo + per : n4;
+  const float4* src = reinterpret_cast<const float4*>(mc_base + in_off);
+  float4* dst = reinterpret_cast<float4*>(mc_base + out_off);
+  constexpr int NU = 4;
+  const int64_t stride = int64_t(gridDim.x) * P2P_THREADS;
+  for (int64_t i0 = lo + int64_t(blockIdx.x) * P2P_THREADS + threadIdx.x; i0 < hi; i0 += stride * NU) {
+    float4 v[NU];
+#pragma unroll
+    for (int t = 0; t < NU; ++t) {
+      const int64_t i = i0 + t * stride;
+      if (i < hi) v[t] = multimem_ld_reduce(src + i);
+    }
+#pragma unroll
+    for (int t = 0; t < NU; ++t) {
+      const int64_t i = i0 + t * stride;
+      if (i < hi) multimem_st(dst + i, v[t]);
+    }
+  }
+  // ---- barrier B: every slice delivered ----
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(my_flags + 2 * world, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x == 0) my_flags[2 * world] = 0;   // self-resetting
+  if (threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<uint32_t*>(peers.base[threadIdx.x] + flag_off) + world + rank, epoch);
+    wait_flag(my_flags + world + threadIdx.x, epoch, timeout_ns, my_flags + 2 * world + 1,
+              (2u << 8) | (threadIdx.x + 1));
+  }
+  __syncthreads();
+}
+
 // All-gather of one small block per rank (the compact loss gradient of the user-sharded step: <= 2 * batch item rows
 // per rank instead of two dense item tables).  Every rank stores its block into slot `rank` of the gather region of
 // EVERY rank (posted NVLink stores), the last CTA to finish signals the peers (the barrier-A flag slots: "rank p has
@@ -389,6 +462,31 @@ extern "C" int cgx_comm_allreduce_pushed(int rank, int world, void* const* peer_
   k_p2p_reduce_pushed<<<(unsigned)blocks, P2P_THREADS, 0, stream>>>(
       peers, rank, world, stage_off, out_off, flag_off, n_rows, d / 4, rows_per,
       reinterpret_cast<const unsigned long long*>(epoch_dev), p2p_timeout_ns(), dbg);
+  CGX_LAUNCH_CHECK();
+  return CGX_OK;
+}
+
+extern "C" int cgx_comm_allreduce_nvls(int rank, int world, void* const* peer_bases, void* mc_base, size_t in_off,
+                                       size_t out_off, size_t flag_off, int64_t n_floats, const uint64_t* epoch_dev,
+                                       void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CGX_REQUIRE(world >= 1 && world <= P2P_MAX_RANKS && rank >= 0 && rank < world && peer_bases && mc_base, CGX_ERR_ARG,
+              "comm_allreduce_nvls: bad rank/world or no multicast mapping");
+  CGX_REQUIRE(n_floats > 0 && n_floats % 4 == 0 && in_off % 16 == 0 && out_off % 16 == 0 && flag_off % 16 == 0 &&
+                  epoch_dev != nullptr,
+              CGX_ERR_ARG, "comm_allreduce_nvls: bad sizes/offsets");
+  P2PPeers peers;
+  for (int p = 0; p < world; ++p) {
+    CGX_REQUIRE(peer_bases[p] != nullptr, CGX_ERR_ARG, "comm_allreduce_nvls: NULL peer buffer");
+    peers.base[p] = static_cast<char*>(peer_bases[p]);
+  }
+  const int64_t n4 = n_floats / 4;
+  int64_t blocks = ceil_div(ceil_div(n4, world), P2P_THREADS * 4);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  k_nvls_allreduce<<<(unsigned)blocks, P2P_THREADS, 0, stream>>>(
+      peers, static_cast<char*>(mc_base), rank, world, in_off, out_off, flag_off, n4,
+      reinterpret_cast<const unsigned long long*>(epoch_dev), p2p_timeout_ns());
   CGX_LAUNCH_CHECK();
   return CGX_OK;
 }

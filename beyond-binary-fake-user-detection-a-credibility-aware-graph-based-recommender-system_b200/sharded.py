@@ -98,8 +98,10 @@ class P2PExchange:
 
     REGION_ALIGN = 1 << 16
 
-    def __init__(self, max_floats: int, device, group=None, gather_floats: int = 0):
-        """max_floats: largest table exchanged; gather_floats: largest per-rank block of allgather().
+    def __init__(self, max_floats: int, device, group=None, gather_floats: int = 0, backing: str = "auto"):
+        """max_floats: largest table exchanged; gather_floats: largest per-rank block of allgather(); backing: "auto"
+        = torch symmetric memory when it is available (it also provides the NVSwitch multicast mapping of the NVLS
+        exchange), else cudaMalloc + cudaIpc handles ("ipc" forces the latter).
         Collective over `group`: EVERY rank issues the same sequence of torch.distributed calls whether or not
         its own CUDA calls succeed (a failure is agreed on after each phase and raised on all ranks together), so a
         rank without peer access can never leave the others waiting inside a mismatched collective."""
@@ -116,11 +118,9 @@ class P2PExchange:
         self.bases = (C.c_void_p * self.world)()
         self._opened = []
         handle = (C.c_char * 64)()
-        err = None
 
-        def agree(phase):
+        def agree(phase, err):
             """All ranks learn whether ANY rank failed `phase`; all raise together."""
-            nonlocal err
             bad = torch.tensor([0.0 if err is None else 1.0], device=self.device)
             if self.world > 1:
                 dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=group)
@@ -129,13 +129,68 @@ class P2PExchange:
                 raise _lib.CgxError(f"P2PExchange: {phase} failed on " +
                                     (f"this rank: {err}" if err is not None else "another rank"))
 
+        self.mc = 0                 # multicast (NVSwitch) mapping of the buffers: 0 = none (IPC backing)
+        self._symm = None
+        self.bytes = None
+        if backing in ("auto", "symm") and self.world > 1:
+            self._try_symmetric_memory(total, group, agree_soft=lambda bad: self._any(bad, group))
+        if self._symm is None:
+            self._ipc_backing(total, group, handle, agree)
+        self.epoch_dev = torch.zeros(1, dtype=torch.int64, device=self.device)   # exchanges done so far
+        self.slot = 0                                                          # region of the next exchange
+        if self.world > 1:
+            dist.barrier(group=group)          # every rank has mapped every buffer before the first exchange
+
+    def _any(self, bad: bool, group) -> bool:
+        t = torch.tensor([1.0 if bad else 0.0], device=self.device)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        return t.item() != 0
+
+    def _try_symmetric_memory(self, total, group, agree_soft):
+        """Back the buffers with torch symmetric memory: peer mappings AND -- where the fabric has it -- one NVSwitch
+        multicast mapping, which the NVLS form of the exchange needs.  Any failure on any rank (agreed after each
+        phase) leaves every rank on the cudaIpc backing."""
+        import ctypes as C
+        t = hdl = None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            t = symm.empty(int(total), dtype=torch.uint8, device=self.device)
+        except Exception as e:                      # noqa: BLE001
+            self._symm_error = f"{type(e).__name__}: {e}"
+        if agree_soft(t is None):
+            return
+        try:
+            hdl = symm.rendezvous(t, group if group is not None else dist.group.WORLD)
+            ptrs = [int(x) for x in hdl.buffer_ptrs]
+            mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+            assert len(ptrs) == self.world and all(ptrs)
+        except Exception as e:                      # noqa: BLE001
+            self._symm_error = f"{type(e).__name__}: {e}"
+            hdl = None
+        if agree_soft(hdl is None):
+            return
+        if agree_soft(mc == 0):                     # multicast on every rank or on none
+            mc = 0
+        t.zero_()
+        for r in range(self.world):
+            self.bases[r] = ptrs[r]
+        self.base = C.c_void_p(ptrs[self.rank])
+        self.bytes, self._symm, self.mc = t, (t, hdl), mc
+        with torch.cuda.device(self.device):
+            check(lib().cgx_spmm_set_push_peers(self.bases, self.world))
+            torch.cuda.synchronize(self.device)
+
+    def _ipc_backing(self, total, group, handle, agree):
+        import ctypes as C
+        err = None
         with torch.cuda.device(self.device):
             try:                                    # phase 1: allocate + export
                 check(lib().cgx_comm_alloc(total, C.byref(self.base)))
                 check(lib().cgx_comm_ipc_handle(self.base, handle))
             except Exception as e:                  # noqa: BLE001
                 err = f"{type(e).__name__}: {e}"
-            agree("allocating the communication buffer")
+            agree("allocating the communication buffer", err)
             handles = [None] * self.world
             if self.world > 1:                      # outside any try: every rank takes part
                 dist.all_gather_object(handles, bytes(handle.raw), group=group)
@@ -151,12 +206,8 @@ class P2PExchange:
                 check(lib().cgx_spmm_set_push_peers(self.bases, self.world))   # targets of the fused product + exchange
             except Exception as e:                  # noqa: BLE001
                 err = f"{type(e).__name__}: {e}"
-            agree("mapping the peers' buffers (no NVLink / IPC peer access?)")
+            agree("mapping the peers' buffers (no NVLink / IPC peer access?)", err)
         self.bytes = torch.as_tensor(_RawCuda(self.base.value, total), device=self.device)
-        self.epoch_dev = torch.zeros(1, dtype=torch.int64, device=self.device)   # exchanges done so far
-        self.slot = 0                                                          # region of the next exchange
-        if self.world > 1:
-            dist.barrier(group=group)          # every rank has mapped every buffer before the first exchange
 
     def check(self):
         """Raise if a cross-GPU barrier of an exchange timed out (a peer died or lost step): the kernels then gave up
@@ -175,6 +226,10 @@ class P2PExchange:
     def close(self):
         """Unmap the peers' buffers and free the own one (after all ranks are done with the exchange)."""
         self.bytes = None
+        if self._symm is not None:                  # symmetric memory: torch owns the mappings
+            torch.cuda.synchronize(self.device)
+            self._symm, self.base, self.mc = None, None, 0
+            return
         with torch.cuda.device(self.device):
             torch.cuda.synchronize(self.device)
             for peer in self._opened:
@@ -198,7 +253,7 @@ class P2PExchange:
             raise _lib.CgxError("P2PExchange: payload larger than the communication regions")
         return self._view(self.slot * self.region, shape)
 
-    def push_enabled(self) -> bool:
+    def push_enabled(self, avg_row_nnz=None) -> bool:
         """Fused SpMM -> owner push + local reduce (cgx_spmm_push / cgx_comm_allreduce_pushed): the default above
         2 ranks (C2 shards, 4 ranks: 0.896 vs 0.975 ms/step) and for tables of 64 MB and more at any rank count (the
         reduce-scatter half then hides under the product).  At 2 ranks and 10 MB tables the one-shot pull kernel has
@@ -206,7 +261,15 @@ class P2PExchange:
         if self.force_push is not None:
             return self.world > 1 and bool(self.force_push)
         env = os.environ.get("CGX_P2P_PUSH")
-        return self.world > 1 and (env == "1" or (env is None and (self.world > 2 or self.region >= (64 << 20))))
+        if env is not None or self.world < 2:
+            return self.world > 1 and env == "1"
+        if self.region < (64 << 20):                # small tables: latency-bound exchange
+            return self.world > 2
+        # large tables: pushing pays while the product is long next to the table it produces -- its posted stores
+        # need (R-1)/R x table bytes of NVLink per product time.  C4 shards (80 non-zeros per item row) gain
+        # (134.6 vs 137.8 ms at 2 ranks); C5 shards (10 per row, 256-byte rows) lose badly: the product itself becomes
+        # NVLink-bound (134.5 ms per step pushed vs 97.6 pulled vs 85.8 NCCL at 8 ranks).
+        return avg_row_nnz is None or avg_row_nnz >= 32
 
     force_push = None       # True / False overrides the default choice (tests)
 
@@ -242,6 +305,13 @@ class P2PExchange:
         out = self.bytes[self.gather_off: self.gather_off + self.world * nbytes].view(torch.float32)
         return out.view(self.world, nbytes // 4)[:, : block.numel()]
 
+    use_nvls = None         # None: NVLS form for tables of 8 MB and more when a multicast mapping exists; True / False force
+
+    def nvls_enabled(self, nbytes: int) -> bool:
+        if not self.mc or self.world < 2:
+            return False
+        return bool(self.use_nvls) if self.use_nvls is not None else nbytes >= (8 << 20)
+
     def reduce(self, buf):
         par = self.slot
         self.slot ^= 1
@@ -249,6 +319,12 @@ class P2PExchange:
         with torch.cuda.device(self.device):
             st = stream_ptr(self.device)
             check(lib().cgx_tick(ptr(self.epoch_dev), st))
+            if self.nvls_enabled(4 * n_pad):
+                import ctypes as C
+                check(lib().cgx_comm_allreduce_nvls(self.rank, self.world, self.bases, C.c_void_p(self.mc),
+                                                    par * self.region, (2 + par) * self.region, self.flag_off, n_pad,
+                                                    ptr(self.epoch_dev), st))
+                return self._view((2 + par) * self.region, tuple(buf.shape))
             check(lib().cgx_comm_allreduce(self.rank, self.world, self.bases, par * self.region,
                                            (2 + par) * self.region, self.flag_off, n_pad, ptr(self.epoch_dev), st))
         return self._view((2 + par) * self.region, tuple(buf.shape))
@@ -348,6 +424,14 @@ class ShardedPropagation:
         self.b, self.K, self.order, self.group = backend, int(num_layers), order, group
         self.ex = exchange or CollectiveExchange(group)
 
+    def _push(self) -> bool:
+        fn = getattr(self.ex, "push_enabled", None)
+        if fn is None:
+            return False
+        g = getattr(self.b, "graph", None)
+        avg = (g.by_item.nnz / max(g.by_item.n_rows, 1)) if g is not None else None
+        return fn(avg)
+
     def _flags_ok(self):
         return getattr(self.b, "supports_row_flags", False)
 
@@ -359,7 +443,7 @@ class ShardedPropagation:
         """Partial item table of this shard -> whole item table (one exchange).  sparse: x_u is the loss
         gradient itself (rows mostly zero; x_flags = its row flags when the caller has them)."""
         fl = {"x_flags": x_flags} if (sparse and x_flags is not None and self._flags_ok()) else {}
-        if hasattr(self.b, "item_rows_push") and getattr(self.ex, "push_enabled", lambda: False)():
+        if hasattr(self.b, "item_rows_push") and self._push():
             return self.ex.exchange_pushed(
                 shape, lambda off, rank, world, rows_per: self.b.item_rows_push(x_u, bwd, off, rank, world, rows_per,
                                                                               sparse, **fl))
@@ -778,10 +862,27 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
         dist.barrier()
         par_ex.close()
 
-    if strong:      # BASELINE configs[4]: THE 50M x 10M x 1B-edge graph, its users split over the ranks
-        sg = synth.make_graph_device("C5", dev, num_users=shp["num_users"] // world,
-                                     num_edges=shp["num_edges"] // world, seed=20240 + 1000 * (rank + 1),
-                                     item_seed=20242)
+    if strong:
+        # BASELINE configs[4]: THE 50M x 10M x 1B-edge graph.  Every rank generates the same seeded graph on its own
+        # GPU, partition_users cuts the users into `world` contiguous ranges of equal non-zeros, and the rank keeps
+        # the edges (ids rebased), credibilities and test edges of its range.
+        full = synth.make_graph_device("C5", dev)
+        deg_all = torch.bincount(full.train_edges[0].to(torch.int64), minlength=full.num_users)
+        bounds = partition_users(deg_all.cpu().numpy(), world)
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        del deg_all
+
+        def mine(e):
+            keep = (e[0] >= lo) & (e[0] < hi)
+            out = e[:, keep].clone()
+            out[0] -= lo
+            return out
+
+        sg = synth.SynthGraph(name="C5", num_users=hi - lo, num_items=full.num_items, train_edges=mine(full.train_edges),
+                              val_edges=full.val_edges[:, :0], test_edges=mine(full.test_edges),
+                              cred=full.cred[lo:hi].contiguous(), is_fake=full.is_fake[lo:hi], meta=dict(full.meta))
+        del full
+        torch.cuda.empty_cache()
     elif name == "C4":
         sg = synth.make_graph_device(name, dev, seed=20240 + 1000 * (rank + 1), item_seed=20242)
     else:
@@ -885,7 +986,8 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
         torch.cuda.synchronize()
         xs.append(ev[0].elapsed_time(ev[1]))
     ps = [0.0]
-    if getattr(step.ex, "push_enabled", lambda: False)():
+    pushed = step.prop._push()
+    if pushed:
         # the pushed form's own part (barrier, local reduce of the staged rows, delivery, barrier) without a product
         ps = []
         for _ in range(4):
@@ -938,8 +1040,10 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
             "loss": loss_host,
             "collectives_per_step": f"{2 * K} item-table exchanges + 1 all-gather of the compact loss gradient",
             "cuda_graph": graphed, "exchange": type(step.ex).__name__ +
-            (" (rows pushed from the SpMM epilogue + local reduce)" if getattr(step.ex, "push_enabled", lambda: False)()
-             else ""),
+            (" (rows pushed from the SpMM epilogue + local reduce)" if pushed else
+             " (NVLS: multimem.ld_reduce / multimem.st through the switch)" if
+             (getattr(step.ex, "nvls_enabled", lambda n: False)(4 * step.ei.numel())) else
+             " (pull kernel)" if isinstance(step.ex, P2PExchange) else ""),
             "parity_vs_1gpu": parity, "parity_vs_1gpu_detail": {k: float(v) for k, v in parity_detail.items()},
             "roofline": {
                 "bound": "hbm + nvlink", "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,

@@ -335,6 +335,13 @@ int cgx_comm_ipc_close(void* peer_base);
 int cgx_comm_allreduce(int rank, int world, void* const* peer_bases, size_t in_off, size_t out_off,
                        size_t flag_off, int64_t n_floats, const uint64_t* epoch_dev, void* stream);
 int cgx_comm_status(const void* base, size_t flag_off, int world, uint32_t* error_out);
+/* The same exchange through the NVSwitch (NVLS): the `world` buffers must be bound to one multicast object whose
+ * mapping is mc_base (same offsets as the unicast mappings in peer_bases; e.g. torch symmetric memory).  Rank r sums
+ * slice r inside the switch (multimem.ld_reduce) and the switch replicates the result into every rank's out region
+ * (multimem.st): about half the NVLink traffic of the pull form.  Every rank receives identical bits; the order of
+ * the in-switch sum is the switch's, so the last place may differ from cgx_comm_allreduce. */
+int cgx_comm_allreduce_nvls(int rank, int world, void* const* peer_bases, void* mc_base, size_t in_off,
+                            size_t out_off, size_t flag_off, int64_t n_floats, const uint64_t* epoch_dev, void* stream);
 /* All-gather of one block of bytes_per_rank bytes (16-byte granularity) per rank: block `rank` is read from the
  * local device pointer src and lands at byte offset dst_off + rank * bytes_per_rank of EVERY rank's buffer; returns
  * when all `world` blocks are local.  One epoch tick like the all-reduces.  Used for the compact loss gradient of the

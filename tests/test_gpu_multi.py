@@ -35,20 +35,30 @@ def _worker(rank, world, port, out):
                           gather_floats=ShardedTrainStep._block_floats(2048, d))
         for variant, order in (("v2", "gs"), ("cu", "jacobi"), ("da", "gs")):
             outs = {}
-            for ex_name, ex, push in (("nccl", CollectiveExchange(), None), ("p2p", p2p, False), ("p2p_push", p2p, True)):
-                p2p.force_push = push
+            cases = [("nccl", CollectiveExchange(), None, False), ("p2p", p2p, False, False),
+                     ("p2p_push", p2p, True, False)]
+            if p2p.mc:                        # NVSwitch multicast mapping available: the NVLS form of the exchange
+                cases.append(("p2p_nvls", p2p, False, True))
+            for ex_name, ex, push, nvls in cases:
+                p2p.force_push, p2p.use_nvls = push, nvls
                 worst, errs, tensors = parity_vs_single_gpu(rank, world, dev, variant, order, exchange=ex)
                 outs[ex_name] = [t.clone() for t in tensors]
                 res[f"{variant}/{ex_name}"] = worst
-            p2p.force_push = None
-            # the pull kernel and the pushed form add the partials in rank order: identical bits; NCCL's order is
-            # only the same at two ranks
+            p2p.force_push, p2p.use_nvls = None, None
+            # the pull kernel and the pushed form add the partials in rank order: identical bits; NCCL's order (and
+            # the switch's, in the NVLS form) is only the same at two ranks
             same = all(torch.equal(a, b) for a, b in zip(outs["p2p"], outs["p2p_push"]))
             if world == 2:
                 same = same and all(torch.equal(a, b) for a, b in zip(outs["nccl"], outs["p2p"]))
+                if "p2p_nvls" in outs:
+                    same = same and all(torch.equal(a, b) for a, b in zip(outs["p2p_nvls"], outs["p2p"]))
             flag = torch.tensor([1.0 if same else 0.0], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             res[f"{variant}/bitwise"] = 0.0 if flag.item() == 1.0 else 1.0
+        res["nvls_cases_ran"] = 0.0
+        if rank == 0:
+            print(f"[multi] world={world} backing={'symmetric memory' if p2p._symm is not None else 'cudaIpc'} "
+                  f"multicast={'yes' if p2p.mc else 'no'}", flush=True)
         p2p.check()
 
         # user-sharded full-rank evaluation == single-GPU evaluation of the whole graph
