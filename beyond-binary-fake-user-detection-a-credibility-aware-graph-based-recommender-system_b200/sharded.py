@@ -305,12 +305,20 @@ class P2PExchange:
         out = self.bytes[self.gather_off: self.gather_off + self.world * nbytes].view(torch.float32)
         return out.view(self.world, nbytes // 4)[:, : block.numel()]
 
-    use_nvls = None         # None: NVLS form for tables of 8 MB and more when a multicast mapping exists; True / False force
+    use_nvls = None         # None: automatic (below); True / False force it on / off (CGX_P2P_NVLS=1 / 0 likewise)
 
     def nvls_enabled(self, nbytes: int) -> bool:
+        """NVLS form of reduce(): needs the multicast mapping.  Automatic choice: tables of 64 MB and more on 4+
+        ranks -- at 2 ranks the one-shot pull kernel moves the same bytes per direction and is faster (2.56 GB:
+        3.84 vs 6.46 ms), and small tables are latency-bound (9.7 MB: 36 vs 54 us)."""
         if not self.mc or self.world < 2:
             return False
-        return bool(self.use_nvls) if self.use_nvls is not None else nbytes >= (8 << 20)
+        if self.use_nvls is not None:
+            return bool(self.use_nvls)
+        env = os.environ.get("CGX_P2P_NVLS")
+        if env is not None:
+            return env == "1"
+        return self.world >= 4 and nbytes >= (64 << 20)
 
     def reduce(self, buf):
         par = self.slot
@@ -530,6 +538,8 @@ class ShardedTrainStep:
         I, d = self.ei.shape
         self.max_batch = int(max_batch)
         self.ex = None
+        if exchange == "auto":
+            exchange = self.choose_exchange(graph, I, d, _world(group))
         if not isinstance(exchange, str):          # an exchange object made by the caller (tests share one)
             self.ex = exchange
         elif exchange == "p2p" and _world(group) > 1:
@@ -559,6 +569,19 @@ class ShardedTrainStep:
         self.tick = torch.zeros(1, dtype=torch.int64, device=dev)
         self._bufs = {}
         self._graph = None
+
+    # Exchange for tables of 256 MB and more whose item rows are short (C5 shards: 10 non-zeros per row -- the pushed
+    # form makes the product NVLink-bound there): measured on 8 B200s, C5, ms per step: pushed 134.5, pull kernel
+    # 97.6, NCCL (NVLS inside) 85.8, this library's NVLS kernel: see DESIGN.md section 6.
+    BIG_SHORT_ROWS_EXCHANGE = "p2p"
+
+    @classmethod
+    def choose_exchange(cls, graph, I, d, world) -> str:
+        if world < 2:
+            return "p2p"
+        big = I * d * 4 >= (256 << 20)
+        short = graph.by_item.nnz / max(graph.by_item.n_rows, 1) < 32
+        return cls.BIG_SHORT_ROWS_EXCHANGE if (big and short) else "p2p"
 
     @staticmethod
     def _block_floats(B: int, d: int) -> int:
@@ -846,11 +869,11 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
     name = args.workload or "C4"
     shp = synth.SHAPES[name]
     strong = name == "C5"
-    ex_kind = os.environ.get("CGX_EXCHANGE", "p2p")
+    ex_kind = os.environ.get("CGX_EXCHANGE", "auto")
 
     # ---- parity of this very exchange against the single-GPU path, before anything is timed ----
     par_ex = None
-    if ex_kind == "p2p":
+    if ex_kind in ("p2p", "auto"):
         try:
             par_ex = P2PExchange(2 * synth.SHAPES["C1"]["num_items"] * 64 + 4, dev,
                                  gather_floats=ShardedTrainStep._block_floats(2048, 64))
