@@ -132,3 +132,39 @@ def test_shard_edges_and_partition_cover_the_graph():
         assert total == sg.train_edges.shape[1]
         nnz = [int(deg_u[bounds[r]:bounds[r + 1]].sum()) for r in range(world)]
         assert max(nnz) - min(nnz) <= 2 * int(deg_u.max())                  # balanced by non-zeros, not by users
+
+
+def test_exchange_selection_rules():
+    """Host-side policy of the multi-GPU exchange, without a GPU: which form a table takes."""
+    from types import SimpleNamespace
+    from credgcn import sharded
+
+    def ex(world, region_mb, mc=1):
+        e = sharded.P2PExchange.__new__(sharded.P2PExchange)          # policy methods only: no buffers
+        e.world, e.region, e.mc, e.force_push, e.use_nvls = world, region_mb << 20, mc, None, None
+        return e
+
+    import os
+    os.environ.pop("CGX_P2P_PUSH", None)
+    os.environ.pop("CGX_P2P_NVLS", None)
+    # small tables: pull at 2 ranks, pushed above
+    assert not ex(2, 10).push_enabled(33) and ex(4, 10).push_enabled(33)
+    # large tables: pushed while the item rows are long (C4 shards: 80 per row), not for short rows (C5 shards: 10)
+    assert ex(2, 1024).push_enabled(80) and ex(8, 1024).push_enabled(80) and not ex(8, 2560).push_enabled(10)
+    assert ex(8, 2560).push_enabled(None)                              # unknown row length: the old default
+    # NVLS form: needs the multicast mapping, 4+ ranks and a large table; forced on / off by use_nvls
+    assert ex(8, 2560).nvls_enabled(2560 << 20) and not ex(2, 2560).nvls_enabled(2560 << 20)
+    assert not ex(8, 2560, mc=0).nvls_enabled(2560 << 20) and not ex(8, 10).nvls_enabled(10 << 20)
+    e = ex(2, 10)
+    e.use_nvls = True
+    assert e.nvls_enabled(1 << 20)
+    e.force_push = True
+    assert e.push_enabled(1)
+    # whole-step choice: big table + short rows -> the configured exchange, everything else the peer-memory one
+    g = SimpleNamespace(by_item=SimpleNamespace(nnz=100_000_000, n_rows=10_000_000))
+    assert sharded.ShardedTrainStep.choose_exchange(g, 10_000_000, 64, 8) == sharded.ShardedTrainStep.BIG_SHORT_ROWS_EXCHANGE
+    g4 = SimpleNamespace(by_item=SimpleNamespace(nnz=160_000_000, n_rows=2_000_000))
+    assert sharded.ShardedTrainStep.choose_exchange(g4, 2_000_000, 128, 8) == "p2p"
+    assert sharded.ShardedTrainStep.choose_exchange(g, 10_000_000, 64, 1) == "p2p"
+    # compact loss-gradient block: rows | coefficients | row ids | loss, the same size on every rank
+    assert sharded.ShardedTrainStep._block_floats(4096, 128) == 2 * 4096 * 130 + 4
