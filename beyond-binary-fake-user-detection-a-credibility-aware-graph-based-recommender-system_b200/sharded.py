@@ -98,14 +98,19 @@ class P2PExchange:
 
     REGION_ALIGN = 1 << 16
 
-    def __init__(self, max_floats: int, device, group=None, gather_floats: int = 0, backing: str = "auto"):
-        """max_floats: largest table exchanged; gather_floats: largest per-rank block of allgather(); backing: "auto"
-        = torch symmetric memory when it is available (it also provides the NVSwitch multicast mapping of the NVLS
-        exchange), else cudaMalloc + cudaIpc handles ("ipc" forces the latter).
+    # Backing of the communication buffers: "ipc" = cudaMalloc + cudaIpc handles; "symm" / "auto" = torch symmetric
+    # memory (peer mappings + the NVSwitch multicast mapping the NVLS form needs), falling back to "ipc" when any rank
+    # cannot.  CGX_P2P_BACKING overrides the default.
+    DEFAULT_BACKING = "ipc"
+
+    def __init__(self, max_floats: int, device, group=None, gather_floats: int = 0, backing: str | None = None):
+        """max_floats: largest table exchanged; gather_floats: largest per-rank block of allgather(); backing: see
+        DEFAULT_BACKING.
         Collective over `group`: EVERY rank issues the same sequence of torch.distributed calls whether or not
         its own CUDA calls succeed (a failure is agreed on after each phase and raised on all ranks together), so a
         rank without peer access can never leave the others waiting inside a mismatched collective."""
         import ctypes as C
+        backing = backing or os.environ.get("CGX_P2P_BACKING", self.DEFAULT_BACKING)
         self.group, self.device = group, torch.device(device)
         self.world = _world(group)
         self.rank = dist.get_rank(group) if self.world > 1 else 0

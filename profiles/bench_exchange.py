@@ -8,7 +8,7 @@ dist.init_process_group("nccl", device_id=dev)
 from credgcn.sharded import P2PExchange, CollectiveExchange
 out = {}
 for n in (38048 * 64, 2_000_000 * 128, 10_000_000 * 64):
-    p2p = P2PExchange(n, dev)
+    p2p = P2PExchange(n, dev, backing="auto")
     cases = [("p2p_pull", p2p, False), ("nccl", CollectiveExchange(), None)] + ([("p2p_nvls", p2p, True)] if p2p.mc else [])
     for name, ex, nvls in cases:
         p2p.use_nvls = nvls

@@ -31,7 +31,7 @@ def _worker(rank, world, port, out):
                                      parity_vs_single_gpu, partition_users, shard_edges)
         I, d = synth.SHAPES["C1"]["num_items"], 64
         res = {}
-        p2p = P2PExchange(2 * I * d + 4, dev,         # NVLink peer-memory exchange (csrc/comm.cu)
+        p2p = P2PExchange(2 * I * d + 4, dev, backing="auto",   # NVLink peer-memory exchange (csrc/comm.cu)
                           gather_floats=ShardedTrainStep._block_floats(2048, d))
         for variant, order in (("v2", "gs"), ("cu", "jacobi"), ("da", "gs")):
             outs = {}
