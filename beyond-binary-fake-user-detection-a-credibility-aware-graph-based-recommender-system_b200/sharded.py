@@ -549,10 +549,12 @@ class ShardedTrainStep:
             self.ex = exchange
         elif exchange == "p2p" and _world(group) > 1:
             # peer mapping can be unavailable (no NVLink/IPC between the ranks): P2PExchange agrees on the outcome
-            # over `group` and raises on ALL ranks together, which then all use the collective exchange
+            # over `group` and raises on ALL ranks together, which then all use the collective exchange.
+            # Big tables with short item rows take the NVLS form, which needs the multicast mapping of symmetric memory.
             try:
                 self.ex = P2PExchange((I + _world(group)) * d, dev, group,
-                                      gather_floats=self._block_floats(self.max_batch, d))
+                                      gather_floats=self._block_floats(self.max_batch, d),
+                                      backing="auto" if self.wants_nvls(graph, I, d, _world(group)) else None)
             except _lib.CgxError as e:
                 self._p2p_error = str(e)
         if self.ex is None:
@@ -575,10 +577,16 @@ class ShardedTrainStep:
         self._bufs = {}
         self._graph = None
 
-    # Exchange for tables of 256 MB and more whose item rows are short (C5 shards: 10 non-zeros per row -- the pushed
-    # form makes the product NVLink-bound there): measured on 8 B200s, C5, ms per step: pushed 134.5, pull kernel
-    # 97.6, NCCL (NVLS inside) 85.8, this library's NVLS kernel: see DESIGN.md section 6.
+    # Tables of 256 MB and more whose item rows are short (C5 shards: 10 non-zeros per row -- the pushed form makes
+    # the product NVLink-bound there).  Measured on 8 B200s, C5, ms per step: pushed 134.5, pull kernel 97.6, NCCL 85.8,
+    # this library's NVLS kernel (inside the CUDA graph) 85.4 -- so the peer-memory exchange stays, in its NVLS form.
     BIG_SHORT_ROWS_EXCHANGE = "p2p"
+
+    @staticmethod
+    def wants_nvls(graph, I, d, world) -> bool:
+        big = I * d * 4 >= (256 << 20)
+        short = graph.by_item.nnz / max(graph.by_item.n_rows, 1) < 32
+        return world >= 4 and big and short
 
     @classmethod
     def choose_exchange(cls, graph, I, d, world) -> str:
