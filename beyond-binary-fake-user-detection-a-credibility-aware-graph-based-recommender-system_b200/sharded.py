@@ -7,8 +7,9 @@ The reference is single-device; this is the row partition BASELINE.json names (S
   * the item table is replicated;
   * user <- item products (A x_i, C^T x_i) read the replicated item table: no communication;
   * item <- user products (C x_u, A^T x_u) give every rank a PARTIAL item table (the sum over its own
-    users); one all-reduce (NCCL over NVLink; reduce-scatter + all-gather inside) per layer makes
-    it whole again.  Forward: K all-reduces of [I, d]; backward: K + 1.
+    users); one exchange per layer makes it whole again (csrc/comm.cu over NVLink peer memory: pushed / pull /
+    NVLS form, or a torch.distributed all-reduce).  Forward: K exchanges of [I, d]; backward: K, plus ONE
+    all-gather of the compact loss gradient (the <= 2 * batch item rows each rank's triples touched).
   * evaluation is user-sharded with no exchange (only metric sums are reduced).
 
 `ShardedPropagation` is written against a two-method backend so that the host-side schedule can
@@ -92,9 +93,11 @@ class _RawCuda:
 
 
 class P2PExchange:
-    """Same contract over NVLink peer memory (csrc/comm.cu): partials are written straight into a
-    peer-mapped buffer and summed in rank order by one two-shot pull kernel.  Needs all ranks on one node
-    with peer access (NVSwitch); the process group is only used once, to hand out the IPC handles."""
+    """Same contract over NVLink peer memory (csrc/comm.cu): partials are written straight into a peer-mapped
+    buffer and summed by a kernel of the library -- in rank order by the pull kernel (one- or two-shot) or, when the
+    product pushed its rows to their owners, by the pushed form; inside the NVSwitch by the NVLS form when the
+    buffers have a multicast mapping.  Needs all ranks on one node with peer access (NVSwitch); the process group is
+    only used to hand out the mappings and to agree on failures."""
 
     REGION_ALIGN = 1 << 16
 
