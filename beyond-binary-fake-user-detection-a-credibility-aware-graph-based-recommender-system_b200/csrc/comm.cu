@@ -29,6 +29,13 @@
 //     this kernel has completed.
 //   * above 2 ranks the propagation uses the PUSHED form (k_p2p_reduce_pushed, below): the SpMM epilogue has already
 //     stored every partial row into its owner's staging slot, so the reduce needs local loads only.
+//   * large tables whose item rows are short (C5 shards) take the NVLS form (k_nvls_allreduce): slice r is summed
+//     INSIDE the NVSwitch by multimem.ld_reduce on a multicast mapping of the `in` regions and replicated into every
+//     `out` region by multimem.st -- about half the NVLink bytes of the pull form, level with NCCL at 2.56 GB.
+//   * the loss gradient of the sharded step travels as one small all-gather (k_p2p_allgather: <= 2 * batch item rows
+//     per rank, posted stores into every rank's gather region + one barrier).
+//   * every cross-GPU wait is bounded (wait_flag, CGX_OPT_P2P_TIMEOUT_MS): a dead peer turns into an error word
+//     the host can read (cgx_comm_status), not into eight GPUs spinning inside a replayed graph.
 //   * the epoch is a device-side counter (cgx_tick before every exchange) that advances identically on all
 //     ranks (the propagation schedule is deterministic), so a whole step can be replayed as a CUDA graph.
 #include <stdlib.h>

@@ -5,22 +5,24 @@
 // Version-2/lighgcn_cu_pop.py:483-484, the stack().mean() at lightgcn_cu.py:446-447 /
 // lighgcn_cu_pop.py:488-489, and autograd's SparseAddmmBackward for the same calls.
 //
-// Kernel shape: the path is an HBM/L2-bound gather.  A group of G = d/4 lanes owns one work item
-// (d=64: half a warp, two items per warp; d=128: one warp); every lane keeps one float4 of the
-// output row in registers, column ids/values are fetched coalesced G at a time (the next batch is
-// prefetched while the current one is consumed) and broadcast by shuffle, and the embedding-row
-// gathers are issued UNR at a time before any FMA so that each lane keeps UNR independent 16-byte
-// loads in flight.
-// Work items follow the schedule built by cgx_row_schedule: first the CGX_CHUNK-sized chunks of the
-// rows longer than CGX_LONG_ROW (partials in workspace, summed IN CHUNK ORDER by the chunk that
-// arrives last, or by a finishing kernel for rows above CGX_HUGE_ROW), then all other rows in
-// descending degree order.  Neighbouring groups therefore carry equal work (no idle lanes inside a
-// warp or CTA) and the heavy items start first (no tail).
-// No floating-point atomics anywhere (the only atomic is an integer arrival counter): results are
-// bitwise reproducible.
-// Tuning (profiles/r1_spmm_variants.txt): 8 gathers in flight per lane with the register budget
-// capped for 4 CTAs/SM is within 3 % of the best variant on both the L2-resident C2 shape and the
-// HBM-bound 64M-edge shape; higher unrolls lose occupancy (d=128: 86 registers -> 2 CTAs/SM).
+// Kernel shape: the path is an HBM/L2-bound gather.  A group of G lanes owns one work item and keeps V float4 of the
+// output row per lane (G V = d/4).  Two regimes (cgx_spmm switches on the size of the gathered table,
+// CGX_OPT_L2_TABLE_BYTES):
+//   * table inside L2 (C2, C3; latency-bound): G = d/4 lanes, one float4 each, 8 gathers in flight per lane;
+//   * table beyond L2 (C4, C5; HBM-bound): G = d/8 lanes, 32 contiguous bytes each -- ONE 256-bit access per lane and
+//     row (LDG.E.256 / STG.E.256, new on sm_100) -- 4 gathers in flight, and, when the graph carries hot-row hints
+//     (cgx_hot_hints: bit 31 of a second column-id array marks the columns of the highest-degree rows), per-row L2
+//     eviction priorities: hot rows are loaded evict_last and stay resident, everything else (cold rows, the running
+//     sums, both outputs) goes through evict_first and does not displace them.
+// Column ids / values are fetched coalesced G at a time (the next batch is prefetched while the current one is
+// consumed) and broadcast by shuffle; the gathers of a batch are issued before any FMA.
+// Work items follow the schedule built by cgx_row_schedule: first the CGX_CHUNK-sized chunks of the rows longer than
+// CGX_LONG_ROW (partials in workspace, summed IN CHUNK ORDER by the chunk that arrives last, or by a finishing kernel
+// for rows above CGX_HUGE_ROW), then all other rows in descending degree order; every item is ONE 16-byte descriptor.
+// Neighbouring groups therefore carry equal work and the heavy items start first (no tail).
+// No floating-point atomics anywhere (the only atomic is an integer arrival counter): results are bitwise
+// reproducible, and both regimes / all flag combinations add the same terms in the same order (same bits).
+// Measured history of the kernel: DESIGN.md section 4.1 (profiles/r1_spmm_variants.txt, profiles/r2_ncu_spmm_c4.txt).
 #include "common.cuh"
 
 namespace cgx {
