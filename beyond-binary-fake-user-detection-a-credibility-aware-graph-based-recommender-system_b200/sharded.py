@@ -968,6 +968,12 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
     launches_per_step = lib().cgx_launch_count() - c0
     for s in range(max(args.warmup, 3)):
         step.step(dev_batches[s % len(dev_batches)])
+    clocks = None
+    if rank == 0:                                # nvidia-smi clocks / throttle reasons of rank 0's GPU during the timed steps
+        sys.path.insert(0, str(root))
+        import bench as _bench
+        clocks = _bench.ClockSampler(dev.index if dev.index is not None else 0)
+        clocks.__enter__()
     torch.cuda.synchronize()
     dist.barrier()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
@@ -989,6 +995,8 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
     for s in range(args.steps):
         loss_host = float(step.step(pinned[s % len(pinned)]).item())
     torch.cuda.synchronize()
+    if clocks is not None:
+        clocks.__exit__(None, None, None)
     e2e = torch.tensor([1e3 * (time.perf_counter() - t0)], device=dev)
     dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
     step.check()                                 # no exchange gave up on a peer
@@ -1047,8 +1055,6 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
     tu = torch.tensor([len(train_users)], dtype=torch.int64, device=dev)
     dist.all_reduce(tu, op=dist.ReduceOp.MAX)
     if rank == 0:
-        sys.path.insert(0, str(root))
-        import bench as _bench
         ms = float(total_ms.item()) / args.steps
         e2e_ms = float(e2e.item()) / args.steps
         E = int(edges.item())
@@ -1105,6 +1111,7 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
             },
             "steps_per_epoch": steps_per_epoch, "epoch_ms": ms * steps_per_epoch,
             "epoch_ms_kind": f"extrapolated: {steps_per_epoch} steps x the timed mean step",
+            "clocks": clocks.summary(),
         }
         print(json.dumps(line))
     if n_eval:      # user-sharded full-rank evaluation of the first n_eval users of every shard (second JSON line)
