@@ -545,6 +545,10 @@ class ShardedTrainStep:
         dev = self.ei.device
         I, d = self.ei.shape
         self.max_batch = int(max_batch)
+        # The loss gradient travels compact (rows the batch touched) when the item table is large; for small tables
+        # (C2 shards: 10 MB) one dense exchange of [seed ; L2 gradient ; loss] is cheaper than the ~40 small launches
+        # of packing, gathering and unpacking (C2 x 2: 0.78 vs 1.06 ms per step).
+        self.compact = I * d * 4 >= (64 << 20) if self.force_compact is None else bool(self.force_compact)
         self.ex = None
         if exchange == "auto":
             exchange = self.choose_exchange(graph, I, d, _world(group))
@@ -555,7 +559,7 @@ class ShardedTrainStep:
             # over `group` and raises on ALL ranks together, which then all use the collective exchange.
             # Big tables with short item rows take the NVLS form, which needs the multicast mapping of symmetric memory.
             try:
-                self.ex = P2PExchange((I + _world(group)) * d, dev, group,
+                self.ex = P2PExchange(max((I + _world(group)) * d, 0 if self.compact else 2 * I * d + 4), dev, group,
                                       gather_floats=self._block_floats(self.max_batch, d),
                                       backing="auto" if self.wants_nvls(graph, I, d, _world(group)) else None)
             except _lib.CgxError as e:
@@ -584,6 +588,8 @@ class ShardedTrainStep:
     # the product NVLink-bound there).  Measured on 8 B200s, C5, ms per step: pushed 134.5, pull kernel 97.6, NCCL 85.8,
     # this library's NVLS kernel (inside the CUDA graph) 85.4 -- so the peer-memory exchange stays, in its NVLS form.
     BIG_SHORT_ROWS_EXCHANGE = "p2p"
+
+    force_compact = None        # tests: True / False overrides the size rule of the loss-gradient exchange
 
     @staticmethod
     def wants_nvls(graph, I, d, world) -> bool:
@@ -625,6 +631,8 @@ class ShardedTrainStep:
             pos, neg = (torch.as_tensor(t, device=dev).to(torch.int64) for t in triples)
         bpr_plan(g, users_local, pos, neg, plan)
         f_u, f_i = self.prop.forward(self.eu.data, self.ei.data)
+        if not self.compact:
+            return self._finish_dense(users_local, pos, neg, plan, bufs, f_u, f_i, B_total)
         loss, _, _, ego_rows, ego_coef = bpr_fused(g, f_u, f_i, self.eu.data, self.ei.data, users_local, pos, neg,
                                                    self.reg, 0.0, None, self.g_u, self.gi_local, plan, bufs, B_total)
         with torch.cuda.device(dev):
@@ -686,6 +694,31 @@ class ShardedTrainStep:
         if d_i is None:                                 #  CUDA-graph capture does not allow)
             self.ei.grad.index_fill_(0, flat_c, 0.0)
         return total_loss
+
+    def _finish_dense(self, users_local, pos, neg, plan, bufs, f_u, f_i, B_total):
+        """Loss, adjoint and Adam with ONE dense exchange of [item gradient seed ; item L2 gradient ; loss] -- the
+        small-table form of the step (2 I d + 4 floats through the same exchange as the item tables)."""
+        g, dev = self.graph, self.eu.device
+        n = self.ei.numel()
+        red = self.ex.partial_buffer((2 * n + 4,), dev)
+        gi2 = red[: 2 * n].view(2, *self.ei.shape)
+        self.g_u.zero_()
+        red.zero_()
+        if self._ego_u is None:
+            self._ego_u = torch.zeros_like(self.eu)
+        self._ego_u.zero_()
+        bufs = (red[2 * n: 2 * n + 1],) + tuple(bufs[1:])
+        _, _, _, ego_rows, ego_coef = bpr_fused(g, f_u, f_i, self.eu.data, self.ei.data, users_local, pos, neg,
+                                                self.reg, 0.0, None, self.g_u, gi2[0], plan, bufs, B_total)
+        apply_ego(g, ego_rows, ego_coef, self.eu.data, self.ei.data, self._ego_u, gi2[1])
+        # cloned: the exchange's output region is recycled two exchanges later, the seed is needed by every layer
+        red = self.ex.reduce(red).clone()
+        gi2 = red[: 2 * n].view(2, *self.ei.shape)
+        d_u, d_i = self.prop.backward(self.g_u, gi2[0])
+        self.eu.grad.copy_(d_u.add_(self._ego_u))
+        self.ei.grad.copy_(d_i.add_(gi2[1]))
+        self.opt.step()
+        return red[2 * n: 2 * n + 1]
 
     def capture(self, batch: int):
         """Record the whole sharded step as one CUDA graph.  Only with the peer-memory exchange: every launch
@@ -859,15 +892,23 @@ def parity_vs_single_gpu(rank: int, world: int, dev, variant="v2", order="gs", e
     # Adam's first-moment buffers after one step are 0.1 x the gradients the step used
     if hasattr(ex, "allgather"):         # (every rank of the C1 split owns users and triples; all ranks must take part)
         assert hi > lo and int(mine.sum()) > 0, "parity graph too small for this many ranks"
-        sh = ShardedTrainStep(gl, eu[lo:hi].to(dev), ei.to(dev), K, order, reg_weight=1e-4,
-                              mix_pop=None if variant == "cu" else 0.7, exchange=ex, max_batch=batch)
-        loss2 = sh(ul, batch_total=len(users), triples=(pos[mine], neg[mine]))
         st.opt.step()
-        errs["step_loss"] = abs(float(loss2.item()) - float(want.item())) / abs(float(want.item()))
-        errs["step_m_u"] = rel(sh.opt.m[0], st.opt.m[0][lo:hi])
-        errs["step_m_i"] = rel(sh.opt.m[1], st.opt.m[1])
-        errs["step_g_u_clean"] = float(sh.g_u.abs().max().item() + sh.g_i.abs().max().item()
-                                       + sh.gi_local.abs().max().item() + sh.nz_u.sum().item())
+        for form, compact in (("compact", True), ("dense", False)):
+            ShardedTrainStep.force_compact = compact
+            try:
+                sh = ShardedTrainStep(gl, eu[lo:hi].to(dev), ei.to(dev), K, order, reg_weight=1e-4,
+                                      mix_pop=None if variant == "cu" else 0.7, exchange=ex, max_batch=batch)
+            finally:
+                ShardedTrainStep.force_compact = None
+            if not compact and isinstance(ex, P2PExchange) and ex.region < 4 * (2 * ei.numel() + 4):
+                continue                  # the caller's exchange has no room for the dense form
+            loss2 = sh(ul, batch_total=len(users), triples=(pos[mine], neg[mine]))
+            errs[f"step_{form}_loss"] = abs(float(loss2.item()) - float(want.item())) / abs(float(want.item()))
+            errs[f"step_{form}_m_u"] = rel(sh.opt.m[0], st.opt.m[0][lo:hi])
+            errs[f"step_{form}_m_i"] = rel(sh.opt.m[1], st.opt.m[1])
+            if compact:
+                errs["step_tables_clean"] = float(sh.g_u.abs().max().item() + sh.g_i.abs().max().item()
+                                                  + sh.gi_local.abs().max().item() + sh.nz_u.sum().item())
     worst = torch.tensor([max(errs.values())], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(worst, op=dist.ReduceOp.MAX)
