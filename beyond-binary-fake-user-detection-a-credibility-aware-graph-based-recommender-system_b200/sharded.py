@@ -581,6 +581,7 @@ class ShardedTrainStep:
         self.g_i = torch.zeros_like(self.ei)                 # dL/d(final_i), summed over ranks
         self.owner = torch.full((I + 1,), -1, dtype=torch.int64, device=dev)
         self.tick = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._ego_u = None          # dense form only: user L2 gradient buffer
         self._bufs = {}
         self._graph = None
 
