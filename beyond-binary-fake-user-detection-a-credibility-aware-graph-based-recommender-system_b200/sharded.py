@@ -80,7 +80,7 @@ class CollectiveExchange:
         world = _world(self.group)
         out = torch.empty(world, block.numel(), dtype=block.dtype, device=block.device)
         if world > 1:
-            dist.all_gather_into_tensor(out, block.contiguous(), group=self.group)
+            dist.all_gather_into_tensor(out.view(-1), block.contiguous().view(-1), group=self.group)
         else:
             out[0] = block
         return out
@@ -527,6 +527,58 @@ def build_local_graph(local_edges, num_local_users, num_items, cred_local, varia
                        reduce_item_degrees=lambda d: all_reduce_sum(d, group))
 
 
+# ------------------------------------------------------------------------------------------
+# compact loss gradient of the sharded step: pack / unpack (pure tensor code)
+# ------------------------------------------------------------------------------------------
+def item_gradient_block_floats(B: int, d: int) -> int:
+    """[2B, d] gradient rows | 2B L2 coefficients | 2B row ids (int32 bits) | loss (+ 3 floats of padding)."""
+    return 2 * B * (d + 2) + 4
+
+
+def pack_item_gradient(ego_rows, ego_coef, gi_local, loss, B: int, Bm: int, U: int, d: int) -> torch.Tensor:
+    """One rank's block.  ego_rows int32[3B] / ego_coef float[3B] come from cgx_bpr_fwd_bwd: entry k names the row of
+    the k-th position of the scatter plan when that position starts a run (users < U, items offset by U), else -1; the
+    plan is sorted by row with the B user entries first, so the item runs live in positions [B, 3B).  gi_local [I, d]
+    holds the gradient rows the loss wrote.  Blocks have the size of Bm = max_batch on every rank (ranks may hold
+    different batch sizes): unused slots carry row id -1 and zeros."""
+    dev = gi_local.device
+    er = ego_rows[B:]
+    valid = er >= U
+    rows = torch.where(valid, er - U, torch.zeros_like(er)).to(torch.int64)
+    block = torch.zeros(item_gradient_block_floats(Bm, d), dtype=torch.float32, device=dev)
+    block[: 2 * B * d].view(2 * B, d).copy_(torch.where(valid[:, None], gi_local[rows], 0.0))
+    o_coef, o_rows, o_loss = 2 * Bm * d, 2 * Bm * (d + 1), 2 * Bm * (d + 2)
+    block[o_coef: o_coef + 2 * B] = torch.where(valid, ego_coef[B:], 0.0)   # (non-head slots are uninitialised)
+    rid_local = torch.full((2 * Bm,), -1, dtype=torch.int32, device=dev)
+    rid_local[: 2 * B] = torch.where(valid, rows, torch.full_like(rows, -1)).to(torch.int32)
+    block[o_rows: o_rows + 2 * Bm] = rid_local.view(torch.float32)
+    block[o_loss] = loss.reshape(-1)[0]
+    return block
+
+
+def unpack_item_gradient(blocks: torch.Tensor, Bm: int, d: int, I: int):
+    """blocks [world, n] (rank order) -> (vals [world, 2Bm, d], coef [world, 2Bm], rows [world, 2Bm] with invalid
+    slots mapped to the dummy row I, ok [world, 2Bm], total loss [1])."""
+    world = blocks.shape[0]
+    o_coef, o_rows, o_loss = 2 * Bm * d, 2 * Bm * (d + 1), 2 * Bm * (d + 2)
+    vals = blocks[:, : 2 * Bm * d].reshape(world, 2 * Bm, d)
+    coef = blocks[:, o_coef: o_coef + 2 * Bm]
+    rid = blocks[:, o_rows: o_rows + 2 * Bm].contiguous().view(torch.int32).to(torch.int64)
+    ok = rid >= 0
+    rows_all = torch.where(ok, rid, torch.full_like(rid, I))
+    return vals, coef, rows_all, ok, blocks[:, o_loss].sum().reshape(1)
+
+
+def distinct_rows(rows_all: torch.Tensor, ok: torch.Tensor, owner: torch.Tensor, I: int):
+    """(rows int64[n] clamped to [0, I), keep bool[n]): keep marks ONE slot per distinct valid row (which of the
+    duplicates wins is irrelevant: callers read the row's value from a dense table).  owner: int64[I + 1] scratch."""
+    flat = rows_all.reshape(-1)
+    ar = torch.arange(flat.numel(), device=flat.device)
+    owner.scatter_(0, flat, ar)
+    keep = (owner[flat] == ar) & ok.reshape(-1)
+    return flat.clamp(max=I - 1), keep
+
+
 class ShardedTrainStep:
     """One training step over user shards: local sampling, sharded forward, fused loss on the local
     triples (means over the GLOBAL batch), sharded backward, Adam on (local users, replicated items).
@@ -608,7 +660,7 @@ class ShardedTrainStep:
 
     @staticmethod
     def _block_floats(B: int, d: int) -> int:
-        return 2 * B * (d + 2) + 4            # [2B, d] rows | 2B L2 coefficients | 2B row ids | loss (+ padding)
+        return item_gradient_block_floats(B, d)
 
     @torch.no_grad()
     def __call__(self, users_local: torch.Tensor, batch_total: int | None = None, triples=None):
@@ -639,37 +691,16 @@ class ShardedTrainStep:
         with torch.cuda.device(dev):
             check(lib().cgx_bpr_mark_rows(ptr(ego_rows), ego_rows.numel(), U, ptr(self.nz_u), ptr(self.nz_i_local),
                                           stream_ptr(dev)))
-        # ---- compact item part: the plan is sorted by row, users first, so item runs live in positions [B, 3B).
-        # Blocks have the size of max_batch on every rank (ranks may hold different batch sizes); unused slots carry
-        # row id -1. ----
+        # ---- compact item part (pack -> all-gather -> unpack: pure tensor code, unit-tested on the CPU with gloo) ----
         Bm = self.max_batch
         if B > Bm:
             raise _lib.CgxError(f"ShardedTrainStep: batch of {B} users exceeds max_batch={Bm}")
-        er = ego_rows[B:]
-        valid = er >= U
-        rows = torch.where(valid, er - U, torch.zeros_like(er)).to(torch.int64)
-        block = torch.zeros(self._block_floats(Bm, d), dtype=torch.float32, device=dev)
-        block[: 2 * B * d].view(2 * B, d).copy_(torch.where(valid[:, None], self.gi_local[rows], 0.0))
-        o_coef, o_rows, o_loss = 2 * Bm * d, 2 * Bm * (d + 1), 2 * Bm * (d + 2)
-        block[o_coef: o_coef + 2 * B] = torch.where(valid, ego_coef[B:], 0.0)   # (non-head slots are uninitialised)
-        rid_local = torch.full((2 * Bm,), -1, dtype=torch.int32, device=dev)
-        rid_local[: 2 * B] = torch.where(valid, rows, torch.full_like(rows, -1)).to(torch.int32)
-        block[o_rows: o_rows + 2 * Bm] = rid_local.view(torch.float32)
-        block[o_loss] = loss[0]
+        block = pack_item_gradient(ego_rows, ego_coef, self.gi_local, loss, B, Bm, U, d)
         blocks = self.ex.allgather(block)                                   # [world, n], rank order
-        vals = blocks[:, : 2 * Bm * d].reshape(world, 2 * Bm, d)
-        coef = blocks[:, o_coef: o_coef + 2 * Bm]
-        rid = blocks[:, o_rows: o_rows + 2 * Bm].contiguous().view(torch.int32).to(torch.int64)
-        ok = rid >= 0
-        rows_all = torch.where(ok, rid, torch.full_like(rid, I))            # invalid slots -> the dummy row I
-        total_loss = blocks[:, o_loss].sum().reshape(1)
+        vals, coef, rows_all, ok, total_loss = unpack_item_gradient(blocks, Bm, d, I)
         for r in range(world):                                              # rank order: same bits on every rank
             self.g_i.index_add_(0, rows_all[r].clamp(max=I - 1), torch.where(ok[r][:, None], vals[r], 0.0))
-        flat = rows_all.reshape(-1)
-        ar = torch.arange(flat.numel(), device=dev)
-        self.owner.scatter_(0, flat, ar)                                    # one representative per distinct row
-        keep = (self.owner[flat] == ar) & ok.reshape(-1)
-        flat_c = flat.clamp(max=I - 1)
+        flat_c, keep = distinct_rows(rows_all, ok, self.owner, I)
         d_u, d_i = self.prop.backward(self.g_u, self.g_i, seed_rows=(flat_c, keep), g_u_flags=self.nz_u,
                                       out_u=self.eu.grad)
         if d_u is not self.eu.grad:

@@ -114,3 +114,72 @@ def test_sharded_propagation_matches_single_process_world2():
     for rank, errs in res.items():
         for variant, e in errs.items():
             assert max(e) < 1e-5, (rank, variant, e)
+
+
+def _gather_worker(rank, world, port, out):
+    """Compact loss-gradient exchange of ShardedTrainStep on the CPU: pack -> all-gather (gloo) -> unpack -> rank-order
+    accumulation == an all-reduce of the dense tables; sparse seed addition of the adjoint == the dense addition."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from credgcn.sharded import (CollectiveExchange, ShardedPropagation, distinct_rows, item_gradient_block_floats,
+                                     pack_item_gradient, unpack_item_gradient)
+        U, I, d, Bm = 40, 60, 8, 16
+        B = 16 if rank == 0 else 11                               # ranks may hold different batch sizes
+        rng = np.random.default_rng(100 + rank)
+        # what cgx_bpr_fwd_bwd leaves behind: a plan sorted by row (B user entries, then 2B item entries); ego_rows names
+        # the row at the head of every run and is -1 elsewhere; ego_coef is only written at heads (NaN elsewhere here)
+        items = np.sort(rng.integers(0, I, size=2 * B))
+        head = np.concatenate([[True], items[1:] != items[:-1]])
+        ego_rows = np.full(3 * B, -1, np.int32)
+        ego_rows[:B] = np.arange(B)                               # user part (ignored by the packer)
+        ego_rows[B:][head] = (U + items[head]).astype(np.int32)
+        ego_coef = np.full(3 * B, np.nan, np.float32)
+        ego_coef[B:][head] = rng.random(int(head.sum())).astype(np.float32)
+        gi_local = np.zeros((I, d), np.float32)
+        gi_local[items[head]] = rng.standard_normal((int(head.sum()), d)).astype(np.float32)
+        loss = torch.tensor([0.25 * (rank + 1)])
+        block = pack_item_gradient(torch.from_numpy(ego_rows), torch.from_numpy(ego_coef), torch.from_numpy(gi_local), loss,
+                                   B, Bm, U, d)
+        assert block.numel() == item_gradient_block_floats(Bm, d) and torch.isfinite(block[: 2 * Bm * (d + 1)]).all()
+        blocks = CollectiveExchange().allgather(block)
+        vals, coef, rows_all, ok, total_loss = unpack_item_gradient(blocks, Bm, d, I)
+        assert abs(float(total_loss) - 0.25 * sum(range(1, world + 1))) < 1e-6
+        assert int(ok[rank].sum()) == int(head.sum())
+        seed = torch.zeros(I, d)
+        l2 = torch.zeros(I, d)
+        e0_i = torch.from_numpy(np.random.default_rng(7).standard_normal((I, d)).astype(np.float32))
+        for r in range(world):
+            rr = rows_all[r].clamp(max=I - 1)
+            seed.index_add_(0, rr, torch.where(ok[r][:, None], vals[r], 0.0))
+            l2.index_add_(0, rr, e0_i[rr] * (coef[r] * ok[r])[:, None])
+        # dense truth: all-reduce of the per-rank dense tables
+        want_seed = torch.from_numpy(gi_local.copy())
+        c_dense = np.zeros(I, np.float32)
+        c_dense[items[head]] = ego_coef[B:][head]
+        want_l2 = e0_i * torch.from_numpy(c_dense)[:, None]
+        dist.all_reduce(want_seed)
+        dist.all_reduce(want_l2)
+        err = max(float((seed - want_seed).abs().max()), float((l2 - want_l2).abs().max()))
+        # one representative per distinct row; sparse seed addition == dense addition
+        owner = torch.full((I + 1,), -1, dtype=torch.int64)
+        flat_c, keep = distinct_rows(rows_all, ok, owner, I)
+        touched = torch.unique(rows_all[ok])
+        assert int(keep.sum()) == touched.numel() and set(flat_c[keep].tolist()) == set(touched.tolist())
+        t = torch.from_numpy(np.random.default_rng(9).standard_normal((I, d)).astype(np.float32))
+        sparse = t.clone().index_add_(0, flat_c, seed[flat_c] * keep[:, None])
+        err = max(err, float((sparse - (t + seed)).abs().max()))
+        out[rank] = err
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_compact_loss_gradient_exchange_world2():
+    world = 2
+    port = 29500 + (os.getpid() % 2000) + 7
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_gather_worker, args=(world, port, out), nprocs=world, join=True)
+        res = dict(out)
+    assert set(res) == {0, 1} and max(res.values()) < 1e-6, res
