@@ -16,22 +16,25 @@
 // is therefore identical to CGX_SCORE_FP32.  precision = BF16 is the single-pass variant (K' = d,
 // error ~2^-8 relative, no proof, no redo) for callers that accept approximate ranking.
 //
-// Kernel anatomy (one CTA per 128 users, 13 or 17 warps):
-//   warp 0      TMEM allocation, then one elected lane issues tcgen05.mma (M=128, N=128, K=16 per
+// Kernel anatomy (one CTA per 128 users, 17 warps with two scanning groups, 13 with one):
+//   warp 0      TMEM allocation, then one elected lane (elect.sync) issues tcgen05.mma (M=128, N=128, K=16 per
 //               instruction, K'/16 instructions per item tile), tcgen05.commit -> mbarriers
-//   warps 1-4 (and 5-8 when two epilogue groups are used: group g owns accumulator stage g)
-//               epilogue: tcgen05.ld 32x32b.x16 -> registers, predicated append of scores >= the row
-//               threshold, warp-uniform drain into the row's K' kept candidates (one thread per user)
+//   warps 1-8   epilogue, two groups of four warps (round 2; one group when the lists of two do not fit shared
+//               memory or K > 20): group g scans the item tiles of parity g -- tcgen05.ld 32x32b.x16 -> registers, 16
+//               compares -> hit mask, one select tree + one shared store per hit, warp-uniform drain into the row's
+//               K' kept candidates (one thread per user and group).  The scan is a chain of dependent ALU latencies:
+//               ONE warp per scheduler issued on 23 % of its cycles (profiles/r2_ncu_eval_umma_c2_one_group.txt),
+//               two warps overlap each other's stalls: C2 1.52 -> 1.09 ms, C3 4.21 -> 2.85 ms
+//               (profiles/r2_eval_variants.jsonl), same ids and score bits.
 //   next 4      producer: ONE elected thread issues a TMA tile load (cp.async.bulk.tensor.2d, SWIZZLE_128B tensor
 //               map over the bf16 item operand [I, Kp]; rows past I are zero-filled by the unit) per ring stage:
 //               one 64-column k-block (128 items x 128 B) lands in the canonical K-major SWIZZLE_128B UMMA layout
 //               and completes the stage's mbarrier by transaction bytes -- no register staging, no per-thread
-//               address arithmetic, no proxy fence; the other producer lanes are idle and leave their issue slots
-//               to the epilogue.  The ring (3..8 stages) is k-block granular so that wide tables fit: d = 128 with
-//               BF16X3 needs 64 KB per item tile next to 64 KB of users.  (Round 1 staged the same layout with
-//               128 threads of 16-byte cp.async.)
+//               address arithmetic, no proxy fence.  The ring (3..8 stages) is k-block granular so that wide tables
+//               fit: d = 128 with BF16X3 needs 64 KB per item tile next to 64 KB of users.
 //   last 4      mask builders: per user row, 128 "is a train item" bits per item tile, a few tiles ahead
-// Two 128-column TMEM accumulators: the MMA of tile j+1 overlaps the epilogue of tile j.
+// TMEM: 2 accumulators of 128 columns per scanning group (4 x 128 = all 512 columns with two groups).  Group g owns
+// stages g and g + 2: the MMA of its next tile fills one while it scans the other.
 #include <cuda.h>        // CUtensorMap + the cuTensorMapEncodeTiled prototype (resolved at run time, no -lcuda)
 #include <cuda_bf16.h>
 #include <float.h>
@@ -50,6 +53,7 @@ constexpr int TC_N = 128;          // items per tile
 constexpr int TC_MAX_STAGES = 8;   // B ring: up to 8 stages of one 64-column k-block (128 items x 128 B = 16 KB)
 constexpr int TC_KB_BYTES = TC_N * 128;
 constexpr int TC_MASK_RING = 4;    // train-item bitmasks of that many item tiles are built ahead of the epilogue
+constexpr int TC_MAX_ACC = 4;      // TMEM accumulator stages of 128 columns: two per epilogue group
 constexpr float TC_MASKED = -1e9f;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -76,6 +80,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+// one lane of a converged warp (the form ptxas recognises as "exactly one thread": operands of the tcgen05
+// instructions under it move to uniform registers without a per-operand broadcast loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}"
+      : "=r"(pred));
+  return pred != 0u;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -154,8 +171,8 @@ __global__ void k_tc_convert(const float* __restrict__ src, const int64_t* __res
 
 // ---- the UMMA kernel ---------------------------------------------------------------------------
 // KC kept candidates and BC arrival-buffer slots per (user, epilogue group); NG epilogue groups of 4 warps.
-// With NG = 2 group g drains accumulator stage g (tiles of parity g) into its own list, which doubles the
-// warps that scan scores -- the epilogue, not the MMA, bounds this kernel (d is only 64..128).
+// The epilogue, not the MMA, bounds this kernel (d is only 64..128: 768 tensor-pipe cycles per tile with BF16X3
+// against ~2000 cycles of scanning even when no score enters a list, profiles/r2_eval_ablation_one_group.json).
 template <int KC, int BC, int NG>
 __global__ void __launch_bounds__(32 * (9 + 4 * NG), 1) k_eval_umma(const __grid_constant__ CUtensorMap b_map,   // item operand [I, Kp] bf16
                                                              const __nv_bfloat16* __restrict__ Au,   // [n_users, Kp]
@@ -181,11 +198,16 @@ __global__ void __launch_bounds__(32 * (9 + 4 * NG), 1) k_eval_umma(const __grid
   uint64_t* bars = reinterpret_cast<uint64_t*>(mask_all + TC_MASK_RING * TC_M);
   uint64_t* full_bar = bars;                     // [TC_MAX_STAGES]  producers -> MMA
   uint64_t* empty_bar = bars + TC_MAX_STAGES;    // [TC_MAX_STAGES]  MMA (commit) -> producers
-  uint64_t* tfull_bar = bars + 2 * TC_MAX_STAGES;       // [2]       MMA (commit) -> epilogue
-  uint64_t* tempty_bar = bars + 2 * TC_MAX_STAGES + 2;  // [2]       epilogue -> MMA
-  uint64_t* mfull_bar = bars + 2 * TC_MAX_STAGES + 4;                    // [TC_MASK_RING] mask warps -> epilogue
-  uint64_t* mempty_bar = bars + 2 * TC_MAX_STAGES + 4 + TC_MASK_RING;    // [TC_MASK_RING] epilogue -> mask warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 4 + 2 * TC_MASK_RING);
+  uint64_t* tfull_bar = bars + 2 * TC_MAX_STAGES;                        // [TC_MAX_ACC]  MMA (commit) -> epilogue
+  uint64_t* tempty_bar = bars + 2 * TC_MAX_STAGES + TC_MAX_ACC;          // [TC_MAX_ACC]  epilogue -> MMA
+  uint64_t* mfull_bar = bars + 2 * TC_MAX_STAGES + 2 * TC_MAX_ACC;                   // [TC_MASK_RING] mask warps -> epilogue
+  uint64_t* mempty_bar = bars + 2 * TC_MAX_STAGES + 2 * TC_MAX_ACC + TC_MASK_RING;   // [TC_MASK_RING] epilogue -> mask warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 2 * TC_MAX_ACC + 2 * TC_MASK_RING);
+  // NS accumulator stages of TC_N TMEM columns; tile j lives in stage j % NS.  With two epilogue groups, group g owns
+  // the tiles of parity g and therefore stages g and g + 2: while it scans one of them the MMA of its next tile fills
+  // the other (with one stage per group the group would idle through the issue + execution of its own next tile).
+  constexpr int NS = 2 * NG;
+  static_assert(NS <= TC_MAX_ACC, "accumulator stages");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t u0 = int64_t(blockIdx.x) * TC_M;
@@ -201,13 +223,13 @@ __global__ void __launch_bounds__(32 * (9 + 4 * NG), 1) k_eval_umma(const __grid
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + a, 1); mbar_init(tempty_bar + a, 128); }
+    for (int a = 0; a < TC_MAX_ACC; ++a) { mbar_init(tfull_bar + a, 1); mbar_init(tempty_bar + a, 128); }
     for (int m = 0; m < TC_MASK_RING; ++m) { mbar_init(mfull_bar + m, 128); mbar_init(mempty_bar + m, 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(256));
+                 "r"(NS * TC_N));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   // A tile: this CTA's 128 users, staged once by every thread (rows past n_users are zero)
@@ -230,27 +252,31 @@ __global__ void __launch_bounds__(32 * (9 + 4 * NG), 1) k_eval_umma(const __grid
     const uint32_t a_addr = smem_u32(smem_a);
     int s = 0;                                      // ring position and its phase bit, advanced without dividing
     uint32_t ph = 0;
+    // The leader comes from elect.sync (ptxas then knows that exactly one thread runs the block and moves the
+    // descriptors to uniform registers directly; under `lane == 0` every tcgen05.mma was wrapped in a broadcast loop:
+    // 175 instructions per k-block against 95, and the issuing warp was busy for half of a tile period), and the
+    // descriptors are one base each plus (byte offset >> 4): the address field holds (addr & 0x3FFFF) >> 4 and every
+    // operand lies below 256 KB, so the sum never carries out of the field.
+    const uint64_t a_desc0 = umma_desc_sw128(a_addr);
+    const uint64_t b_desc0 = umma_desc_sw128(smem_u32(smem_b));
     for (int j = 0; j < n_tiles; ++j) {
-      const int a = j & 1;
-      mbar_wait(tempty_bar + a, ((j >> 1) & 1) ^ 1);
+      const int a = j & (NS - 1);
+      mbar_wait(tempty_bar + a, ((j / NS) & 1) ^ 1);
       for (int u = 0; u < n_units; ++u) {
         mbar_wait(full_bar + s, ph);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t b_addr = smem_u32(smem_b + s * TC_KB_BYTES);
+        if (elect_one()) {
+          const uint64_t bd = b_desc0 + uint64_t(uint32_t(s * TC_KB_BYTES) >> 4);
           const int ka = u < nkb ? u : u - nkb;                       // a_hi k-block paired with this unit
+          const uint64_t ad = a_desc0 + uint64_t(uint32_t(ka * (TC_M * 128)) >> 4);
           if (!(dbg & 2)) {
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              umma_bf16(tmem_base + a * TC_N, umma_desc_sw128(a_addr + ka * (TC_M * 128) + k4 * 32),
-                        umma_desc_sw128(b_addr + k4 * 32), idesc, (u | k4) ? 1u : 0u);
-            }
+            for (int k4 = 0; k4 < 4; ++k4)   // a K = 16 step inside a k-block: + 32 bytes
+              umma_bf16(tmem_base + a * TC_N, ad + 2 * k4, bd + 2 * k4, idesc, (u | k4) ? 1u : 0u);
             if (u < nkb && n_units > nkb) {                           // BF16X3: a_lo[u] . b_hi[u]
+              const uint64_t al = a_desc0 + uint64_t(uint32_t((nkb + u) * (TC_M * 128)) >> 4);
 #pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4) {
-                umma_bf16(tmem_base + a * TC_N, umma_desc_sw128(a_addr + (nkb + u) * (TC_M * 128) + k4 * 32),
-                          umma_desc_sw128(b_addr + k4 * 32), idesc, 1u);
-              }
+              for (int k4 = 0; k4 < 4; ++k4) umma_bf16(tmem_base + a * TC_N, al + 2 * k4, bd + 2 * k4, idesc, 1u);
             }
           }
           umma_commit(empty_bar + s);                   // ring stage reusable once these MMAs have read it
@@ -343,7 +369,7 @@ __global__ void __launch_bounds__(32 * (9 + 4 * NG), 1) k_eval_umma(const __grid
           list_s[weakest * TC_M + row] = sc;
           list_i[weakest * TC_M + row] = item;
           // new weakest: KC independent loads, then a min tree of depth log2(KC) (a sequential scan would be a
-          // chain of KC dependent compare+select steps, and this warp is alone on its scheduler)
+          // chain of KC dependent compare+select steps)
           float mv[KC];
           int ms[KC];
 #pragma unroll
@@ -365,8 +391,8 @@ __global__ void __launch_bounds__(32 * (9 + 4 * NG), 1) k_eval_umma(const __grid
     };
 
     for (int j = grp; j < n_tiles; j += NG) {
-      const int a = j & 1;
-      mbar_wait(tfull_bar + a, (j >> 1) & 1);
+      const int a = j & (NS - 1);
+      mbar_wait(tfull_bar + a, (j / NS) & 1);
       tc_fence_after();
       const int32_t i0 = j * TC_N;
       const int valid = I - i0 < TC_N ? I - i0 : TC_N;   // columns of this tile that are real items
@@ -392,7 +418,9 @@ __global__ void __launch_bounds__(32 * (9 + 4 * NG), 1) k_eval_umma(const __grid
         if (dbg & 1) hit = 0;
         // one hit per lane per pass (a warp sees ~3 hits per chunk early on, < 1 later): the passes are
         // warp-uniform, and a hit costs a 16 -> 1 select tree instead of 16 predicated store sequences
-        while (__any_sync(0xffffffffu, hit != 0u)) {
+        bool any_hit = __any_sync(0xffffffffu, hit != 0u);
+        const bool had_hits = any_hit;
+        while (any_hit) {
           if (hit != 0u) {
             const int q = __ffs(hit) - 1;
             hit &= hit - 1u;
@@ -405,8 +433,10 @@ __global__ void __launch_bounds__(32 * (9 + 4 * NG), 1) k_eval_umma(const __grid
             wr0[cnt * TC_M] = make_uint2(__float_as_uint((q & 8) ? s2b : s2a), uint32_t(i0 + ch * 16 + q));
             ++cnt;
           }
+          any_hit = __any_sync(0xffffffffu, hit != 0u);
         }
-        if (__any_sync(0xffffffffu, cnt > BC - 16)) {
+        // the buffers only grow in a chunk with hits: with two groups the overflow vote is skipped otherwise
+        if ((NG == 1 || had_hits) && __any_sync(0xffffffffu, cnt > BC - 16)) {
           if (dbg & 8) cnt = 0; else drain();
         }
         if (ch + 1 < TC_N / 16) tmem_wait_ld();
@@ -427,7 +457,7 @@ __global__ void __launch_bounds__(32 * (9 + 4 * NG), 1) k_eval_umma(const __grid
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(NS * TC_N));
   }
 }
 
@@ -600,24 +630,33 @@ __global__ void __launch_bounds__(ER_THREADS) k_eval_redo_rows(const int64_t* __
 struct TcConfig {
   int KC, BC, NG, stride;   // stride = candidates per user handed to k_rescore (32 or 64)
 };
-static TcConfig tc_config(int32_t K, int precision) {
-  // Measured and rejected in round 1 (no longer compiled): two epilogue groups (24, 16, 2, 64) -- SLOWER on C2
-  // (3.69 vs 3.19 ms): each group keeps its own, weaker threshold, so more scores reach the merge code; K' = 24
-  // (margin 4) -- 4 % faster on C2, but on C3 the completeness proof fails for enough rows that the exact redo
-  // doubles the time (10.9 vs 5.7 ms).
-  (void)precision;
-  if (K + 12 <= 32) return {32, 32, 1, 32};
-  return {64, 16, 1, 64};
-}
+constexpr int TC_DEFAULT_GROUPS = 2;   // what CGX_OPT_EVAL_GROUPS = 0 selects
 // shared memory with a ring of S k-blocks; tc_stages picks the deepest ring that fits (0: the shape does not fit)
 static size_t tc_smem(const TcConfig& c, int Kp, int S) {
   return size_t(TC_M) * Kp * 2 + size_t(S) * TC_KB_BYTES + size_t(c.NG) * (c.KC + c.BC) * TC_M * 8 +
-         size_t(TC_MASK_RING) * TC_M * 16 + 256 + 1024;
+         size_t(TC_MASK_RING) * TC_M * 16 + 512 + 1024;
 }
 static int tc_stages(const TcConfig& c, int Kp) {
   for (int S = TC_MAX_STAGES; S >= 3; --S)
     if (tc_smem(c, Kp, S) <= 227 * 1024) return S;
   return 0;
+}
+static TcConfig tc_config(int32_t K, int Kp) {
+  // Measured and rejected in round 1 (no longer compiled): K' = 24 with ONE list (margin 4) -- 4 % faster on C2, but
+  // on C3 the completeness proof fails for enough rows that the exact redo doubles the time (10.9 vs 5.7 ms).
+  // Two epilogue groups (CGX_OPT_EVAL_GROUPS = 2): group g scans the item tiles of parity g into its own K' = 24
+  // list, eight scanning warps instead of four -- the scan is a chain of dependent ALU latencies, one warp per
+  // scheduler issues on 23 % of its cycles (profiles/r2_ncu_eval_umma_c2.txt).  The proof compares the K-th exact
+  // score with the LARGER of the two lists' weakest entries, each about the 48th best of the catalogue, so it
+  // holds more often than with one list of 32.  Needs four accumulator stages (see the kernel) and 64 candidates
+  // per user in k_rescore.
+  if (K + 12 <= 32) {
+    const TcConfig two{24, 24, 2, 64};
+    const int64_t groups = option(CGX_OPT_EVAL_GROUPS);
+    if ((groups == 0 ? TC_DEFAULT_GROUPS : groups) == 2 && K + 4 <= 24 && tc_stages(two, Kp) > 0) return two;
+    return {32, 32, 1, 32};
+  }
+  return {64, 16, 1, 64};
 }
 static int tc_parts(int precision) { return precision == CGX_SCORE_BF16X3 ? 2 : 1; }   // stored parts: [hi | lo]
 static int tc_dp(int32_t d) { return (d + 63) / 64 * 64; }
@@ -630,7 +669,8 @@ size_t eval_topk_tc_workspace(int64_t n_users, int32_t I, int32_t d, int32_t K, 
 
 static bool tc_supported(int32_t d, int32_t K, int precision) {
   if (K + 12 > 64) return false;
-  return tc_stages(tc_config(K, precision), tc_parts(precision) * tc_dp(d)) > 0;
+  const int Kp = tc_parts(precision) * tc_dp(d);
+  return tc_stages(tc_config(K, Kp), Kp) > 0;
 }
 
 // Tensor map of the bf16 item operand [I rows, Kp columns], box = one ring stage (64 columns x 128 rows), 128-byte
@@ -695,7 +735,7 @@ int eval_topk_tc(const int64_t* users, int64_t n_users, const float* f_u, const 
   CGX_REQUIRE(workspace_bytes >= eval_topk_tc_workspace(n_users, I, d, K, precision), CGX_ERR_WORKSPACE,
               "eval_topk: workspace too small");
   const int Kp = parts * Dp, nkb = Dp / 64;
-  const TcConfig cfg = tc_config(K, precision);
+  const TcConfig cfg = tc_config(K, Kp);
   Arena ws(workspace, workspace_bytes);
   __nv_bfloat16* Au = ws.take<__nv_bfloat16>(size_t(n_users) * Kp);
   __nv_bfloat16* Bi = ws.take<__nv_bfloat16>(size_t(I) * Kp);
@@ -716,7 +756,9 @@ int eval_topk_tc(const int64_t* users, int64_t n_users, const float* f_u, const 
   int32_t* n_redo = reinterpret_cast<int32_t*>(scal + 1);
 #define CGX_TC_ARGS Au, Bi, users, n_users, f_u, f_i, I, d, Kp, nkb, tr_indptr, tr_idx, K, cand, thr, unorm, scal, eps_rel, \
                     out_ids, out_scores, redo_rows, n_redo, stream
-  if (cfg.KC == 32) {
+  if (cfg.NG == 2) {
+    CGX_TRY((tc_launch<24, 24, 2, 64>(CGX_TC_ARGS)));
+  } else if (cfg.KC == 32) {
     CGX_TRY((tc_launch<32, 32, 1, 32>(CGX_TC_ARGS)));
   } else {
     CGX_TRY((tc_launch<64, 16, 1, 64>(CGX_TC_ARGS)));

@@ -68,7 +68,8 @@ typedef enum {
   CGX_OPT_P2P_TIMEOUT_MS = 5,        /* [20000] a cross-GPU barrier that waits longer gives up (cgx_comm_status) */
   CGX_OPT_EVAL_DEBUG = 6,            /* [0] bit 0: cgx_eval_topk prints the redo-row count (synchronises) */
   CGX_OPT_HOT_ROWS = 7,              /* [1] cgx_spmm uses the hot-row hints of cgx_csr.idx_hint when present */
-  CGX_OPT_COUNT_ = 8
+  CGX_OPT_EVAL_GROUPS = 8,           /* [0] scanning warp groups of the tensor-core cgx_eval_topk: 0 = library choice, 1, 2 */
+  CGX_OPT_COUNT_ = 9
 } cgx_option;
 int cgx_set_option(int option, int64_t value, int64_t* previous);
 int64_t cgx_get_option(int option);
