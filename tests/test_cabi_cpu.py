@@ -37,6 +37,30 @@ def test_version_and_dim_table():
     assert lib.cgx_graph_build_workspace_bytes(1000, 10, 10) > 3 * 8 * 1000
 
 
+def test_options_table_and_eval_kernel_selection():
+    """Every option of the header's enum is reachable by name from the binding, and the shape -> kernel decision of
+    the evaluation (a host-side function, no launch) holds under both scanning-group settings: d <= 128 runs on the
+    tensor cores with BF16X3, d = 256 only with the single-pass BF16 operand (shared-memory fit)."""
+    from credgcn import _lib
+    text = (ROOT / "include" / "credgcn.h").read_text()
+    enum = dict(re.findall(r"^\s+CGX_OPT_([A-Z0-9_]+?)_? = (\d+)", text, flags=re.M))      # the enum's own lines
+    count = int(enum.pop("COUNT"))
+    assert {k: int(v) for k, v in enum.items()} == _lib.OPTIONS and count == len(_lib.OPTIONS)
+    lib = _lib.lib()
+    assert lib.cgx_get_option(count) == -1
+    keep = _lib.get_option("EVAL_GROUPS")
+    try:
+        for groups in (0, 1, 2):
+            _lib.set_option("EVAL_GROUPS", groups)
+            x3, b = _lib.PRECISIONS["bf16x3"], _lib.PRECISIONS["bf16"]
+            assert [lib.cgx_eval_topk_uses_tensor_cores(d, 20, x3) for d in (16, 64, 128, 256)] == [1, 1, 1, 0]
+            assert lib.cgx_eval_topk_uses_tensor_cores(256, 20, b) == 1
+            assert lib.cgx_eval_topk_uses_tensor_cores(64, 40, x3) == 1 and lib.cgx_eval_topk_uses_tensor_cores(64, 60, x3) == 0
+            assert lib.cgx_eval_topk_uses_tensor_cores(64, 20, _lib.PRECISIONS["fp32"]) == 0
+    finally:
+        _lib.set_option("EVAL_GROUPS", keep)
+
+
 def test_struct_layout_matches_header():
     from credgcn._lib import CsrStruct
     # int32,int32,int64, 5 pointers (indptr, idx, val_fwd, val_bwd, perm), int32,int32, 2 pointers, int32,int32,

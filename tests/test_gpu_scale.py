@@ -173,3 +173,28 @@ def test_spmm_forms_give_identical_bits(cg, d):
             lib.set_option(k, v)
         gr.by_user.set_hot_columns(gr.by_item.perm, 0)
         gr.by_item.set_hot_columns(gr.by_user.perm, 0)
+
+
+def test_eval_scanning_groups_give_identical_results(cg):
+    """CGX_OPT_EVAL_GROUPS: the tensor-core evaluation kernel with one scanning warp group (one list of 32 candidates
+    per user) and with two (two lists of 24 over four TMEM accumulators, the default) must both return what the fp32
+    kernel returns -- same ids, same score bits -- with exact score ties across many items and masked train items."""
+    lib, ev = cg["lib"], cg["evaluate"]
+    U, I, d = 700, 9000, 64
+    sg = cg["synth"].make_graph("C1", num_users=U, num_items=I, num_edges=60_000)
+    rng = np.random.default_rng(11)
+    fu = torch.tensor((rng.standard_normal((U, d)) * 0.2).astype(np.float32), device=DEV)
+    fi = torch.tensor((rng.standard_normal((I, d)) * 0.2).astype(np.float32), device=DEV)
+    fi[::7] = fi[3]
+    csr = ev._device_csr(orc.edges_to_user_csr(sg.train_edges, U), DEV)
+    users = torch.arange(0, U, 2)
+    ids0, sc0 = ev.topk_device(fu, fi, users, csr, 20, "fp32")
+    keep = lib.get_option("EVAL_GROUPS")
+    try:
+        for groups in (1, 2):
+            lib.set_option("EVAL_GROUPS", groups)
+            ids1, sc1 = ev.topk_device(fu, fi, users, csr, 20, "bf16x3")
+            assert torch.equal(ids0, ids1), (groups, int((ids0 != ids1).sum()))
+            assert torch.equal(sc0, sc1), groups
+    finally:
+        lib.set_option("EVAL_GROUPS", keep)
