@@ -1,4 +1,4 @@
-"""Host-side logic of the user-sharded path on CPU: world_size-2 gloo process group, with an
+"""Host-side logic of the user-sharded path on CPU: world_size-2 and -4 gloo process groups, with an
 oracle-backed stand-in for the two per-shard products (the product backend is CUDA only).
 Checks that the sharded forward / adjoint schedules with their all-reduces reproduce the
 single-process oracle, for both layer orders."""
@@ -102,15 +102,15 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.timeout(180)
-def test_sharded_propagation_matches_single_process_world2():
-    world = 2
-    port = 29500 + (os.getpid() % 2000)
+@pytest.mark.timeout(240)
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_propagation_matches_single_process(world):
+    port = 29500 + (os.getpid() % 2000) + 11 * world
     with mp.Manager() as mgr:
         out = mgr.dict()
         mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
         res = dict(out)
-    assert set(res) == {0, 1}
+    assert set(res) == set(range(world))
     for rank, errs in res.items():
         for variant, e in errs.items():
             assert max(e) < 1e-5, (rank, variant, e)
@@ -174,12 +174,12 @@ def _gather_worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.timeout(180)
-def test_compact_loss_gradient_exchange_world2():
-    world = 2
-    port = 29500 + (os.getpid() % 2000) + 7
+@pytest.mark.timeout(240)
+@pytest.mark.parametrize("world", [2, 4])
+def test_compact_loss_gradient_exchange(world):
+    port = 29500 + (os.getpid() % 2000) + 7 + 11 * world
     with mp.Manager() as mgr:
         out = mgr.dict()
         mp.spawn(_gather_worker, args=(world, port, out), nprocs=world, join=True)
         res = dict(out)
-    assert set(res) == {0, 1} and max(res.values()) < 1e-6, res
+    assert set(res) == set(range(world)) and max(res.values()) < 1e-6, res
