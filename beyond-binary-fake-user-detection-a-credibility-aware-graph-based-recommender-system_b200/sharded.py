@@ -103,7 +103,7 @@ class P2PExchange:
 
     # Backing of the communication buffers: "ipc" = cudaMalloc + cudaIpc handles; "symm" / "auto" = torch symmetric
     # memory (peer mappings + the NVSwitch multicast mapping the NVLS form needs), falling back to "ipc" when any rank
-    # cannot.  CGX_P2P_BACKING overrides the default.
+    # cannot.  (The classes read no environment; `bench.py --gpus N` maps its experiment switches onto these attributes.)
     DEFAULT_BACKING = "ipc"
 
     def __init__(self, max_floats: int, device, group=None, gather_floats: int = 0, backing: str | None = None):
@@ -113,7 +113,7 @@ class P2PExchange:
         its own CUDA calls succeed (a failure is agreed on after each phase and raised on all ranks together), so a
         rank without peer access can never leave the others waiting inside a mismatched collective."""
         import ctypes as C
-        backing = backing or os.environ.get("CGX_P2P_BACKING", self.DEFAULT_BACKING)
+        backing = backing or self.DEFAULT_BACKING
         self.group, self.device = group, torch.device(device)
         self.world = _world(group)
         self.rank = dist.get_rank(group) if self.world > 1 else 0
@@ -265,12 +265,11 @@ class P2PExchange:
         """Fused SpMM -> owner push + local reduce (cgx_spmm_push / cgx_comm_allreduce_pushed): the default above
         2 ranks (C2 shards, 4 ranks: 0.896 vs 0.975 ms/step) and for tables of 64 MB and more at any rank count (the
         reduce-scatter half then hides under the product).  At 2 ranks and 10 MB tables the one-shot pull kernel has
-        one barrier less and wins (0.793 vs 0.812 ms).  force_push / CGX_P2P_PUSH=1 / 0 force it on / off."""
+        one barrier less and wins (0.793 vs 0.812 ms).  force_push = True / False forces it on / off."""
+        if self.world < 2:
+            return False
         if self.force_push is not None:
-            return self.world > 1 and bool(self.force_push)
-        env = os.environ.get("CGX_P2P_PUSH")
-        if env is not None or self.world < 2:
-            return self.world > 1 and env == "1"
+            return bool(self.force_push)
         if self.region < (64 << 20):                # small tables: latency-bound exchange
             return self.world > 2
         # large tables: pushing pays while the product is long next to the table it produces -- its posted stores
@@ -279,7 +278,7 @@ class P2PExchange:
         # NVLink-bound (134.5 ms per step pushed vs 97.6 pulled vs 85.8 NCCL at 8 ranks).
         return avg_row_nnz is None or avg_row_nnz >= 32
 
-    force_push = None       # True / False overrides the default choice (tests)
+    force_push = None       # True / False overrides the default choice (tests, bench experiments)
 
     def exchange_pushed(self, shape, push_product):
         """One item-table exchange in pushed form.  `push_product(stage_off, rank, world, rows_per)` must launch the
@@ -313,7 +312,7 @@ class P2PExchange:
         out = self.bytes[self.gather_off: self.gather_off + self.world * nbytes].view(torch.float32)
         return out.view(self.world, nbytes // 4)[:, : block.numel()]
 
-    use_nvls = None         # None: automatic (below); True / False force it on / off (CGX_P2P_NVLS=1 / 0 likewise)
+    use_nvls = None         # None: automatic (below); True / False force it on / off
 
     def nvls_enabled(self, nbytes: int) -> bool:
         """NVLS form of reduce(): needs the multicast mapping.  Automatic choice: tables of 64 MB and more on 4+
@@ -323,9 +322,6 @@ class P2PExchange:
             return False
         if self.use_nvls is not None:
             return bool(self.use_nvls)
-        env = os.environ.get("CGX_P2P_NVLS")
-        if env is not None:
-            return env == "1"
         return self.world >= 4 and nbytes >= (64 << 20)
 
     def reduce(self, buf):
@@ -958,7 +954,15 @@ def bench_main(args, rank: int, world: int, dev: torch.device):
     name = args.workload or "C4"
     shp = synth.SHAPES[name]
     strong = name == "C5"
+    # experiment switches of this benchmark command (the classes themselves read no environment):
+    #   CGX_EXCHANGE=auto|p2p|nccl, CGX_P2P_BACKING=ipc|symm|auto, CGX_P2P_PUSH=0|1, CGX_P2P_NVLS=0|1
     ex_kind = os.environ.get("CGX_EXCHANGE", "auto")
+    if "CGX_P2P_BACKING" in os.environ:
+        P2PExchange.DEFAULT_BACKING = os.environ["CGX_P2P_BACKING"]
+    if "CGX_P2P_PUSH" in os.environ:
+        P2PExchange.force_push = os.environ["CGX_P2P_PUSH"] == "1"
+    if "CGX_P2P_NVLS" in os.environ:
+        P2PExchange.use_nvls = os.environ["CGX_P2P_NVLS"] == "1"
 
     # ---- parity of this very exchange against the single-GPU path, before anything is timed ----
     par_ex = None

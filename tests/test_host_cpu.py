@@ -144,11 +144,15 @@ def test_exchange_selection_rules():
         e.world, e.region, e.mc, e.force_push, e.use_nvls = world, region_mb << 20, mc, None, None
         return e
 
+    # small tables: pull at 2 ranks, pushed above -- whatever the environment says (the classes read none; only the
+    # benchmark command maps its experiment switches onto force_push / use_nvls / DEFAULT_BACKING)
     import os
-    os.environ.pop("CGX_P2P_PUSH", None)
-    os.environ.pop("CGX_P2P_NVLS", None)
-    # small tables: pull at 2 ranks, pushed above
-    assert not ex(2, 10).push_enabled(33) and ex(4, 10).push_enabled(33)
+    os.environ["CGX_P2P_PUSH"], os.environ["CGX_P2P_NVLS"] = "1", "1"
+    try:
+        assert not ex(2, 10).push_enabled(33) and ex(4, 10).push_enabled(33)
+        assert not ex(2, 2560).nvls_enabled(2560 << 20)
+    finally:
+        del os.environ["CGX_P2P_PUSH"], os.environ["CGX_P2P_NVLS"]
     # large tables: pushed while the item rows are long (C4 shards: 80 per row), not for short rows (C5 shards: 10)
     assert ex(2, 1024).push_enabled(80) and ex(8, 1024).push_enabled(80) and not ex(8, 2560).push_enabled(10)
     assert ex(8, 2560).push_enabled(None)                              # unknown row length: the old default
