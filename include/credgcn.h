@@ -66,7 +66,9 @@ typedef enum {
   CGX_OPT_P2P_ONESHOT_MAX = 3,       /* [2] cgx_comm_allreduce uses the one-shot form up to this many ranks */
   CGX_OPT_P2P_TIMING = 4,            /* [0] accumulate in-kernel phase times for cgx_comm_timing */
   CGX_OPT_P2P_TIMEOUT_MS = 5,        /* [20000] a cross-GPU barrier that waits longer gives up (cgx_comm_status) */
-  CGX_OPT_EVAL_DEBUG = 6,            /* [0] bit 0: cgx_eval_topk prints the redo-row count (synchronises) */
+  CGX_OPT_EVAL_DEBUG = 6,            /* [0] diagnostics of cgx_eval_topk.  bit 0: print the redo-row count (synchronises);
+                                        bits 1-4 switch parts of the tensor-core kernel off for timing (no list
+                                        insertions / no MMAs / no TMA loads / no merges): WRONG RESULTS, profiles/eval_ablate.py */
   CGX_OPT_HOT_ROWS = 7,              /* [1] cgx_spmm uses the hot-row hints of cgx_csr.idx_hint when present */
   CGX_OPT_EVAL_GROUPS = 8,           /* [0] scanning warp groups of the tensor-core cgx_eval_topk: 0 = library choice, 1, 2 */
   CGX_OPT_COUNT_ = 9
