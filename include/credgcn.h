@@ -56,7 +56,8 @@ uint64_t cgx_launch_count(void);
 /* Supported embedding widths: 16, 32, 64, 128, 256 (reference default emb_dim = 64, CU:53). */
 int cgx_emb_dim_supported(int32_t d);
 
-/* Process-wide tuning options (defaults in brackets).  None of them changes a result bit: tests force both sides.
+/* Process-wide tuning options (defaults in brackets).  None of them changes a result bit (tests force both sides),
+ * the diagnostic bits 1-4 of CGX_OPT_EVAL_DEBUG excepted.
  * cgx_set_option stores `value` (negative = restore the default) and returns the previous one through
  * `previous` (nullable); cgx_get_option returns -1 for an unknown option. */
 typedef enum {
