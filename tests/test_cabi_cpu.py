@@ -61,6 +61,24 @@ def test_options_table_and_eval_kernel_selection():
         _lib.set_option("EVAL_GROUPS", keep)
 
 
+def test_sass_carries_the_blackwell_instructions():
+    """The shipped library is sm_100a code that uses what DESIGN.md says it uses: tcgen05 MMAs with TMEM loads and
+    commits, TMA tile loads, 256-bit gathers with L2 eviction priorities, the in-switch reduction of the NVLS exchange,
+    programmatic dependent launch (profiles/sass_evidence.py; profiles/r2_sass_evidence.txt holds the counts)."""
+    import shutil
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sys.path.insert(0, str(ROOT / "profiles"))
+    try:
+        import sass_evidence
+    finally:
+        sys.path.pop(0)
+    from credgcn import _lib
+    got = sass_evidence.counts(_lib.LIB_PATH)
+    assert all(n > 0 for n in got.values()), got
+
+
 def test_struct_layout_matches_header():
     from credgcn._lib import CsrStruct
     # int32,int32,int64, 5 pointers (indptr, idx, val_fwd, val_bwd, perm), int32,int32, 2 pointers, int32,int32,
